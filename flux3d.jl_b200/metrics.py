@@ -1,0 +1,116 @@
+"""chamfer_distance / laplacian_loss / edge_loss — host-side mirror of src/metrics/{pcloud,mesh}.jl.
+
+Same names, argument meaning and error behaviour as the reference; all arithmetic happens in
+libflux3d_b200.so (hand-written sm_100a kernels) through the C ABI.  No CPU / PyTorch fallback."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .pcloud import PointCloud, as_f32_tensor
+
+FLAG_NONE = 0
+FLAG_FMA = 1  # non-reference arithmetic (fused multiply-add distances); see include/flux3d_b200.h
+
+_ws_cache: dict = {}
+
+
+def _workspace(key, nbytes: int, device) -> torch.Tensor:
+    """Caller-owned workspace, cached per (op, shape, device, stream) like CUDA.jl would cache a CuArray."""
+    k = (key, str(device), torch.cuda.current_stream(device).cuda_stream)
+    t = _ws_cache.get(k)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _ws_cache[k] = t
+    return t
+
+
+def _stream_ptr(device):
+    import ctypes
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def chamfer_forward_raw(A: torch.Tensor, B: torch.Tensor, w1: float, w2: float, *, batch_total: int = 0,
+                        want_indices: bool = True, flags: int = FLAG_NONE, out=None):
+    """One call of f3d_chamfer_fwd on device tensors A (B,N,3), B (B,M,3).
+    Returns (loss[1], terms[2], nnA (B,N) | None, nnB (B,M) | None) — all device tensors, no sync."""
+    L = _lib.lib()
+    if not (A.is_cuda and B.is_cuda):
+        raise _lib.Flux3DB200Error("chamfer_forward_raw needs CUDA tensors (there is no CPU path)")
+    if A.dim() != 3 or B.dim() != 3 or A.shape[2] != 3 or B.shape[2] != 3:
+        raise ValueError("expected (B, N, 3) and (B, M, 3) point arrays")
+    if A.shape[0] != B.shape[0]:
+        raise ValueError(f"batch sizes differ: {A.shape[0]} vs {B.shape[0]}")
+    Bn, N, M = A.shape[0], A.shape[1], B.shape[1]
+    dev = A.device
+    with torch.cuda.device(dev):
+        ws = _workspace(("chamfer", Bn, N, M), L.f3d_chamfer_workspace_bytes(Bn, N, M), dev)
+        if out is None:
+            res = torch.empty(3, dtype=torch.float32, device=dev)
+            nnA = torch.empty((Bn, N), dtype=torch.int32, device=dev) if want_indices else None
+            nnB = torch.empty((Bn, M), dtype=torch.int32, device=dev) if want_indices else None
+        else:
+            res, nnA, nnB = out
+        loss, terms = res[0:1], res[1:3]
+        _lib.check(L.f3d_chamfer_fwd(_lib.ptr(A), _lib.ptr(B), Bn, N, M, w1, w2, batch_total,
+                                     _lib.ptr(loss), _lib.ptr(terms), _lib.ptr(nnA), _lib.ptr(nnB),
+                                     _lib.ptr(ws), ws.numel(), flags, _stream_ptr(dev)))
+    return loss, terms, nnA, nnB
+
+
+class _ChamferFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A, B, w1, w2, batch_total, flags):
+        loss, _, nnA, nnB = chamfer_forward_raw(A, B, w1, w2, batch_total=batch_total, flags=flags)
+        ctx.save_for_backward(A, B, nnA, nnB)
+        ctx.cfg = (w1, w2, batch_total)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        A, B, nnA, nnB = ctx.saved_tensors
+        w1, w2, batch_total = ctx.cfg
+        L = _lib.lib()
+        gA = torch.empty_like(A)
+        gB = torch.empty_like(B)
+        g = gout.to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(A.device):
+            _lib.check(L.f3d_chamfer_bwd(_lib.ptr(A), _lib.ptr(B), A.shape[0], A.shape[1], B.shape[1], w1, w2,
+                                         batch_total, _lib.ptr(nnA), _lib.ptr(nnB), _lib.ptr(g), _lib.ptr(gA),
+                                         _lib.ptr(gB), _stream_ptr(A.device)))
+        return gA, gB, None, None, None, None
+
+
+def chamfer_distance(A, B, num_samples: int = 5000, *, w1: float = 1.0, w2: float = 1.0,
+                     flags: int = FLAG_NONE, batch_total: int = 0, device="cuda"):
+    """chamfer_distance(A, B; w1=1.0, w2=1.0) — src/metrics/pcloud.jl:11-37; for two TriMesh arguments,
+    chamfer_distance(m1, m2, num_samples=5000; w1, w2) — src/metrics/mesh.jl:34-44.
+
+    A, B: PointCloud, or arrays/tensors of shape (N,3) / (B,N,3) (== Julia (3,N) / (3,N,B)).  Host inputs
+    are copied to ``device``.  Returns a 0-dim float32 CUDA tensor (differentiable w.r.t. A and B)."""
+    from .mesh import TriMesh  # local import: mesh.py imports this module's helpers
+    if isinstance(A, TriMesh) and isinstance(B, TriMesh):
+        from .sampling import sample_points
+        A = sample_points(A, num_samples)
+        B = sample_points(B, num_samples)
+    if isinstance(A, PointCloud):
+        A = A.points
+    if isinstance(B, PointCloud):
+        B = B.points
+    A = as_f32_tensor(A, None if (isinstance(A, torch.Tensor) and A.is_cuda) else device)
+    B = as_f32_tensor(B, A.device)
+    if A.dim() == 2:
+        A = A.unsqueeze(0)
+    if B.dim() == 2:
+        B = B.unsqueeze(0)
+    return _ChamferFn.apply(A, B, float(w1), float(w2), int(batch_total), int(flags))
+
+
+def nearest_neighbors(A, B, flags: int = FLAG_NONE):
+    """_nearest_neighbors(x, y) — src/metrics/pcloud.jl:54-86: (nn_for_x (B,N), nn_for_y (B,M)), 0-based int32."""
+    A = as_f32_tensor(A.points if isinstance(A, PointCloud) else A, "cuda")
+    B = as_f32_tensor(B.points if isinstance(B, PointCloud) else B, "cuda")
+    if A.dim() == 2:
+        A, B = A.unsqueeze(0), B.unsqueeze(0)
+    _, _, nnA, nnB = chamfer_forward_raw(A, B, 1.0, 1.0, flags=flags)
+    return nnA, nnB

@@ -1,0 +1,188 @@
+/*
+ * flux3d_b200.h — C ABI of libflux3d_b200.so: the Blackwell (sm_100a) implementation of the
+ * Flux3D.jl batched 3D-metric hot path.  This is the drop-in boundary: a Julia `ccall`
+ * (flux3d.jl_b200/julia/Flux3DB200.jl), Python ctypes (flux3d.jl_b200/_lib.py) or any other FFI
+ * binds exactly these symbols.  No torch / CUDA.jl types appear: plain device pointers, sizes and a
+ * CUDA stream handle.
+ *
+ * Conventions
+ *   - Every function returns an int32 status: 0 OK, 1 invalid argument, 2 misaligned buffer,
+ *     3 workspace too small, 4 CUDA error, 5 NCCL error.  f3d_last_error() gives the message of the
+ *     last failure on the calling thread.  No exceptions cross the boundary.
+ *   - All array pointers are DEVICE pointers unless the name ends in `_host`.  The caller owns every
+ *     buffer, workspace included; the library allocates nothing on the hot path and launches
+ *     asynchronously on `stream` (no host synchronisation).
+ *   - Layout: a Julia (3,N,B) Float32 array == C [B][N][3] (xyz interleaved).  Julia (F,K,N,B) ==
+ *     C [B][N][K][F].  Indices are 0-based int32 here; the Julia shim adds 1.
+ *   - Arithmetic: every distance / cross product / normalisation is evaluated in the operation
+ *     order of the Julia reference with separately rounded IEEE binary32 operations (Julia does not
+ *     contract a*b+c), unless F3D_FLAG_FMA is passed.
+ *
+ * Each entry point cites the reference code (FluxML/Flux3D.jl v0.1.6, file:line) it replaces.
+ */
+#ifndef FLUX3D_B200_H
+#define FLUX3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* f3d_stream_t; /* cudaStream_t / CUstream */
+
+#if defined(__GNUC__)
+#define F3D_API __attribute__((visibility("default")))
+#else
+#define F3D_API
+#endif
+
+enum {
+    F3D_OK = 0,
+    F3D_ERR_INVALID = 1,
+    F3D_ERR_MISALIGNED = 2,
+    F3D_ERR_WORKSPACE = 3,
+    F3D_ERR_CUDA = 4,
+    F3D_ERR_NCCL = 5
+};
+
+enum {
+    F3D_FLAG_NONE = 0,
+    /* Evaluate squared distances as fma(dz,dz,fma(dy,dy,dx*dx)) instead of the reference's
+       ((dx*dx)+(dy*dy))+(dz*dz).  Faster (6 instead of 8 FP32 operations per pair) but NOT the
+       reference arithmetic: near-ties may resolve differently.  Off by default. */
+    F3D_FLAG_FMA = 1
+};
+
+enum {
+    F3D_NORMALS_REFERENCE_CPU = 0, /* last face per corner slot wins (what rep/mesh.jl:604-615 does on CPU) */
+    F3D_NORMALS_ACCUMULATE = 1     /* sum over all incident corners (what its docstring says) */
+};
+
+F3D_API int32_t f3d_version(void);
+/* Copies the calling thread's last error message (NUL-terminated) into buf; returns its length. */
+F3D_API int32_t f3d_last_error(char* buf, size_t n);
+
+/* ------------------------------------------------------------------------------------------------
+ * chamfer_distance — replaces _chamfer_distance + _nearest_neighbors(::CuArray, ::CuArray)
+ * (src/metrics/pcloud.jl:39-52 and :72-86; semantics of the CPU method :54-70).
+ *
+ *   A [B][N][3], Bp [B][M][3]  →  loss_dev[0] = w1*ΣΣ‖a-b_nn(a)‖²/(N*B_total) + w2*ΣΣ‖b-a_nn(b)‖²/(M*B_total)
+ *
+ * B_total is the GLOBAL batch size of the mean (pass B, or the un-sharded batch when this call
+ * handles one shard of a batch split across GPUs; the shard results then add up to the reference
+ * value — see f3d_allreduce_sum_f32).  terms_dev (optional, 2 floats) receives the two un-weighted
+ * means.  nnA_dev [B][N] / nnB_dev [B][M] (optional) receive the argmin indices (ties → lowest).
+ * Brute force, O(N+M) memory: the N×M matrix of :75-78 is never materialised.
+ * ---------------------------------------------------------------------------------------------- */
+F3D_API size_t f3d_chamfer_workspace_bytes(int32_t B, int32_t N, int32_t M);
+F3D_API int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M, float w1,
+                        float w2, int32_t B_total, float* loss_dev, float* terms_dev,
+                        int32_t* nnA_dev, int32_t* nnB_dev, void* ws, size_t ws_bytes,
+                        int32_t flags, f3d_stream_t stream);
+
+/* Pullback of src/metrics/pcloud.jl:47-50 (indices constant, :45 is @ignore):
+ *   gA = gout*( 2w1/(N*B_total) (A - B[nnA])  -  scatter_add_{nnB}( 2w2/(M*B_total) (B - A[nnB]) ) ), gB symmetric.
+ * gout_dev: 1 float (upstream gradient of the scalar loss).  gA/gB are fully overwritten. */
+F3D_API int32_t f3d_chamfer_bwd(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M, float w1,
+                        float w2, int32_t B_total, const int32_t* nnA_dev, const int32_t* nnB_dev,
+                        const float* gout_dev, float* gA, float* gB, f3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * kNN graph — replaces CreateSingleKNNGraph + the batch loop / gather / concat prologue of EdgeConv
+ * (src/models/dgcnn.jl:3-9 and :32-45).
+ *   X [B][N][F]; for every point the K nearest OTHER points = positions 2..K+1 of the (K+1)-NN list
+ *   sorted ascending by (squared distance, index).  1 <= K < N, K <= 64, F <= 128.
+ *   idx [B][N][K] (required); dist [B][N][K] (optional squared distances);
+ *   gathered [B][N][K][F] (optional; == the Julia (F,K,N,B) KNNGraph tensor of :36);
+ *   edge_feat [B][N][K][2F] (optional; == cat(X, KNNGraph - X; dims=1) of :45).
+ * ---------------------------------------------------------------------------------------------- */
+F3D_API size_t f3d_knn_graph_workspace_bytes(int32_t B, int32_t N, int32_t F, int32_t K);
+F3D_API int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F, int32_t K, int32_t* idx,
+                      float* dist, float* gathered, float* edge_feat, void* ws, size_t ws_bytes,
+                      int32_t flags, f3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * TriMesh kernels on packed verts [nV][3] / packed faces [nF][3] (global 0-based vertex ids).
+ * ---------------------------------------------------------------------------------------------- */
+/* compute_faces_areas_packed (src/rep/mesh.jl:765-780) and compute_faces_normals_packed (:689-700).
+ * areas [nF] and/or normals [nF][3] may be NULL. */
+F3D_API int32_t f3d_faces_areas_normals(const float* verts, const int32_t* faces, int32_t nV, int32_t nF,
+                                float* areas, float* normals, f3d_stream_t stream);
+
+/* Topology products, built ONCE per mesh topology on the HOST and cached by the caller, mirroring
+ * the cached fields of TriMesh (src/rep/mesh.jl:93-97):
+ *   edges_host [<=3nF][2] unique (min,max) edges sorted lexicographically (_compute_edges_packed :907-955)
+ *   f2e_host [nF][3]      faces→edges, column order (e23,e31,e12)                (:943-949)   (optional)
+ *   lap_rowptr_host [nV+1], lap_colidx_host [2nE+nV], lap_vals_host [2nE+nV]: CSR of the Laplacian,
+ *                          L[i,i]=-1, L[i,j]=Float32(1/deg i), columns ascending (_compute_laplacian_packed :957-1002)
+ *   v2c_rowptr_host [nV+1], v2c_host [3nF]: vertex → incident corners (face*3+slot), ascending — the
+ *                          gather form of the scatter at :604-615 (deterministic, no atomics).
+ * All pointers are HOST pointers; *nE_host receives the edge count. */
+F3D_API int32_t f3d_mesh_topology_build_host(const int32_t* faces_host, int32_t nV, int32_t nF,
+                                     int32_t* edges_host, int32_t* nE_host, int32_t* f2e_host,
+                                     int32_t* lap_rowptr_host, int32_t* lap_colidx_host,
+                                     float* lap_vals_host, int32_t* v2c_rowptr_host,
+                                     int32_t* v2c_host);
+
+/* compute_verts_normals_packed (src/rep/mesh.jl:589-618).  mode: F3D_NORMALS_*.  out [nV][3]. */
+F3D_API int32_t f3d_verts_normals(const float* verts, const int32_t* faces, const int32_t* v2c_rowptr,
+                          const int32_t* v2c, int32_t nV, int32_t nF, int32_t mode, float* out,
+                          f3d_stream_t stream);
+
+/* laplacian_loss (src/metrics/mesh.jl:9-15): mean_i ‖Σ_j L[i,j] v_j‖₂ over all nV packed vertices.
+ * nV_total: global vertex count of the mean (nV, or the un-sharded count for a mesh-sharded call).
+ * ws: f3d_laplacian_workspace_bytes(nV). */
+F3D_API size_t f3d_laplacian_workspace_bytes(int32_t nV);
+F3D_API int32_t f3d_laplacian_loss(const float* verts, const int32_t* lap_rowptr, const int32_t* lap_colidx,
+                           const float* lap_vals, int32_t nV, int32_t nV_total, float* loss_dev,
+                           void* ws, size_t ws_bytes, f3d_stream_t stream);
+/* Pullback: gverts[j] = gout * Σ_i L[i,j] * n̂_i / nV_total, n̂_i = (Lv)_i/‖(Lv)_i‖ (0 where the norm is 0).
+ * Uses the CSR of Lᵀ = same pattern (L's pattern is symmetric) with values 1/deg(i) per source row. */
+F3D_API int32_t f3d_laplacian_loss_bwd(const float* verts, const int32_t* lap_rowptr,
+                               const int32_t* lap_colidx, const float* lap_vals, int32_t nV,
+                               int32_t nV_total, const float* gout_dev, float* gverts, void* ws,
+                               size_t ws_bytes, f3d_stream_t stream);
+
+/* edge_loss (src/metrics/mesh.jl:24-32): mean_e (‖v_e1 - v_e2‖ - target)².  ws: f3d_edge_loss_workspace_bytes(nE). */
+F3D_API size_t f3d_edge_loss_workspace_bytes(int32_t nE);
+F3D_API int32_t f3d_edge_loss(const float* verts, const int32_t* edges, int32_t nE, int32_t nE_total,
+                      float target, float* loss_dev, void* ws, size_t ws_bytes, f3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * sample_points — replaces sample_points/_sample_points/_rand_barycentric_coords
+ * (src/transforms/mesh_func.jl:21-82).
+ *   verts_padded [Nmesh][Vmax][3], faces_padded [Nmesh][Fmax][3] (LOCAL 0-based ids, padding = any),
+ *   verts_len/faces_len [Nmesh] (device).  samples [Nmesh][S][3]; face_idx_out [Nmesh][S] optional.
+ *   Face probabilities are Float64 area/max(Σarea,eps) as at :32-39.  Draws: Philox4x32-10 keyed by
+ *   (seed, offset) — counter (s, mesh) — unless inj_face/inj_r1/inj_r2 ([Nmesh][S], device) are given,
+ *   in which case the face ids and the two uniforms are taken from them (bit-parity mode; the
+ *   reference's own draws come from Julia's global RNG and cannot be reproduced).
+ *   ws: f3d_sample_points_workspace_bytes(Nmesh, Fmax).
+ * ---------------------------------------------------------------------------------------------- */
+F3D_API size_t f3d_sample_points_workspace_bytes(int32_t Nmesh, int32_t Fmax);
+F3D_API int32_t f3d_sample_points(const float* verts_padded, const int32_t* faces_padded,
+                          const int32_t* verts_len, const int32_t* faces_len, int32_t Nmesh,
+                          int32_t Vmax, int32_t Fmax, int32_t S, double eps, uint64_t seed,
+                          uint64_t offset, const int32_t* inj_face, const float* inj_r1,
+                          const float* inj_r2, float* samples, int32_t* face_idx_out, void* ws,
+                          size_t ws_bytes, f3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: the batch axis is sharded across ranks (one process per GPU); the only data-path
+ * exchange is one all-reduce of the per-shard scalar loss.  NCCL is loaded lazily (dlopen), so the
+ * library itself has no link-time NCCL dependency.
+ *   f3d_comm_unique_id_host: rank 0 fills a 128-byte ncclUniqueId to broadcast out of band.
+ *   f3d_comm_init: collective; *comm receives an opaque handle.
+ *   f3d_allreduce_sum_f32: in-place ncclAllReduce(sum) of `count` floats at dev_buf, on `stream`.
+ * ---------------------------------------------------------------------------------------------- */
+F3D_API int32_t f3d_comm_unique_id_host(void* id128_host);
+F3D_API int32_t f3d_comm_init(int32_t nranks, int32_t rank, const void* id128_host, void** comm);
+F3D_API int32_t f3d_allreduce_sum_f32(void* comm, float* dev_buf, int32_t count, f3d_stream_t stream);
+F3D_API int32_t f3d_comm_destroy(void* comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUX3D_B200_H */

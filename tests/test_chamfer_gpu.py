@@ -1,0 +1,142 @@
+"""GPU parity: f3d_chamfer_fwd (through the C ABI) vs the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star): argmin indices bit-exact, Float32 loss within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star: "within 1e-5 relative for Float32 losses"
+
+
+def _run(f3d, A, B, w1=1.0, w2=1.0, flags=0):
+    tA = torch.from_numpy(A).cuda()
+    tB = torch.from_numpy(B).cuda()
+    loss, terms, nnA, nnB = f3d.chamfer_forward_raw(tA, tB, w1, w2, flags=flags)
+    torch.cuda.synchronize()
+    return float(loss.item()), terms.cpu().numpy(), nnA.cpu().numpy(), nnB.cpu().numpy()
+
+
+def _check(f3d, oracle, A, B, w1=1.0, w2=1.0):
+    loss, terms, nnA, nnB = _run(f3d, A, B, w1, w2)
+    ol, onA, onB, oterms = oracle.chamfer_distance(A, B, w1, w2, return_all=True)
+    assert np.array_equal(nnA, onA), f"nn_for_A mismatch at {np.argwhere(nnA != onA)[:5]}"
+    assert np.array_equal(nnB, onB), f"nn_for_B mismatch at {np.argwhere(nnB != onB)[:5]}"
+    assert abs(loss - float(ol)) <= RTOL * abs(float(ol)) + 1e-30, (loss, float(ol))
+    assert np.allclose(terms, oterms, rtol=RTOL, atol=0)
+    return loss
+
+
+@pytest.mark.parametrize("B,N,M,seed", [
+    (2, 1024, 1024, 101),   # BASELINE configs[0] (cfg1, seeds 101/102)
+    (2, 1000, 500, 7),      # the reference's own test shape, N != M (test/metrics.jl:109-110)
+    (1, 257, 33, 8),        # ragged: one row past a 256-row block, one column past a chunk
+    (3, 31, 1, 9),          # single column
+    (1, 1, 1, 10),          # single pair
+    (2, 777, 1301, 11),     # N % 4 != 0, M odd, M > one column tile
+    (4, 2048, 4096, 12),
+])
+def test_parity_random(f3d, oracle, B, N, M, seed):
+    rng = np.random.default_rng(seed)
+    A = rng.random((B, N, 3), dtype=np.float32)
+    Bc = np.random.default_rng(seed + 1).random((B, M, 3), dtype=np.float32)
+    _check(f3d, oracle, A, Bc)
+
+
+def test_cfg1_known_value(f3d, oracle):
+    """cfg1 golden: loss 0.0074543296 (seeds 101/102) — oracle and kernel both."""
+    A = np.random.default_rng(101).random((2, 1024, 3), dtype=np.float32)
+    B = np.random.default_rng(102).random((2, 1024, 3), dtype=np.float32)
+    loss = _check(f3d, oracle, A, B)
+    assert abs(loss - 0.0074543296) <= 1e-5 * 0.0074543296
+
+
+def test_weights(f3d, oracle):
+    rng = np.random.default_rng(21)
+    A = rng.standard_normal((2, 300, 3)).astype(np.float32)
+    B = rng.standard_normal((2, 400, 3)).astype(np.float32)
+    _check(f3d, oracle, A, B, w1=0.25, w2=3.0)
+
+
+def test_ties_lowest_index(f3d, oracle):
+    """Exact duplicates and lattice points: every tie must resolve to the lowest index, in both directions."""
+    rng = np.random.default_rng(31)
+    base = rng.integers(0, 4, size=(2, 600, 3)).astype(np.float32)  # 64 distinct lattice points → massive ties
+    A = base[:, :520]
+    B = base[:, 80:]
+    _check(f3d, oracle, A, B)
+    # duplicated cloud: nearest neighbour of a point is its lowest-indexed copy
+    P = rng.random((1, 300, 3), dtype=np.float32)
+    A2 = np.concatenate([P, P], axis=1)
+    loss, _, nnA, nnB = _run(f3d, A2, A2)
+    assert loss == 0.0
+    assert np.array_equal(nnA[0], np.r_[np.arange(300), np.arange(300)])
+    _check(f3d, oracle, A2, A2)
+
+
+def test_reference_benchmark_input(f3d, oracle):
+    """The reference's own benchmark input: points on the diagonal cumsum(ones)/n (benchmarks/metrics.jl:11-15)."""
+    n = 4096
+    P = (np.cumsum(np.ones((n, 3), np.float32), axis=0) / np.float32(n)).astype(np.float32)[None]
+    _check(f3d, oracle, P, P[:, ::-1].copy())
+
+
+def test_self_distance_zero(f3d):
+    """chamfer_distance(m, m) ≈ 0 (test/metrics.jl:88-89)."""
+    A = np.random.default_rng(41).random((2, 1500, 3), dtype=np.float32)
+    loss, _, nnA, nnB = _run(f3d, A, A)
+    assert loss == 0.0
+    assert np.array_equal(nnA, np.broadcast_to(np.arange(1500), (2, 1500)))
+
+
+def test_naive_chamfer_identity(f3d, oracle):
+    """The reference test's identity: chamfer_distance ≈ naive_chamfer (test/metrics.jl:94-111), default
+    isapprox rtol = sqrt(eps(Float32)) ≈ 3.45e-4."""
+    x = np.random.default_rng(51).random((2, 1000, 3), dtype=np.float32)
+    y = np.random.default_rng(52).random((2, 500, 3), dtype=np.float32)
+    loss, *_ = _run(f3d, x, y)
+    assert abs(loss - oracle.np_naive_chamfer(x, y)) <= 3.4526698e-4 * abs(loss)
+
+
+def test_cfg2_full_size(f3d, oracle):
+    """BASELINE configs[1]: B=32, N=M=4096 (seeds 201/202) — full-size index + loss parity."""
+    A = np.random.default_rng(201).random((32, 4096, 3), dtype=np.float32)
+    B = np.random.default_rng(202).random((32, 4096, 3), dtype=np.float32)
+    loss = _check(f3d, oracle, A, B)
+    assert abs(loss - 0.0028460352) <= 1e-5 * 0.0028460352
+
+
+def test_fma_mode_close(f3d, oracle):
+    """F3D_FLAG_FMA is a different (non-reference) rounding: loss within 1e-5, indices equal except near-ties."""
+    A = np.random.default_rng(61).random((4, 2048, 3), dtype=np.float32)
+    B = np.random.default_rng(62).random((4, 2048, 3), dtype=np.float32)
+    loss, _, nnA, nnB = _run(f3d, A, B, flags=f3d.FLAG_FMA)
+    ol, onA, onB, _ = oracle.chamfer_distance(A, B, return_all=True)
+    assert abs(loss - float(ol)) <= RTOL * float(ol)
+    assert (nnA != onA).mean() < 1e-3 and (nnB != onB).mean() < 1e-3
+
+
+def test_properties_large(f3d):
+    """Size-independent properties at a size the oracle would take minutes for (cfg5 per-GPU shard:
+    B=32, N=M=8192): symmetry under swapping the clouds/weights, permutation invariance of the loss,
+    idempotence (bitwise-identical reruns) and nn index validity."""
+    g = torch.Generator(device="cuda").manual_seed(71)
+    A = torch.rand((32, 8192, 3), generator=g, device="cuda")
+    B = torch.rand((32, 8192, 3), generator=g, device="cuda")
+    l1, t1, nnA, nnB = f3d.chamfer_forward_raw(A, B, 0.3, 1.7)
+    l2, t2, nnB2, nnA2 = f3d.chamfer_forward_raw(B, A, 1.7, 0.3)
+    l3, *_ = f3d.chamfer_forward_raw(A, B, 0.3, 1.7)
+    torch.cuda.synchronize()
+    assert torch.equal(l1, l3)                          # deterministic
+    assert torch.equal(nnA, nnA2) and torch.equal(nnB, nnB2)
+    assert torch.allclose(t1, t2.flip(0), rtol=1e-6)
+    assert abs(l1.item() - l2.item()) <= 1e-6 * abs(l1.item())
+    perm = torch.randperm(8192, device="cuda")
+    l4, _, nnA4, _ = f3d.chamfer_forward_raw(A, B[:, perm], 0.3, 1.7)
+    assert abs(l4.item() - l1.item()) <= 1e-6 * abs(l1.item())
+    # gathered distances reproduce the reported terms
+    gB = torch.gather(B, 1, nnA.long().unsqueeze(-1).expand(-1, -1, 3))
+    dAB = ((A - gB) ** 2).sum(-1).double().mean()
+    assert abs(dAB.item() - t1[0].item()) <= 1e-5 * dAB.item()
+    assert int(nnA.min()) >= 0 and int(nnA.max()) < 8192
