@@ -94,3 +94,24 @@ def ptr(t):
     if hasattr(t, "data_ptr"):
         return C.c_void_p(t.data_ptr())
     return C.c_void_p(t.ctypes.data)
+
+
+# ---- caller-owned device workspaces (the library allocates nothing; torch owns the memory) ----------
+_ws_cache: dict = {}
+
+
+def workspace(key, nbytes: int, device):
+    """A >= nbytes uint8 device buffer, cached per (op key, device, stream) the way CUDA.jl would keep a
+    scratch CuArray.  256-byte aligned (torch's caching allocator guarantees 512)."""
+    import torch
+    k = (key, str(device), torch.cuda.current_stream(device).cuda_stream)
+    t = _ws_cache.get(k)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[k] = t
+    return t
+
+
+def stream_ptr(device):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -12,22 +12,8 @@ from .pcloud import PointCloud, as_f32_tensor
 FLAG_NONE = 0
 FLAG_FMA = 1  # non-reference arithmetic (fused multiply-add distances); see include/flux3d_b200.h
 
-_ws_cache: dict = {}
-
-
-def _workspace(key, nbytes: int, device) -> torch.Tensor:
-    """Caller-owned workspace, cached per (op, shape, device, stream) like CUDA.jl would cache a CuArray."""
-    k = (key, str(device), torch.cuda.current_stream(device).cuda_stream)
-    t = _ws_cache.get(k)
-    if t is None or t.numel() < nbytes:
-        t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
-        _ws_cache[k] = t
-    return t
-
-
-def _stream_ptr(device):
-    import ctypes
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+_workspace = _lib.workspace
+_stream_ptr = _lib.stream_ptr
 
 
 def chamfer_forward_raw(A: torch.Tensor, B: torch.Tensor, w1: float, w2: float, *, batch_total: int = 0,

@@ -63,15 +63,29 @@ static inline float sqdist3(const float* a, const float* b) {
 }
 
 /* Julia Base.mapreduce_impl(identity,+,A,ifirst,ilast,blksize=1024): pairwise summation that
- * `mean`/`sum` use on a dense Array{Float32}.  (The <1024 leaf is a @simd loop in Julia whose
- * lane order is not specified; it is sequential here — differences are O(1e-7) relative and
- * covered by the 1e-5 tolerance north_star states for Float32 losses.) */
+ * `mean`/`sum` use on a dense Array{Float32}.  The <1024 leaf is
+ *     v = A[ifirst] + A[ifirst+1];  @simd for i = ifirst+2:ilast  v += A[i]  end
+ * and @simd licenses LLVM to re-associate: on x86-64 it keeps ORC_SIMD_LANES lane-strided partial
+ * sums (8-wide vectors x 4 interleave on AVX2) and reduces them by a halving tree, the scalar
+ * remainder is added last.  The lane count is the compiler's choice, so the reference value itself
+ * is machine-dependent at the last ulps; every width from 4 to 32 reproduces the published
+ * laplacian_loss(teapot) = 0.05888283f0 (README.md:111-112) exactly, the strictly sequential
+ * order does not (0.058882844f0) — which is why the leaf is written this way. */
+#define ORC_SIMD_LANES 32
 static float pairwise_sum_f32(const float* a, long n) {
     if (n <= 0) return 0.0f;
     if (n == 1) return a[0];
     if (n - 1 < 1024) { /* ilast - ifirst < blksize */
         float v = a[0] + a[1];
-        for (long i = 2; i < n; ++i) v = v + a[i];
+        float lane[ORC_SIMD_LANES];
+        long rest = n - 2, nv = rest / ORC_SIMD_LANES * ORC_SIMD_LANES;
+        for (int l = 0; l < ORC_SIMD_LANES; ++l) lane[l] = 0.0f;
+        for (long i = 0; i < nv; i += ORC_SIMD_LANES)
+            for (int l = 0; l < ORC_SIMD_LANES; ++l) lane[l] = lane[l] + a[2 + i + l];
+        for (int w = ORC_SIMD_LANES / 2; w >= 1; w /= 2)
+            for (int l = 0; l < w; ++l) lane[l] = lane[l] + lane[l + w];
+        v = v + lane[0];
+        for (long i = nv; i < rest; ++i) v = v + a[2 + i];
         return v;
     }
     long left = ((n - 1) >> 1) + 1; /* imid = ifirst + ((ilast-ifirst) >> 1); left block = ifirst..imid */
@@ -486,26 +500,28 @@ static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
 }
 
 /* Draws for sample s of mesh i: counter = (s, i, offset_lo, offset_hi), key = seed.
- * out[0] → u_face as a Float64 in [0,1) from 53 bits (out0,out1); r1,r2 Float32 in [0,1) from the
- * top 24 bits of out2,out3 (Julia's rand(Float32) also yields multiples of 2^-24... of 2^-23 in
+ * (out0,out1) → u_face, a 53-bit uniform integer (u_face / 2^53 is the Float64 uniform in [0,1));
+ * r1,r2 Float32 in [0,1) from the top 24 bits of out2,out3 (Julia's rand(Float32) also yields multiples of 2^-24... of 2^-23 in
  * older versions; either way a uniform grid on [0,1)). */
-ORC_API void orc_philox_draws(uint64_t seed, uint64_t offset, int mesh, int s, double* u_face,
+ORC_API void orc_philox_draws(uint64_t seed, uint64_t offset, int mesh, int s, uint64_t* u_face,
                               float* r1, float* r2) {
     uint32_t c[4] = {(uint32_t)s, (uint32_t)mesh, (uint32_t)offset, (uint32_t)(offset >> 32)};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    uint64_t m = (((uint64_t)c[0] << 32) | c[1]) >> 11;
-    *u_face = (double)m * (1.0 / 9007199254740992.0);
+    *u_face = (((uint64_t)c[0] << 32) | c[1]) >> 11;
     *r1 = (float)(c[2] >> 8) * (1.0f / 16777216.0f);
     *r2 = (float)(c[3] >> 8) * (1.0f / 16777216.0f);
 }
 
 /* sample_points — src/transforms/mesh_func.jl:21-82.
- * verts_padded: [Nmesh][Vmax][3]; faces_padded: [Nmesh][Fmax][3] local 0-based (pad = -1);
- * Face probabilities: Float64 area / max(Σarea, eps) (:32-39), categorical draw by inverse CDF over
- * the first faces_len[i] faces (sequential Float64 cumsum; the last valid face absorbs the residual,
- * the analogue of :36-37).  If inj_face != NULL the face ids / r1 / r2 are taken from the injected
- * arrays ([Nmesh][S]) instead of Philox — this is the mode in which parity with the reference's
- * arithmetic (:60-82) is bit-exact:
+ * verts_padded: [Nmesh][Vmax][3]; faces_padded: [Nmesh][Fmax][3] local 0-based (pad = anything);
+ * Face probabilities: Float64 area / max(Σarea, eps) (:32-39; Σ sequential in Float64 as Julia's
+ * sum(...; dims=2) does).  The reference then draws from Distributions.Categorical (alias tables)
+ * with Julia's global RNG — irreproducible — so the draw is DEFINED here as inverse-CDF with the CDF
+ * held in 53-bit fixed point: C_f = Σ_{g<=f} floor(p_g * 2^53) (integer sums: order-independent),
+ * face = smallest f with C_f > m for a 53-bit uniform integer m, clamped to the last valid face
+ * (which thereby absorbs the rounding residual, the analogue of :36-37).
+ * If inj_face != NULL the face ids / r1 / r2 are taken from the injected arrays ([Nmesh][S]) instead
+ * of Philox — this is the mode in which parity with the reference's arithmetic (:60-82) is bit-exact:
  *   u = sqrt(r1); w1 = 1-u; w2 = u*(1-v); w3 = u*v;  p = ((w1*v1)+(w2*v2))+(w3*v3)
  * samples: [Nmesh][S][3]; face_idx_out (opt): [Nmesh][S]. */
 ORC_API void orc_sample_points(const float* verts_padded, const int32_t* faces_padded,
@@ -514,7 +530,7 @@ ORC_API void orc_sample_points(const float* verts_padded, const int32_t* faces_p
                                uint64_t offset, const int32_t* inj_face, const float* inj_r1,
                                const float* inj_r2, float* samples, int32_t* face_idx_out) {
     (void)verts_len;
-    double* cdf = (double*)malloc(sizeof(double) * (size_t)(Fmax > 0 ? Fmax : 1));
+    uint64_t* cdf = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(Fmax > 0 ? Fmax : 1));
     float* areas = (float*)malloc(sizeof(float) * (size_t)(Fmax > 0 ? Fmax : 1));
     for (int i = 0; i < Nmesh; ++i) {
         const float* V = verts_padded + (long)i * Vmax * 3;
@@ -524,8 +540,8 @@ ORC_API void orc_sample_points(const float* verts_padded, const int32_t* faces_p
         double tot = 0.0;
         for (int f = 0; f < nF; ++f) tot = tot + (double)areas[f];
         double den = tot > eps ? tot : eps;
-        double run = 0.0;
-        for (int f = 0; f < nF; ++f) { run = run + (double)areas[f] / den; cdf[f] = run; }
+        uint64_t run = 0;
+        for (int f = 0; f < nF; ++f) { run += (uint64_t)(((double)areas[f] / den) * 9007199254740992.0); cdf[f] = run; }
         for (int s = 0; s < S; ++s) {
             int face;
             float r1, r2;
@@ -534,7 +550,7 @@ ORC_API void orc_sample_points(const float* verts_padded, const int32_t* faces_p
                 r1 = inj_r1[(long)i * S + s];
                 r2 = inj_r2[(long)i * S + s];
             } else {
-                double u;
+                uint64_t u;
                 orc_philox_draws(seed, offset, i, s, &u, &r1, &r2);
                 int lo = 0, hi = nF - 1; /* smallest f with cdf[f] > u, clamped to nF-1 */
                 while (lo < hi) {

@@ -61,7 +61,7 @@ def lib():
         L.orc_sample_points.argtypes = [f32p, i32p, i32p, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                         C.c_uint64, C.c_uint64, i32p, f32p, f32p, f32p, i32p]
         L.orc_sample_points.restype = None
-        L.orc_philox_draws.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double), f32p, f32p]
+        L.orc_philox_draws.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), f32p, f32p]
         L.orc_philox_draws.restype = None
         L.orc_num_threads.restype = C.c_int
         _lib = L
@@ -227,7 +227,7 @@ def sample_points(verts_padded, faces_padded, verts_len, faces_len, S, eps=1e-6,
 
 
 def philox_draws(seed, offset, mesh, s):
-    u = C.c_double()
+    u = C.c_uint64()
     r1 = C.c_float()
     r2 = C.c_float()
     lib().orc_philox_draws(seed, offset, mesh, s, C.byref(u), C.byref(r1), C.byref(r2))
