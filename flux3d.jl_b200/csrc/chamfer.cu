@@ -362,6 +362,7 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
         chamfer_sweep_kernel<false><<<grid, kThreads, smem, stream>>>(sp);
     }
     F3D_CHECK_LAUNCH("chamfer_sweep_kernel");
+    if (flags & F3D_FLAG_SWEEP_ONLY) return F3D_OK;
 
     FinalizeParams fp;
     fp.A = A; fp.Bp = Bp; fp.B = B; fp.N = N; fp.M = M;

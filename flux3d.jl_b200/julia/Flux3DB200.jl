@@ -1,0 +1,175 @@
+# Flux3DB200.jl — the Julia side of the drop-in: methods that out-dispatch Flux3D's generic ones for
+# CuArray{Float32} storage and `ccall` libflux3d_b200.so (include/flux3d_b200.h).
+#
+# STATUS: written against Flux3D v0.1.6 + CUDA.jl, NOT executed — the build image has no Julia
+# (SURVEY.md §0 fact 2).  The same C symbols are exercised from Python/ctypes by tests/ and bench.py.
+#
+# Usage (a maintainer adds ONE line to src/Flux3D.jl after the includes):
+#     include(joinpath(ENV["FLUX3D_B200_HOME"], "julia", "Flux3DB200.jl"))
+# Layout: a Julia (3,N,B) Float32 CuArray is byte-identical to the C [B][N][3] array the library reads,
+# so no copies or permutes are made.  Indices come back 0-based Int32; +1 is applied here.
+module Flux3DB200
+
+using CUDA, Zygote
+import Flux3D
+import Flux3D: TriMesh, PointCloud, get_verts_packed, get_verts_padded, get_faces_packed, get_faces_padded
+
+const LIB = get(ENV, "FLUX3D_B200_LIB", joinpath(@__DIR__, "..", "libflux3d_b200.so"))
+
+function check(status::Int32)
+    status == 0 && return
+    buf = Vector{UInt8}(undef, 512)
+    ccall((:f3d_last_error, LIB), Int32, (Ptr{UInt8}, Csize_t), buf, 512)
+    error("libflux3d_b200 status $status: ", unsafe_string(pointer(buf)))   # same style as rep/mesh.jl:126-128
+end
+
+devptr(x::CuArray{T}) where {T} = reinterpret(Ptr{T}, pointer(x))
+cur_stream() = reinterpret(Ptr{Cvoid}, CUDA.stream().handle)
+
+const _ws = Dict{Any,CuVector{UInt8}}()
+function workspace(key, nbytes)
+    w = get(_ws, key, nothing)
+    if w === nothing || length(w) < nbytes
+        w = CuVector{UInt8}(undef, max(nbytes, 256)); _ws[key] = w
+    end
+    return w
+end
+
+# ---- chamfer_distance: replaces _chamfer_distance + _nearest_neighbors(::CuArray,::CuArray) -------------
+# (src/metrics/pcloud.jl:39-52, :72-86)
+function chamfer_fwd(A::CuArray{Float32,3}, B::CuArray{Float32,3}, w1::Float32, w2::Float32; want_indices = true, batch_total = 0)
+    (_, N, Bn) = size(A); M = size(B, 2)
+    size(B, 3) == Bn || error("batch sizes differ: $Bn vs $(size(B, 3))")
+    nbytes = ccall((:f3d_chamfer_workspace_bytes, LIB), Csize_t, (Int32, Int32, Int32), Bn, N, M)
+    ws = workspace((:chamfer, Bn, N, M), nbytes)
+    res = CUDA.zeros(Float32, 3)
+    nnA = want_indices ? CuArray{Int32}(undef, N, Bn) : nothing
+    nnB = want_indices ? CuArray{Int32}(undef, M, Bn) : nothing
+    check(ccall((:f3d_chamfer_fwd, LIB), Int32,
+        (Ptr{Float32}, Ptr{Float32}, Int32, Int32, Int32, Float32, Float32, Int32, Ptr{Float32}, Ptr{Float32},
+         Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}, Csize_t, Int32, Ptr{Cvoid}),
+        devptr(A), devptr(B), Bn, N, M, w1, w2, batch_total, devptr(res), devptr(res) + 4,
+        want_indices ? devptr(nnA) : C_NULL, want_indices ? devptr(nnB) : C_NULL, devptr(ws), length(ws), 0, cur_stream()))
+    return res, nnA, nnB
+end
+
+function Flux3D._chamfer_distance(A::CuArray{Float32,3}, B::CuArray{Float32,3}, w1::Float32, w2::Float32)
+    res, _, _ = chamfer_fwd(A, B, w1, w2; want_indices = false)
+    return CUDA.@allowscalar res[1]
+end
+
+Zygote.@adjoint function Flux3D._chamfer_distance(A::CuArray{Float32,3}, B::CuArray{Float32,3}, w1::Float32, w2::Float32)
+    res, nnA, nnB = chamfer_fwd(A, B, w1, w2)
+    (_, N, Bn) = size(A); M = size(B, 2)
+    function back(g)
+        gout = CuArray(Float32[g]); gA = similar(A); gB = similar(B)
+        check(ccall((:f3d_chamfer_bwd, LIB), Int32,
+            (Ptr{Float32}, Ptr{Float32}, Int32, Int32, Int32, Float32, Float32, Int32, Ptr{Int32}, Ptr{Int32},
+             Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Cvoid}),
+            devptr(A), devptr(B), Bn, N, M, w1, w2, 0, devptr(nnA), devptr(nnB), devptr(gout), devptr(gA), devptr(gB), cur_stream()))
+        return (gA, gB, nothing, nothing)
+    end
+    return CUDA.@allowscalar(res[1]), back
+end
+
+# _nearest_neighbors(::CuArray, ::CuArray) — src/metrics/pcloud.jl:72-86: CartesianIndex matrices (N,B),(M,B)
+function Flux3D._nearest_neighbors(x::CuArray{Float32,3}, y::CuArray{Float32,3})
+    _, nnx, nny = chamfer_fwd(x, y, 1f0, 1f0)
+    hx, hy = Array(nnx), Array(nny)
+    return ([CartesianIndex(Int(hx[i, b]) + 1, b) for i in axes(hx, 1), b in axes(hx, 2)],
+            [CartesianIndex(Int(hy[j, b]) + 1, b) for j in axes(hy, 1), b in axes(hy, 2)])
+end
+
+# ---- kNN graph: replaces CreateSingleKNNGraph / the EdgeConv prologue (src/models/dgcnn.jl:3-9, 32-45) ----
+function knn_graph(X::CuArray{Float32,3}, K::Int; gathered = false, edge = false)
+    (F, N, Bn) = size(X)
+    idx = CuArray{Int32}(undef, K, N, Bn)
+    G = gathered ? CuArray{Float32}(undef, F, K, N, Bn) : nothing
+    E = edge ? CuArray{Float32}(undef, 2F, K, N, Bn) : nothing
+    check(ccall((:f3d_knn_graph, LIB), Int32,
+        (Ptr{Float32}, Int32, Int32, Int32, Int32, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Cvoid}, Csize_t, Int32, Ptr{Cvoid}),
+        devptr(X), Bn, N, F, K, devptr(idx), C_NULL, gathered ? devptr(G) : C_NULL, edge ? devptr(E) : C_NULL, C_NULL, 0, 0, cur_stream()))
+    return idx, G, E
+end
+
+Flux3D.CreateSingleKNNGraph(X::CuArray{Float32,2}, K::Int) =
+    dropdims(knn_graph(reshape(X, size(X, 1), size(X, 2), 1), K; gathered = true)[2]; dims = 4)
+Zygote.@nograd knn_graph
+
+# EdgeConv on device arrays: the prologue (:36-45) is one kernel; the MLP/MaxPool tail (:46-61) is unchanged.
+function (m::Flux3D.EdgeConv)(X::CuArray{Float32,3})
+    F, N, B = size(X)
+    E = Zygote.ignore(() -> knn_graph(X, m.K; edge = true)[3])      # (2F, K, N, B) == cat(X, KNNGraph - X; dims=1)
+    Xe = reshape(PermutedDimsArray(E, (2, 3, 1, 4)), N * m.K, 2F, B)
+    Xe = m.mlp(Xe)
+    an = size(Xe, 2)
+    Xe = reshape(Xe, m.K, an * N, B)
+    Xe = m.maxpool_K(Xe)
+    Xe = reshape(Xe, N, an, B)
+    return permutedims(Xe, (2, 1, 3))
+end
+
+# ---- TriMesh: device-resident faces/topology cached per mesh (the reference caches the same products on the
+# host, src/rep/mesh.jl:93-97) ---------------------------------------------------------------------------
+struct Topology
+    faces::CuArray{Int32,2}; edges::CuArray{Int32,2}; nE::Int
+    rowptr::CuVector{Int32}; colidx::CuVector{Int32}; vals::CuVector{Float32}
+    v2c_rowptr::CuVector{Int32}; v2c::CuVector{Int32}
+end
+const _topo = WeakKeyDict{Any,Topology}()
+
+function topology(m::TriMesh)
+    get!(_topo, m._faces_list) do
+        faces = Int32.(get_faces_packed(m)) .- Int32(1)                  # (3, ΣF) == C [ΣF][3], 0-based
+        nV = size(get_verts_packed(m), 2); nF = size(faces, 2)
+        edges = Matrix{Int32}(undef, 2, max(3nF, 1)); nE = Ref{Int32}(0)
+        rowptr = Vector{Int32}(undef, nV + 1); colidx = Vector{Int32}(undef, 6nF + nV); vals = Vector{Float32}(undef, 6nF + nV)
+        v2c_rowptr = Vector{Int32}(undef, nV + 1); v2c = Vector{Int32}(undef, max(3nF, 1))
+        check(ccall((:f3d_mesh_topology_build_host, LIB), Int32,
+            (Ptr{Int32}, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Ptr{Int32}, Ptr{Int32}),
+            faces, nV, nF, edges, nE, C_NULL, rowptr, colidx, vals, v2c_rowptr, v2c))
+        nnz = 2 * nE[] + nV
+        Topology(CuArray(faces), CuArray(edges[:, 1:nE[]]), nE[], CuArray(rowptr), CuArray(colidx[1:nnz]), CuArray(vals[1:nnz]),
+                 CuArray(v2c_rowptr), CuArray(v2c))
+    end
+end
+
+# laplacian_loss — src/metrics/mesh.jl:9-15 (the reference copies verts to the host and runs a CPU SpMM)
+function Flux3D.laplacian_loss(m::TriMesh{Float32,R,CuArray}) where {R}
+    t = topology(m); verts = get_verts_packed(m); nV = size(verts, 2)
+    ws = workspace((:lap, nV), ccall((:f3d_laplacian_workspace_bytes, LIB), Csize_t, (Int32,), nV))
+    loss = CUDA.zeros(Float32, 1)
+    check(ccall((:f3d_laplacian_loss, LIB), Int32,
+        (Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Int32, Int32, Ptr{Float32}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        devptr(verts), devptr(t.rowptr), devptr(t.colidx), devptr(t.vals), nV, 0, devptr(loss), devptr(ws), length(ws), cur_stream()))
+    return CUDA.@allowscalar loss[1]
+end
+
+# compute_verts_normals_packed — src/rep/mesh.jl:589-618.  mode 0 = what the reference computes on the CPU
+# (last face per corner slot), mode 1 = what its docstring says (sum over incident faces).
+function Flux3D.compute_verts_normals_packed(m::TriMesh{Float32,R,CuArray}; mode::Integer = 0) where {R}
+    t = topology(m); verts = get_verts_packed(m); out = similar(verts)
+    check(ccall((:f3d_verts_normals, LIB), Int32,
+        (Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Int32, Int32, Ptr{Float32}, Ptr{Cvoid}),
+        devptr(verts), devptr(t.faces), devptr(t.v2c_rowptr), devptr(t.v2c), size(verts, 2), size(t.faces, 2), mode, devptr(out), cur_stream()))
+    return out
+end
+
+# sample_points — src/transforms/mesh_func.jl:21-58: one launch for the whole batch, device RNG (Philox)
+function Flux3D.sample_points(m::TriMesh{Float32,R,CuArray}, num_samples::Int = 5000; eps::Number = 1e-6,
+                              seed::UInt64 = rand(UInt64), offset::UInt64 = UInt64(0)) where {R}
+    verts = get_verts_padded(m)                                           # (3, V, N)
+    faces = CuArray(Int32.(get_faces_padded(m)) .- Int32(1))              # (3, F, N) local ids, pad = -1
+    vlen = CuArray(Int32.(m._verts_len)); flen = CuArray(Int32.(m._faces_len))
+    samples = similar(verts, 3, num_samples, m.N)
+    nws = ccall((:f3d_sample_points_workspace_bytes, LIB), Csize_t, (Int32, Int32), m.N, m.F)
+    ws = workspace((:sample, m.N, m.F), nws)
+    check(ccall((:f3d_sample_points, LIB), Int32,
+        (Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Int32, Int32, Int32, Float64, UInt64, UInt64,
+         Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        devptr(verts), devptr(faces), devptr(vlen), devptr(flen), m.N, m.V, m.F, num_samples, Float64(eps), seed, offset,
+        C_NULL, C_NULL, C_NULL, devptr(samples), C_NULL, devptr(ws), length(ws), cur_stream()))
+    return samples
+end
+
+end # module

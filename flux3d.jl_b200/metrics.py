@@ -11,6 +11,7 @@ from .pcloud import PointCloud, as_f32_tensor
 
 FLAG_NONE = 0
 FLAG_FMA = 1  # non-reference arithmetic (fused multiply-add distances); see include/flux3d_b200.h
+FLAG_SWEEP_ONLY = 2  # measurement aid: launch only the sweep kernel
 
 _workspace = _lib.workspace
 _stream_ptr = _lib.stream_ptr
@@ -89,6 +90,11 @@ def chamfer_distance(A, B, num_samples: int = 5000, *, w1: float = 1.0, w2: floa
         A = A.unsqueeze(0)
     if B.dim() == 2:
         B = B.unsqueeze(0)
+    if not (torch.is_grad_enabled() and (A.requires_grad or B.requires_grad)):
+        # nothing to differentiate: the argmin indices (only the pullback needs them) are not materialised
+        loss, _, _, _ = chamfer_forward_raw(A, B, float(w1), float(w2), batch_total=int(batch_total),
+                                            want_indices=False, flags=int(flags))
+        return loss.reshape(())
     return _ChamferFn.apply(A, B, float(w1), float(w2), int(batch_total), int(flags))
 
 

@@ -52,7 +52,11 @@ enum {
     /* Evaluate squared distances as fma(dz,dz,fma(dy,dy,dx*dx)) instead of the reference's
        ((dx*dx)+(dy*dy))+(dz*dz).  Faster (6 instead of 8 FP32 operations per pair) but NOT the
        reference arithmetic: near-ties may resolve differently.  Off by default. */
-    F3D_FLAG_FMA = 1
+    F3D_FLAG_FMA = 1,
+    /* Measurement aid for f3d_chamfer_fwd: launch only the pairwise sweep kernel (the dominant kernel)
+       and skip the finalize pass, so a caller can bracket exactly that kernel with events.  The outputs
+       are NOT written in this mode. */
+    F3D_FLAG_SWEEP_ONLY = 2
 };
 
 enum {
@@ -93,7 +97,7 @@ F3D_API int32_t f3d_chamfer_bwd(const float* A, const float* Bp, int32_t B, int3
  * kNN graph — replaces CreateSingleKNNGraph + the batch loop / gather / concat prologue of EdgeConv
  * (src/models/dgcnn.jl:3-9 and :32-45).
  *   X [B][N][F]; for every point the K nearest OTHER points = positions 2..K+1 of the (K+1)-NN list
- *   sorted ascending by (squared distance, index).  1 <= K < N, K <= 64, F <= 128.
+ *   sorted ascending by (squared distance, index).  1 <= K < N, K <= 63, F <= 256.
  *   idx [B][N][K] (required); dist [B][N][K] (optional squared distances);
  *   gathered [B][N][K][F] (optional; == the Julia (F,K,N,B) KNNGraph tensor of :36);
  *   edge_feat [B][N][K][2F] (optional; == cat(X, KNNGraph - X; dims=1) of :45).
@@ -117,8 +121,9 @@ F3D_API int32_t f3d_faces_areas_normals(const float* verts, const int32_t* faces
  *   f2e_host [nF][3]      faces→edges, column order (e23,e31,e12)                (:943-949)   (optional)
  *   lap_rowptr_host [nV+1], lap_colidx_host [2nE+nV], lap_vals_host [2nE+nV]: CSR of the Laplacian,
  *                          L[i,i]=-1, L[i,j]=Float32(1/deg i), columns ascending (_compute_laplacian_packed :957-1002)
- *   v2c_rowptr_host [nV+1], v2c_host [3nF]: vertex → incident corners (face*3+slot), ascending — the
- *                          gather form of the scatter at :604-615 (deterministic, no atomics).
+ *   v2c_rowptr_host [nV+1], v2c_host [3nF]: vertex → incident corners (face*3+slot), ordered by
+ *                          (slot, face) — the gather form of the scatter at :604-615 in the order a
+ *                          serial execution applies it (deterministic, no atomics).
  * All pointers are HOST pointers; *nE_host receives the edge count. */
 F3D_API int32_t f3d_mesh_topology_build_host(const int32_t* faces_host, int32_t nV, int32_t nF,
                                      int32_t* edges_host, int32_t* nE_host, int32_t* f2e_host,

@@ -1,0 +1,98 @@
+"""GPU parity of the TriMesh kernels (normals, areas, laplacian_loss, edge_loss) vs the oracle and the
+reference's golden vectors, through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fixtures import (GOLD_FAREAS, GOLD_FNORMALS, GOLD_VNORMALS, MESH3_FACES, MESH3_VERTS, NORMALS_FACES, NORMALS_VERTS,
+                      TEAPOT_LAPLACIAN_LOSS, pack, teapots)
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _meshes(oracle, golden_dir):
+    vt, ft = oracle.load_obj(os.path.join(golden_dir, "teapot.obj"))
+    vs, fs = oracle.load_obj(os.path.join(golden_dir, "sphere.obj"))
+    return [("mesh3", MESH3_VERTS, MESH3_FACES), ("normals", NORMALS_VERTS, NORMALS_FACES), ("teapot", [vt], [ft]),
+            ("teapot+sphere", [vt, vs], [ft, fs]), ("cfg4", *teapots(16, golden_dir, oracle))]
+
+
+def test_reference_goldens(f3d):
+    """test/rep.jl:178-388 — 4-decimal goldens for vertex normals, face normals and face areas."""
+    m = f3d.TriMesh(NORMALS_VERTS, NORMALS_FACES)
+    for mode in (f3d.NORMALS_REFERENCE_CPU, f3d.NORMALS_ACCUMULATE):
+        vn = m.compute_verts_normals_packed(mode).cpu().numpy()
+        assert np.allclose(vn, np.concatenate(GOLD_VNORMALS), rtol=1e-4, atol=1e-4)
+        for got, gold in zip(m.compute_verts_normals_list(mode), GOLD_VNORMALS):
+            assert np.allclose(got.cpu().numpy(), gold, rtol=1e-4, atol=1e-4)
+    assert np.allclose(m.compute_faces_normals_packed().cpu().numpy(), np.concatenate(GOLD_FNORMALS), rtol=1e-4, atol=1e-4)
+    assert np.allclose(m.compute_faces_areas_packed().cpu().numpy(), np.concatenate(GOLD_FAREAS), rtol=1e-4, atol=1e-4)
+    pad = m.compute_verts_normals_padded().cpu().numpy()
+    assert pad.shape == (2, 12, 3) and np.all(pad[1, 5:] == 0)   # rep.jl:303-304
+    fpad = m.compute_faces_areas_padded().cpu().numpy()
+    assert fpad.shape == (2, 4) and np.all(fpad[1, 2:] == 0)
+
+
+def test_normals_areas_bit_exact(f3d, oracle, golden_dir):
+    for name, vl, fl in _meshes(oracle, golden_dir):
+        m = f3d.TriMesh(vl, fl)
+        v, f = pack(vl, fl)
+        areas, fn = oracle.faces_areas_normals(v, f)
+        assert np.array_equal(m.compute_faces_areas_packed().cpu().numpy(), areas), name
+        assert np.array_equal(m.compute_faces_normals_packed().cpu().numpy(), fn), name
+        for mode in (0, 1):
+            got = m.compute_verts_normals_packed(mode).cpu().numpy()
+            assert np.array_equal(got, oracle.verts_normals(v, f, mode)), (name, mode)
+
+
+def test_laplacian_loss(f3d, oracle, golden_dir):
+    for name, vl, fl in _meshes(oracle, golden_dir):
+        m = f3d.TriMesh(vl, fl)
+        v, f = pack(vl, fl)
+        got = float(f3d.laplacian_loss(m).item())
+        ref = float(oracle.laplacian_loss(v, f))
+        assert abs(got - ref) <= RTOL * abs(ref), (name, got, ref)
+    m = f3d.load_trimesh(os.path.join(golden_dir, "teapot.obj"))
+    got = float(f3d.laplacian_loss(m).item())
+    assert abs(got - float(TEAPOT_LAPLACIAN_LOSS)) <= 1e-6 * got  # README.md:111-112
+    # bitwise repeatable (no atomics in the reduction)
+    assert f3d.laplacian_loss(m).item() == got
+
+
+def test_edge_loss(f3d, oracle, golden_dir):
+    for name, vl, fl in _meshes(oracle, golden_dir):
+        m = f3d.TriMesh(vl, fl)
+        v, f = pack(vl, fl)
+        for target in (0.0, 0.05):
+            got = float(f3d.edge_loss(m, target).item())
+            ref = float(oracle.edge_loss(v, f, target))
+            assert abs(got - ref) <= RTOL * abs(ref) + 1e-12, (name, target, got, ref)
+
+
+def test_laplacian_backward(f3d, oracle, golden_dir):
+    """Pullback vs a float64 torch autograd restatement of the same dense expression (the reference's own
+    gradient test only asserts `isa Tuple`, test/metrics.jl:72)."""
+    vt, ft = oracle.load_obj(os.path.join(golden_dir, "teapot.obj"))
+    m = f3d.TriMesh([vt], [ft])
+    verts = m.get_verts_packed().clone().requires_grad_(True)
+    m2 = f3d.TriMesh._from_packed(m, verts)
+    (f3d.laplacian_loss(m2) * 3.0).backward()
+    rowptr, colidx, vals = m.get_laplacian_packed()
+    rows = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
+    Ld = torch.zeros((vt.shape[0], vt.shape[0]), dtype=torch.float64)
+    Ld[torch.from_numpy(rows), torch.from_numpy(colidx.astype(np.int64))] = torch.from_numpy(vals.astype(np.float64))
+    x = torch.from_numpy(vt.astype(np.float64)).requires_grad_(True)
+    ((Ld @ x).norm(dim=1).mean() * 3.0).backward()
+    assert torch.allclose(verts.grad.cpu().double(), x.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_laplacian_sharded_sum(f3d, oracle, golden_dir):
+    """Mesh-axis sharding: shard losses with the global vertex count add up to the batch loss."""
+    vl, fl = teapots(4, golden_dir, oracle)
+    full = float(f3d.laplacian_loss(f3d.TriMesh(vl, fl)).item())
+    tot = sum(v.shape[0] for v in vl)
+    parts = [float(f3d.laplacian_loss(f3d.TriMesh(vl[a:b], fl[a:b]), verts_total=tot).item()) for a, b in ((0, 2), (2, 4))]
+    assert abs(sum(parts) - full) <= 1e-6 * full
