@@ -22,6 +22,8 @@
 // by every warp of the CTA) × 4 warps × cols_per_warp columns staged in shared memory as packed
 // column pairs {x0,x1,y0,y1},{z0,z1} so that one broadcast LDS.128 + LDS.64 feeds 16 pair distances
 // per lane.
+#include <algorithm>
+
 #include "f3d_common.cuh"
 
 namespace f3d {
@@ -31,8 +33,14 @@ constexpr int kRowsPerLane = 8;
 constexpr int kTileRows = 32 * kRowsPerLane;  // 256
 constexpr int kWarps = 4;
 constexpr int kThreads = 32 * kWarps;
-constexpr int kChunk = 32;         // columns per argmin-locator chunk
-constexpr int kMaxColsPerWarp = 256;
+#ifndef F3D_CHUNK
+#define F3D_CHUNK 32
+#endif
+constexpr int kChunk = F3D_CHUNK;  // columns per argmin-locator chunk
+#ifndef F3D_MAXCPW
+#define F3D_MAXCPW 256
+#endif
+constexpr int kMaxColsPerWarp = F3D_MAXCPW;
 constexpr float kPadA = 1.0e18f;   // padded rows / columns sit ~1e18 apart from everything:
 constexpr float kPadB = -1.0e18f;  // d ≈ 1e37 (finite), never a minimum for in-contract inputs
 
@@ -319,12 +327,527 @@ size_t sweep_smem_bytes(int BN) {
            (size_t)kWarps * kTileRows * (sizeof(float) + sizeof(int));
 }
 
+
+// =====================================================================================================
+// Filtered sweep (default path).  Same result, bit for bit, as the exact sweep above — obtained with
+// about half the FP32 work per pair:
+//
+//   1. FILTER.  Every pair gets an approximate squared distance in the expanded form on centred points
+//        f_ij = ((nb_j - 2 a'x b'x) - 2 a'y b'y) - 2 a'z b'z + na_i        (3 FFMA2 + 1 FADD2 per TWO pairs)
+//      a' = a - c, b' = b - c (c: a centre of the batch element), na = |a'|², nb = |b'|².  The exact form
+//      needs 3 FADD2 + 3 FMUL2 + 4 FADD per two pairs.  |f_ij - d_ij| <= 15.03u (na_i + nb_j) + 5.001u d_ij, d_ij the
+//      reference-arithmetic distance, u = 2^-24 (derivation in DESIGN.md §3.1: 11.02u from the filter's own
+//      roundings incl. the norms, 4.01u from centring, 5.001u relative from the reference's roundings).
+//   2. LOCATE.  Rows keep, per column split, (b1, c1, b2): the filter minimum, the 32-column chunk where
+//      it was first reached, and the minimum over all OTHER chunks.  Columns keep, per 256-row block,
+//      the REDUX minimum m and the ballot of lanes (8 rows each) whose minimum is within the window of m.
+//   3. CERTIFY + RESCAN (finalize).  If every filter value outside the located chunk / lanes exceeds the
+//      located minimum b1 by more than kWinAbs (na+nb) + kWinRel b1, the exact argmin (with the lowest-index tie rule) provably lies
+//      inside: those <=32 / <=8 candidates are re-evaluated in the reference arithmetic.  Otherwise
+//      (~0.2 % of rows on uniform clouds; every row of tie-heavy inputs) every tile whose filter minimum is
+//      within the window is re-evaluated exactly.  Every reported index and distance therefore comes from the exact arithmetic.
+// =====================================================================================================
+// Certificate constants: |f - d| <= 15.03u (na+nb) + 5.001u d with u = 2^-24, hence "every value
+// outside the located set exceeds the located minimum b1 by more than  kWinAbs (na+nb) + kWinRel b1" proves the
+// exact argmin is inside it (30.1u = 1.794e-6 <= kWinAbs, 10.01u = 5.97e-7 <= kWinRel).
+constexpr float kWinAbs = 2.0e-6f;
+constexpr float kWinRel = 6.2e-7f;
+// in-sweep lane ballot: the same window plus 15.1u (na+nb) of slack because REDUX on raw bit patterns may return
+// any of several slightly negative values (all clamp to 0); applied as thr = m * kBallotRel + kBallotAbs (na+nb)
+constexpr float kBallotAbs = 3.0e-6f;   // >= 45.2u = 2.69e-6
+constexpr float kBallotRel = 1.0000007f;  // >= 1 + 10.01u
+constexpr float kPadF = 3.0e38f;     // padded rows / columns: filter value ~3e38 (or +inf), never a minimum
+constexpr float kNormLimit = 1.0e29f;  // above this the filter arithmetic could overflow: certify nothing
+
+struct FiltParams {
+    const float* A;
+    const float* Bp;
+    int N, M;
+    int cols_per_warp, CS, RB, Npad, Mpad;
+    float4* rowpart;   // [B][CS][Npad] {b1, b2, c1 (int bits), -}
+    uint2* colpart;    // [B][RB][Mpad] {m (float bits, may be slightly negative), lane ballot}
+    float* maxna;      // [B][RB]  max |a'|² over the valid rows of the block
+    float* maxnb;      // [B][CS]  max |b'|² over the valid columns of the tile
+    float* centre;     // [B][4]   the centre used for this batch element (finalize recomputes |a'|², |b'|² with it)
+    unsigned* counter;
+};
+
+// The centre of a batch element is the mean of 32 + 32 strided sample points.  ANY point works (the bound uses the
+// norms actually obtained); every warp of every CTA of the element computes the same value with the same operations.
+
+#ifdef F3D_EXP_CLOCK
+__device__ long long g_dbg[8 * 8192];
+#define DBG_T(k) do { if (tid == 0) { long long c_ = clock64(); unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); int id_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; if (id_ < 8192) { g_dbg[id_ * 8 + (k)] = c_; if ((k) == 0) { g_dbg[id_ * 8 + 4] = (long long)g_; unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_dbg[id_ * 8 + 6] = sm_; } if ((k) == 3) g_dbg[id_ * 8 + 5] = (long long)g_; } } } while (0)
+#else
+#define DBG_T(k)
+#endif
+#ifndef F3D_FILT_MINB
+#define F3D_FILT_MINB 4
+#endif
+#ifndef F3D_FILT_UNROLL
+#define F3D_FILT_UNROLL 2
+#endif
+__global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_kernel(FiltParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int BN = kWarps * p.cols_per_warp;
+    float4* s_xy = reinterpret_cast<float4*>(smem_raw);          // [BN/2] {-2x0,-2x1,-2y0,-2y1}
+    float4* s_zn = s_xy + BN / 2;                                // [BN/2] {-2z0,-2z1,nb0,nb1}
+    float4* s_row = s_zn + BN / 2;                               // [kWarps][kTileRows] {b1,b2,c1,-}; first used as s_rm
+    __shared__ unsigned s_maxnb;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cs = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
+    const int col0 = cs * BN, row0 = rb * kTileRows;
+    const float* gA = p.A + (size_t)b * p.N * 3;
+    const float* gB = p.Bp + (size_t)b * p.M * 3;
+
+    DBG_T(0);
+    if (tid == 0 && cs == 0 && rb == 0 && b == 0) *p.counter = 0u;
+    if (tid == 0) s_maxnb = 0u;
+
+    // ---- prologue: issue EVERY global load first (centre samples, this thread's column pairs, this lane's rows),
+    // so the CTA pays one memory latency instead of one per dependent step -------------------------------------
+    constexpr int kMaxPairsPerThread = kMaxColsPerWarp * kWarps / 2 / kThreads;  // 4
+    const int ia = (int)(((long)lane * p.N) >> 5), ib = (int)(((long)lane * p.M) >> 5);
+    const float sx = __ldg(gA + 3 * ia) + __ldg(gB + 3 * ib);
+    const float sy = __ldg(gA + 3 * ia + 1) + __ldg(gB + 3 * ib + 1);
+    const float sz = __ldg(gA + 3 * ia + 2) + __ldg(gB + 3 * ib + 2);
+    float rawc[kMaxPairsPerThread][6];
+#pragma unroll
+    for (int k = 0; k < kMaxPairsPerThread; ++k) {
+        const int pp = tid + k * kThreads;
+        const int j = col0 + 2 * pp;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) rawc[k][e] = (pp < BN / 2 && j + e / 3 < p.M) ? __ldg(gB + 3 * (size_t)j + e) : 0.0f;
+    }
+    float ax[kRowsPerLane], ay[kRowsPerLane], az[kRowsPerLane], na[kRowsPerLane];
+#pragma unroll
+    for (int r = 0; r < kRowsPerLane; ++r) {
+        const int i = row0 + lane * kRowsPerLane + r;
+        const bool ok = i < p.N;
+        ax[r] = ok ? __ldg(gA + 3 * (size_t)i) : 0.0f;
+        ay[r] = ok ? __ldg(gA + 3 * (size_t)i + 1) : 0.0f;
+        az[r] = ok ? __ldg(gA + 3 * (size_t)i + 2) : 0.0f;
+    }
+    // the centre of the batch element: every warp computes it redundantly (same operations => same bits)
+    float cx = sx, cy = sy, cz = sz;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cx += __shfl_xor_sync(0xffffffffu, cx, o);
+        cy += __shfl_xor_sync(0xffffffffu, cy, o);
+        cz += __shfl_xor_sync(0xffffffffu, cz, o);
+    }
+    cx *= (1.0f / 64.0f); cy *= (1.0f / 64.0f); cz *= (1.0f / 64.0f);
+    if (tid == 0 && cs == 0 && rb == 0) { p.centre[4 * b] = cx; p.centre[4 * b + 1] = cy; p.centre[4 * b + 2] = cz; }
+    __syncthreads();  // s_maxnb = 0 visible
+
+    // ---- stage the column tile: centred, pre-scaled by -2, with |b'|² -----------------------------------
+    {
+        float mynb = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kMaxPairsPerThread; ++k) {
+            const int pp = tid + k * kThreads;
+            if (pp < BN / 2) {
+                const int j = col0 + 2 * pp;
+                float x0 = 0.f, y0 = 0.f, z0 = 0.f, n0 = kPadF, x1 = 0.f, y1 = 0.f, z1 = 0.f, n1 = kPadF;
+                if (j < p.M) {
+                    x0 = rawc[k][0] - cx; y0 = rawc[k][1] - cy; z0 = rawc[k][2] - cz;
+                    n0 = fmaf(z0, z0, fmaf(y0, y0, x0 * x0));
+                    mynb = fmaxf(mynb, n0);
+                }
+                if (j + 1 < p.M) {
+                    x1 = rawc[k][3] - cx; y1 = rawc[k][4] - cy; z1 = rawc[k][5] - cz;
+                    n1 = fmaf(z1, z1, fmaf(y1, y1, x1 * x1));
+                    mynb = fmaxf(mynb, n1);
+                }
+                s_xy[pp] = make_float4(-2.0f * x0, -2.0f * x1, -2.0f * y0, -2.0f * y1);
+                s_zn[pp] = make_float4(-2.0f * z0, -2.0f * z1, n0, n1);
+            }
+        }
+        mynb = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mynb)));  // norms are >= 0
+        if (lane == 0) atomicMax(&s_maxnb, __float_as_uint(mynb));
+    }
+    // ---- this lane's 8 rows: centred coordinates and |a'|² ------------------------------------------------
+    float myna = 0.0f;
+#pragma unroll
+    for (int r = 0; r < kRowsPerLane; ++r) {
+        const int i = row0 + lane * kRowsPerLane + r;
+        if (i < p.N) {
+            ax[r] -= cx; ay[r] -= cy; az[r] -= cz;
+            na[r] = fmaf(az[r], az[r], fmaf(ay[r], ay[r], ax[r] * ax[r]));
+            myna = fmaxf(myna, na[r]);
+        } else {
+            ax[r] = 0.f; ay[r] = 0.f; az[r] = 0.f; na[r] = kPadF;
+        }
+    }
+    const float maxna = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(myna)));
+    __syncthreads();
+    const float maxnb = __uint_as_float(s_maxnb);
+    if (tid == 0) {
+        p.maxnb[(size_t)b * p.CS + cs] = maxnb;
+        if (cs == 0) p.maxna[(size_t)b * p.RB + rb] = maxna;
+    }
+    const float wt = kBallotAbs * (maxna + maxnb);
+
+    const int wp0 = warp * (p.cols_per_warp / 2);
+    const int nchunks = p.cols_per_warp / kChunk;
+    const int gchunk0 = (col0 + warp * p.cols_per_warp) / kChunk;
+    // column partials {m0, ballot0, m1, ballot1} go straight to global memory (lane 0, 16 B per column pair): a
+    // shared-memory store here would order against the next pair's LDS and stop the compiler from overlapping
+    // one pair's min/REDUX tail with the next pair's FFMA2s.
+    uint4* __restrict__ gcol4 = reinterpret_cast<uint4*>(p.colpart + ((size_t)b * p.RB + rb) * p.Mpad + col0);
+    // per-chunk row minima are parked in shared memory ([warp][chunk][r][lane], conflict-free) and turned into
+    // (b1, c1, b2) after the sweep: keeping that state out of the loop's registers lets ptxas emit the FFMA2s
+    // stage by stage with operand reuse (each FFMA2 then reads <= 2 registers per bank; the row-by-row order it
+    // picks under register pressure costs 3 cycles per FFMA2 instead of 2 — profiles/r01b notes).
+    float* s_rm = reinterpret_cast<float*>(s_row) + (size_t)warp * nchunks * kTileRows;
+    DBG_T(1);
+#ifdef F3D_EXP_REPEAT
+    for (int rep = 0; rep < F3D_EXP_REPEAT; ++rep)
+#endif
+    for (int ch = 0; ch < nchunks; ++ch) {
+        float rm[kRowsPerLane];
+#pragma unroll
+        for (int r = 0; r < kRowsPerLane; ++r) rm[r] = INFINITY;
+#pragma unroll 2
+        for (int q = 0; q < kChunk / 2; ++q) {
+            const int pp = wp0 + ch * (kChunk / 2) + q;
+            const float4 xy = s_xy[pp];
+            const float4 zn = s_zn[pp];
+            const u64 X2 = pack2(xy.x, xy.y), Y2 = pack2(xy.z, xy.w), Z2 = pack2(zn.x, zn.y), NB = pack2(zn.z, zn.w);
+            u64 t[kRowsPerLane];
+#pragma unroll
+            for (int r = 0; r < kRowsPerLane; ++r) t[r] = fma2(X2, pack2(ax[r], ax[r]), NB);
+#pragma unroll
+            for (int r = 0; r < kRowsPerLane; ++r) t[r] = fma2(Y2, pack2(ay[r], ay[r]), t[r]);
+#pragma unroll
+            for (int r = 0; r < kRowsPerLane; ++r) t[r] = fma2(Z2, pack2(az[r], az[r]), t[r]);
+            float c0 = INFINITY, c1v = INFINITY;
+#pragma unroll
+            for (int r = 0; r < kRowsPerLane; ++r) {
+                float f0, f1;
+                unpack2(add2(t[r], pack2(na[r], na[r])), f0, f1);
+                rm[r] = fminf(rm[r], fminf(f0, f1));
+                c0 = fminf(c0, f0);
+                c1v = fminf(c1v, f1);
+            }
+#ifdef F3D_EXP_NOCOL
+            if (c0 + c1v == 123.0f) gcol4[pp] = make_uint4(1, 2, 3, 4);
+#else
+            const int m0 = __reduce_min_sync(0xffffffffu, __float_as_int(c0));
+            const int m1 = __reduce_min_sync(0xffffffffu, __float_as_int(c1v));
+            const unsigned bal0 = __ballot_sync(0xffffffffu, c0 <= fmaf(__int_as_float(m0), kBallotRel, wt));
+            const unsigned bal1 = __ballot_sync(0xffffffffu, c1v <= fmaf(__int_as_float(m1), kBallotRel, wt));
+            if (lane == 0) gcol4[pp] = make_uint4((unsigned)m0, bal0, (unsigned)m1, bal1);
+#endif
+        }
+#pragma unroll
+        for (int r = 0; r < kRowsPerLane; ++r) s_rm[(ch * kRowsPerLane + r) * 32 + lane] = rm[r];
+    }
+
+    // ---- (b1, c1, b2) per row over this warp's chunks: minimum, the EARLIEST chunk reaching it, and the minimum
+    // over the other chunks (each lane reads back only what it stored) ----------------------------------------
+    float b1[kRowsPerLane], b2[kRowsPerLane];
+    int c1[kRowsPerLane];
+#pragma unroll
+    for (int r = 0; r < kRowsPerLane; ++r) { b1[r] = INFINITY; b2[r] = INFINITY; c1[r] = 0; }
+    for (int ch = 0; ch < nchunks; ++ch) {
+#pragma unroll
+        for (int r = 0; r < kRowsPerLane; ++r) {
+            const float cm = s_rm[(ch * kRowsPerLane + r) * 32 + lane];
+            b2[r] = fminf(b2[r], fmaxf(b1[r], cm));
+            if (cm < b1[r]) c1[r] = gchunk0 + ch;
+            b1[r] = fminf(b1[r], cm);
+        }
+    }
+    __syncthreads();  // s_row below aliases the s_rm regions of all warps
+
+    DBG_T(2);
+    // ---- merge the 4 warps' row triples (ascending column order), store the partials ----------------------
+#pragma unroll
+    for (int r = 0; r < kRowsPerLane; ++r)
+        s_row[warp * kTileRows + lane * kRowsPerLane + r] = make_float4(b1[r], b2[r], __int_as_float(c1[r]), 0.f);
+    __syncthreads();
+    {
+        const size_t base = ((size_t)b * p.CS + cs) * p.Npad + row0;
+        for (int rr = tid; rr < kTileRows; rr += kThreads) {
+            float4 best = s_row[rr];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) {
+                const float4 o = s_row[w * kTileRows + rr];
+                if (o.x < best.x) { best.y = fminf(best.x, o.y); best.x = o.x; best.z = o.z; }
+                else best.y = fminf(best.y, o.x);
+            }
+            p.rowpart[base + rr] = best;
+        }
+    }
+    DBG_T(3);
+}
+
+// ---- finalize for the filtered sweep: certify, rescan exactly, reduce the loss ------------------------------
+struct FiltFinalizeParams {
+    const float* A;
+    const float* Bp;
+    int B, N, M, CS, RB, Npad, Mpad, BN;
+    const float4* rowpart;
+    const uint2* colpart;
+    const float* maxna;
+    const float* maxnb;
+    const float* centre;
+    int32_t* nnA;
+    int32_t* nnB;
+    double* partial;
+    unsigned* counter;
+    int nbA, nbB;
+    float w1, w2;
+    double denomA, denomB;
+    float* loss;
+    float* terms;
+};
+
+// exact (reference-arithmetic) argmin of |q - P[j]|² over j in [j0, j1), cooperatively by one warp, merged into the
+// running (dmin, jmin) with the lowest-index tie rule.  q is warp-uniform; the result is valid in every lane.
+__device__ __forceinline__ void warp_exact_scan(const float* __restrict__ P, int j0, int j1, float qx, float qy, float qz,
+                                                bool q_is_row, int lane, float& dmin, int& jmin) {
+    float best = INFINITY;
+    int bj = 0x7fffffff;
+    // 4 candidates per lane per trip, all 12 loads issued before the arithmetic (this loop is latency-bound:
+    // the warps that hit an ambiguous item set the kernel's tail)
+    for (int j = j0 + lane; j < j1; j += 128) {
+        float px[4], py[4], pz[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int jj = min(j + 32 * k, j1 - 1);  // clamped duplicates are harmless (same value, higher or equal index)
+            px[k] = __ldg(P + 3 * (size_t)jj); py[k] = __ldg(P + 3 * (size_t)jj + 1); pz[k] = __ldg(P + 3 * (size_t)jj + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // operand order of the reference: (a - b) with a from the first cloud
+            const float d = q_is_row ? sqdist3<false>(qx, qy, qz, px[k], py[k], pz[k]) : sqdist3<false>(px[k], py[k], pz[k], qx, qy, qz);
+            const int jj = min(j + 32 * k, j1 - 1);
+            if (d < best || (d == best && jj < bj)) { best = d; bj = jj; }
+        }
+    }
+    const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(best));  // d >= 0: bit order == value order
+    const int cand = (__float_as_uint(best) == mb) ? bj : 0x7fffffff;
+    const int jm = __reduce_min_sync(0xffffffffu, cand);
+    const float dm = __uint_as_float(mb);
+    if (dm < dmin || (dm == dmin && jm < jmin)) { dmin = dm; jmin = jm; }
+}
+
+// (d, j) minimum over the 8 lanes of a group (lowest j on ties); every lane of the group gets the result
+__device__ __forceinline__ void group8_argmin(float& d, int& j) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, d, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, j, o);
+        if (od < d || (od == d && oj < j)) { d = od; j = oj; }
+    }
+}
+
+// Block = 8 warps; a warp owns 32 consecutive items (rows of A, or columns = points of B).
+//   phase 1  lane <-> item: merge the sweep's partials, decide "certified" vs "ambiguous"
+//   phase 2  8 passes x 4 items: 8 lanes per item re-evaluate the located candidates exactly
+//   phase 3  the (rare) ambiguous items, one at a time, whole warp: exact scan of every tile within the window
+__global__ void __launch_bounds__(kFinThreads) chamfer_filter_finalize_kernel(FiltFinalizeParams p) {
+    __shared__ double s_red[kFinThreads / 32];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = lane >> 3, sub = lane & 7;
+    const bool rows = (int)blockIdx.x < p.nbA;
+    const long t = ((long)(rows ? blockIdx.x : blockIdx.x - p.nbA) * (kFinThreads / 32) + warp) * 32 + lane;
+    const int Q = rows ? p.N : p.M;        // items per batch element (queries)
+    const int R = rows ? p.M : p.N;        // points searched per query
+    const float* gQ = rows ? p.A : p.Bp;   // queries
+    const float* gP = rows ? p.Bp : p.A;   // searched cloud
+    const bool valid = t < (long)p.B * Q;
+    double mine = 0.0;
+
+    // ---- phase 1 -------------------------------------------------------------------------------------------------
+    int b = 0, q = 0, loc = 0;     // loc: chunk id (rows) or row block (columns)
+    unsigned bal = 0u;             // columns: lane ballot of the located block
+    float best = 0.0f, win = 0.0f; // clamped filter minimum and the certificate window
+    bool amb = false;
+    if (valid) {
+        b = (int)(t / Q); q = (int)(t - (long)b * Q);
+        const float* c = p.centre + 4 * b;
+        const float* pt = gQ + ((size_t)b * Q + q) * 3;
+        const float x = __ldg(pt) - __ldcg(c), y = __ldg(pt + 1) - __ldcg(c + 1), z = __ldg(pt + 2) - __ldcg(c + 2);
+        const float nq = fmaf(z, z, fmaf(y, y, x * x));  // the sweep's |a'|² / |b'|², bit for bit
+        float second = INFINITY, other = 0.0f;
+        best = INFINITY;
+        if (rows) {
+            for (int cs = 0; cs < p.CS; ++cs) {
+                const float4 e = __ldcg(p.rowpart + ((size_t)b * p.CS + cs) * p.Npad + q);
+                const float e1 = fmaxf(e.x, 0.0f), e2 = fmaxf(e.y, 0.0f);
+                other = fmaxf(other, __ldcg(p.maxnb + (size_t)b * p.CS + cs));
+                if (e1 < best) { second = fminf(best, e2); best = e1; loc = __float_as_int(e.z); }
+                else second = fminf(second, e1);
+            }
+        } else {
+            for (int rb = 0; rb < p.RB; ++rb) {
+                const uint2 e = __ldcg(p.colpart + ((size_t)b * p.RB + rb) * p.Mpad + q);
+                const float v = fmaxf(__uint_as_float(e.x), 0.0f);
+                other = fmaxf(other, __ldcg(p.maxna + (size_t)b * p.RB + rb));
+                if (v < best) { second = best; best = v; loc = rb; bal = e.y; }
+                else second = fminf(second, v);
+            }
+        }
+        win = fmaf(kWinRel, best, kWinAbs * (nq + other));
+        // written so that NaN / inf / out-of-range norms can only make the item ambiguous, never certified
+        amb = !(nq <= kNormLimit && other <= kNormLimit && second > best + win);
+    }
+
+    // ---- phase 2: certified items, 4 per pass ---------------------------------------------------------------------
+    for (int pass = 0; pass < 8; ++pass) {
+        const int src = pass * 4 + grp;
+        const int bb = __shfl_sync(0xffffffffu, b, src), qq = __shfl_sync(0xffffffffu, q, src);
+        const int ll = __shfl_sync(0xffffffffu, loc, src);
+        unsigned bits = __shfl_sync(0xffffffffu, bal, src);
+        const bool go = __shfl_sync(0xffffffffu, (int)(valid && !amb), src) != 0;
+        const float* qp = gQ + ((size_t)bb * Q + qq) * 3;
+        const float* P = gP + (size_t)bb * R * 3;
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        if (go) { qx = __ldg(qp); qy = __ldg(qp + 1); qz = __ldg(qp + 2); }
+        float d = INFINITY;
+        int j = 0x7fffffff;
+        if (rows) {
+            if (go) {
+#pragma unroll
+                for (int k = 0; k < kChunk / 8; ++k) {
+                    const int jj = ll * kChunk + sub * (kChunk / 8) + k;
+                    if (jj < R) {
+                        const float dd = sqdist3<false>(qx, qy, qz, __ldg(P + 3 * (size_t)jj), __ldg(P + 3 * (size_t)jj + 1),
+                                                        __ldg(P + 3 * (size_t)jj + 2));
+                        if (dd < d) { d = dd; j = jj; }
+                    }
+                }
+            }
+        } else {
+            if (!go) bits = 0u;
+            while (__any_sync(0xffffffffu, bits != 0u)) {  // one ballot bit (8 rows) per trip; almost always one trip
+                if (bits) {
+                    const int ii = ll * kTileRows + (__ffs(bits) - 1) * kRowsPerLane + sub;
+                    bits &= bits - 1;
+                    if (ii < R) {
+                        const float dd = sqdist3<false>(__ldg(P + 3 * (size_t)ii), __ldg(P + 3 * (size_t)ii + 1),
+                                                        __ldg(P + 3 * (size_t)ii + 2), qx, qy, qz);
+                        if (dd < d) { d = dd; j = ii; }  // candidates of one lane ascend, so '<' keeps the lowest index
+                    }
+                }
+            }
+        }
+        group8_argmin(d, j);
+        if (go && sub == 0) {
+            int32_t* nn = rows ? p.nnA : p.nnB;
+            if (nn) nn[(size_t)bb * Q + qq] = j;
+            mine += (double)d;
+        }
+    }
+
+    // ---- phase 3: ambiguous items --------------------------------------------------------------------------------
+    for (unsigned rem = __ballot_sync(0xffffffffu, valid && amb); rem; rem &= rem - 1) {
+        const int src = __ffs(rem) - 1;
+        const int bb = __shfl_sync(0xffffffffu, b, src), qq = __shfl_sync(0xffffffffu, q, src);
+        const float lim = __shfl_sync(0xffffffffu, best + win, src);  // NaN/inf → scan everything (comparison below)
+        const float* qp = gQ + ((size_t)bb * Q + qq) * 3;
+        const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        const float* P = gP + (size_t)bb * R * 3;
+        float d = INFINITY;
+        int j = 0x7fffffff;
+        if (rows) {
+            for (int cs = 0; cs < p.CS; ++cs) {
+                const float e1 = fmaxf(__ldcg(&p.rowpart[((size_t)bb * p.CS + cs) * p.Npad + qq].x), 0.0f);
+                if (!(e1 > lim)) warp_exact_scan(P, cs * p.BN, min((cs + 1) * p.BN, R), qx, qy, qz, true, lane, d, j);
+            }
+        } else {
+            for (int rb = 0; rb < p.RB; ++rb) {
+                const float v = fmaxf(__uint_as_float(__ldcg(&p.colpart[((size_t)bb * p.RB + rb) * p.Mpad + qq].x)), 0.0f);
+                if (!(v > lim)) warp_exact_scan(P, rb * kTileRows, min((rb + 1) * kTileRows, R), qx, qy, qz, false, lane, d, j);
+            }
+        }
+        if (lane == 0) {
+            int32_t* nn = rows ? p.nnA : p.nnB;
+            if (nn) nn[(size_t)bb * Q + qq] = j;
+            mine += (double)d;
+        }
+    }
+
+    // ---- block partial sum → last block reduces in a fixed order (deterministic) ------------------------------
+    mine = warp_sum(mine);
+    if (lane == 0) s_red[warp] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < kFinThreads / 32; ++w) s += s_red[w];
+        p.partial[blockIdx.x] = s;
+        __threadfence();
+        s_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double sa = 0.0, sb = 0.0;
+    for (int k = tid; k < p.nbA; k += kFinThreads) sa += __ldcg(p.partial + k);
+    for (int k = tid; k < p.nbB; k += kFinThreads) sb += __ldcg(p.partial + p.nbA + k);
+    sa = warp_sum(sa);
+    sb = warp_sum(sb);
+    __shared__ double s_a[kFinThreads / 32], s_b[kFinThreads / 32];
+    if (lane == 0) { s_a[warp] = sa; s_b[warp] = sb; }
+    __syncthreads();
+    if (tid == 0) {
+        double ta = 0.0, tb = 0.0;
+        for (int w = 0; w < kFinThreads / 32; ++w) { ta += s_a[w]; tb += s_b[w]; }
+        const float dAB = (float)(ta / p.denomA), dBA = (float)(tb / p.denomB);  // pcloud.jl:47-48
+        if (p.terms) { p.terms[0] = dAB; p.terms[1] = dBA; }
+        p.loss[0] = __fadd_rn(__fmul_rn(p.w1, dAB), __fmul_rn(p.w2, dBA));      // pcloud.jl:50
+    }
+}
+
+struct FiltPlan {
+    int cols_per_warp, BN, CS, RB, Npad, Mpad, nbA, nbB;
+    size_t off_rowpart, off_colpart, off_maxna, off_maxnb, off_centre, off_partial, off_counter, total;
+};
+
+FiltPlan make_filt_plan(int B, int N, int M) {
+    FiltPlan pl;
+    int cpw = (int)align_up((size_t)(M + kWarps - 1) / kWarps, kChunk);
+    if (cpw > kMaxColsPerWarp) cpw = kMaxColsPerWarp;
+    pl.cols_per_warp = cpw;
+    pl.BN = kWarps * cpw;
+    pl.CS = (M + pl.BN - 1) / pl.BN;
+    pl.RB = (N + kTileRows - 1) / kTileRows;
+    pl.Npad = pl.RB * kTileRows;
+    pl.Mpad = pl.CS * pl.BN;
+    pl.nbA = (int)(((long)B * N + kFinThreads - 1) / kFinThreads);
+    pl.nbB = (int)(((long)B * M + kFinThreads - 1) / kFinThreads);
+    size_t o = 0;
+    pl.off_rowpart = o; o = align_up(o + sizeof(float4) * (size_t)B * pl.CS * pl.Npad, 256);
+    pl.off_colpart = o; o = align_up(o + sizeof(uint2) * (size_t)B * pl.RB * pl.Mpad, 256);
+    pl.off_maxna = o;   o = align_up(o + sizeof(float) * (size_t)B * pl.RB, 256);
+    pl.off_maxnb = o;   o = align_up(o + sizeof(float) * (size_t)B * pl.CS, 256);
+    pl.off_centre = o;  o = align_up(o + sizeof(float) * 4 * (size_t)B, 256);
+    pl.off_partial = o; o = align_up(o + sizeof(double) * (size_t)(pl.nbA + pl.nbB), 256);
+    pl.off_counter = o; o = align_up(o + sizeof(unsigned), 256);
+    pl.total = o;
+    return pl;
+}
+
+size_t filt_smem_bytes(int BN) {
+    const size_t rm_bytes = (size_t)(BN / kChunk) * kTileRows * sizeof(float);  // [kWarps][chunks per warp][8][32]
+    return (size_t)(BN / 2) * (2 * sizeof(float4)) + std::max(rm_bytes, (size_t)kWarps * kTileRows * sizeof(float4));
+}
+
 }  // namespace
 }  // namespace f3d
 
+#ifdef F3D_EXP_CLOCK
+extern "C" __attribute__((visibility("default"))) int f3d_debug_read(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, f3d::g_dbg, nbytes); }
+#endif
+
 extern "C" size_t f3d_chamfer_workspace_bytes(int32_t B, int32_t N, int32_t M) {
     if (B <= 0 || N <= 0 || M <= 0) return 0;
-    return f3d::make_plan(B, N, M).total;
+    return std::max(f3d::make_plan(B, N, M).total, f3d::make_filt_plan(B, N, M).total);
 }
 
 extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M,
@@ -337,13 +860,50 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
     if (B > 65535) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: B must be <= 65535 per call");
     if (B_total == 0) B_total = B;
     if (B_total < B) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: B_total (%d) < B (%d)", B_total, B);
-    Plan pl = make_plan(B, N, M);
-    if (!ws || ws_bytes < pl.total) return fail(F3D_ERR_WORKSPACE, "f3d_chamfer_fwd: workspace %zu < required %zu bytes", ws_bytes, pl.total);
+    const size_t need = f3d_chamfer_workspace_bytes(B, N, M);
+    if (!ws || ws_bytes < need) return fail(F3D_ERR_WORKSPACE, "f3d_chamfer_fwd: workspace %zu < required %zu bytes", ws_bytes, need);
     if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0) return fail(F3D_ERR_MISALIGNED, "f3d_chamfer_fwd: workspace must be 256-byte aligned");
-    if (pl.RB > 65535) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: N too large");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     unsigned char* w = static_cast<unsigned char*>(ws);
     const bool fma = (flags & F3D_FLAG_FMA) != 0;
+
+    if (!fma && !(flags & F3D_FLAG_EXACT_SWEEP)) {
+        // ---- default: filtered sweep + certified exact finalize (bit-identical results, ~half the FP32 work) ----
+        FiltPlan fl = make_filt_plan(B, N, M);
+        if (fl.RB > 65535) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: N too large");
+        FiltParams sp;
+        sp.A = A; sp.Bp = Bp; sp.N = N; sp.M = M;
+        sp.cols_per_warp = fl.cols_per_warp; sp.CS = fl.CS; sp.RB = fl.RB; sp.Npad = fl.Npad; sp.Mpad = fl.Mpad;
+        sp.rowpart = reinterpret_cast<float4*>(w + fl.off_rowpart);
+        sp.colpart = reinterpret_cast<uint2*>(w + fl.off_colpart);
+        sp.maxna = reinterpret_cast<float*>(w + fl.off_maxna);
+        sp.maxnb = reinterpret_cast<float*>(w + fl.off_maxnb);
+        sp.centre = reinterpret_cast<float*>(w + fl.off_centre);
+        sp.counter = reinterpret_cast<unsigned*>(w + fl.off_counter);
+        const size_t smem = filt_smem_bytes(fl.BN);
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_filter_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chamfer_filter_sweep_kernel<<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
+        F3D_CHECK_LAUNCH("chamfer_filter_sweep_kernel");
+        if (flags & F3D_FLAG_SWEEP_ONLY) return F3D_OK;
+        FiltFinalizeParams fp;
+        fp.A = A; fp.Bp = Bp; fp.B = B; fp.N = N; fp.M = M;
+        fp.CS = fl.CS; fp.RB = fl.RB; fp.Npad = fl.Npad; fp.Mpad = fl.Mpad; fp.BN = fl.BN;
+        fp.rowpart = sp.rowpart; fp.colpart = sp.colpart; fp.maxna = sp.maxna; fp.maxnb = sp.maxnb; fp.centre = sp.centre;
+        fp.nnA = nnA_dev; fp.nnB = nnB_dev;
+        fp.partial = reinterpret_cast<double*>(w + fl.off_partial);
+        fp.counter = sp.counter;
+        fp.nbA = fl.nbA; fp.nbB = fl.nbB;
+        fp.w1 = w1; fp.w2 = w2;
+        fp.denomA = (double)N * (double)B_total;
+        fp.denomB = (double)M * (double)B_total;
+        fp.loss = loss_dev; fp.terms = terms_dev;
+        chamfer_filter_finalize_kernel<<<fl.nbA + fl.nbB, kFinThreads, 0, stream>>>(fp);
+        F3D_CHECK_LAUNCH("chamfer_filter_finalize_kernel");
+        return F3D_OK;
+    }
+
+    Plan pl = make_plan(B, N, M);
+    if (pl.RB > 65535) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: N too large");
 
     SweepParams sp;
     sp.A = A; sp.Bp = Bp; sp.N = N; sp.M = M;

@@ -12,6 +12,7 @@ from .pcloud import PointCloud, as_f32_tensor
 FLAG_NONE = 0
 FLAG_FMA = 1  # non-reference arithmetic (fused multiply-add distances); see include/flux3d_b200.h
 FLAG_SWEEP_ONLY = 2  # measurement aid: launch only the sweep kernel
+FLAG_EXACT_SWEEP = 4  # every pair in the reference arithmetic (cross-check of the default filtered sweep)
 
 _workspace = _lib.workspace
 _stream_ptr = _lib.stream_ptr

@@ -56,7 +56,11 @@ enum {
     /* Measurement aid for f3d_chamfer_fwd: launch only the pairwise sweep kernel (the dominant kernel)
        and skip the finalize pass, so a caller can bracket exactly that kernel with events.  The outputs
        are NOT written in this mode. */
-    F3D_FLAG_SWEEP_ONLY = 2
+    F3D_FLAG_SWEEP_ONLY = 2,
+    /* f3d_chamfer_fwd: evaluate EVERY pair in the reference arithmetic (the original exact sweep) instead
+       of the default filter + certified exact re-evaluation.  Both produce bit-identical results; this
+       one does not depend on the filter's error bound and is kept as the cross-check. */
+    F3D_FLAG_EXACT_SWEEP = 4
 };
 
 enum {

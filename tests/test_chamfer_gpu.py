@@ -18,9 +18,16 @@ def _run(f3d, A, B, w1=1.0, w2=1.0, flags=0):
     return float(loss.item()), terms.cpu().numpy(), nnA.cpu().numpy(), nnB.cpu().numpy()
 
 
-def _check(f3d, oracle, A, B, w1=1.0, w2=1.0):
-    loss, terms, nnA, nnB = _run(f3d, A, B, w1, w2)
+def _check(f3d, oracle, A, B, w1=1.0, w2=1.0, both=True):
+    """Default path (filtered sweep + certified exact finalize) AND the all-exact sweep vs the oracle."""
     ol, onA, onB, oterms = oracle.chamfer_distance(A, B, w1, w2, return_all=True)
+    if both:
+        l2, t2, a2, b2 = _run(f3d, A, B, w1, w2, flags=f3d.FLAG_EXACT_SWEEP)
+        assert np.array_equal(a2, onA) and np.array_equal(b2, onB), "exact-sweep path: index mismatch"
+        assert abs(l2 - float(ol)) <= RTOL * abs(float(ol)) + 1e-30
+    loss, terms, nnA, nnB = _run(f3d, A, B, w1, w2)
+    if both:
+        assert loss == l2 and np.array_equal(terms, t2)  # the two paths agree bit for bit
     assert np.array_equal(nnA, onA), f"nn_for_A mismatch at {np.argwhere(nnA != onA)[:5]}"
     assert np.array_equal(nnB, onB), f"nn_for_B mismatch at {np.argwhere(nnB != onB)[:5]}"
     assert abs(loss - float(ol)) <= RTOL * abs(float(ol)) + 1e-30, (loss, float(ol))
@@ -140,3 +147,41 @@ def test_properties_large(f3d):
     dAB = ((A - gB) ** 2).sum(-1).double().mean()
     assert abs(dAB.item() - t1[0].item()) <= 1e-5 * dAB.item()
     assert int(nnA.min()) >= 0 and int(nnA.max()) < 8192
+
+
+def test_filter_adversarial(f3d, oracle):
+    """Inputs that stress the filter's error bound: clouds far from the origin (cancellation in the expanded
+    form), tiny clusters, wildly different scales per batch element, huge magnitudes (filter must refuse to
+    certify), a cloud and its slightly jittered copy (near-ties everywhere), N and M not multiples of anything."""
+    rng = np.random.default_rng(77)
+    base = rng.random((3, 1500, 3), dtype=np.float32)
+    # far from the origin: offset 1000 leaves ~1e-4 resolution — many exact ties and near ties
+    A = (base + np.float32(1000.0)).astype(np.float32)
+    B = (rng.random((3, 1100, 3), dtype=np.float32) + np.float32(1000.0)).astype(np.float32)
+    _check(f3d, oracle, A, B)
+    # tight clusters inside a wide bounding box
+    C = (rng.integers(0, 4, (2, 2000, 1)) * 50.0 + rng.standard_normal((2, 2000, 3)) * 1e-3).astype(np.float32)
+    D = (rng.integers(0, 4, (2, 1777, 1)) * 50.0 + rng.standard_normal((2, 1777, 3)) * 1e-3).astype(np.float32)
+    _check(f3d, oracle, C, D)
+    # per-element scales from 1e-6 to 1e6
+    sc = np.array([1e-6, 1.0, 1e6], np.float32)[:, None, None]
+    _check(f3d, oracle, base * sc, rng.random((3, 900, 3), dtype=np.float32) * sc)
+    # magnitudes where |x|² overflows the filter's safe range: everything must take the exact fallback
+    _check(f3d, oracle, (base[:1, :300] * np.float32(1e16)), (rng.random((1, 260, 3), dtype=np.float32) * np.float32(1e16)))
+    # jittered copy: the nearest neighbour is at distance ~1e-7·|x|, i.e. inside the filter's noise
+    J = (base + rng.standard_normal(base.shape).astype(np.float32) * np.float32(1e-7)).astype(np.float32)
+    _check(f3d, oracle, base, J)
+    _check(f3d, oracle, base[:, :1], J)        # N = 1
+    _check(f3d, oracle, base[:, :33], J[:, :1])  # M = 1
+
+
+def test_filter_sorted_and_structured(f3d, oracle):
+    """Structured clouds (grid points, points on a line/plane) where many filter values coincide."""
+    g = np.stack(np.meshgrid(*[np.arange(12, dtype=np.float32)] * 3, indexing="ij"), -1).reshape(1, -1, 3) / np.float32(12)
+    rng = np.random.default_rng(5)
+    _check(f3d, oracle, g, g[:, rng.permutation(g.shape[1])] + np.float32(1.0 / 24))
+    line = np.zeros((2, 3000, 3), np.float32)
+    line[..., 0] = np.linspace(0, 1, 3000, dtype=np.float32)
+    plane = rng.random((2, 2500, 3), dtype=np.float32)
+    plane[..., 2] = 0.25
+    _check(f3d, oracle, line, plane)
