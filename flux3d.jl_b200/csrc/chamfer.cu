@@ -584,252 +584,6 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
     DBG_T(3);
 }
 
-// =====================================================================================================
-// Persistent, asynchronously staged version of the filtered sweep (the one the library launches).
-//
-// The one-tile-per-CTA kernel above spends ~24 % of every CTA's life in its prologue (a chain of cold global
-// loads: centre samples -> column points -> row points) and another ~13 % in wave quantisation (2048 CTAs on
-// 592 slots).  Here a fixed grid of CTAs (4 per SM) walks the tile list tile = cta, cta + grid, ...; while tile k
-// is being swept, the RAW bytes of tile k+1 (column points, row points, centre samples) stream into the other
-// half of a double buffer with cp.async (LDGSTS; 16-byte when the clouds are 16-byte aligned, else 4-byte), so
-// the only per-tile overhead left is an on-chip transform pass (raw AoS -> centred, pre-scaled column pairs).
-// Tiles are half as wide (4 x 128 columns) so that ceil(T / grid) * grid / T stays within a few percent.
-// =====================================================================================================
-struct PersParams {
-    FiltParams f;
-    int tiles;       // B * RB * CS
-    int vec16;       // both clouds 16-byte aligned and N, M multiples of 4: 16-byte cp.async
-};
-
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int kPending>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
-
-// words [w0, w1) of a float array -> shared memory, cooperatively; out-of-range words are simply not copied
-__device__ __forceinline__ void stage_words(float* sdst, const float* gsrc, long avail_words, int want_words, bool vec16,
-                                            int tid) {
-    const int n = (int)min((long)want_words, avail_words);
-    if (vec16) {  // base and counts are multiples of 4 words by construction when vec16 is set
-        for (int w = tid * 4; w < n; w += kThreads * 4) cp_async16(sdst + w, gsrc + w);
-    } else {
-        for (int w = tid; w < n; w += kThreads) cp_async4(sdst + w, gsrc + w);
-    }
-}
-
-__global__ void __launch_bounds__(kThreads, 4) chamfer_filter_sweep_persistent_kernel(PersParams pp_) {
-    const FiltParams& p = pp_.f;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int BN = kWarps * p.cols_per_warp;
-    const int raw_words = BN * 3 + kTileRows * 3 + 64 * 3;       // columns | rows | centre samples (A 32, B 32)
-    float4* s_xy = reinterpret_cast<float4*>(smem_raw);          // [BN/2] {-2x0,-2x1,-2y0,-2y1}
-    float4* s_zn = s_xy + BN / 2;                                // [BN/2] {-2z0,-2z1,nb0,nb1}
-    float4* s_row = s_zn + BN / 2;                               // [kWarps][kTileRows] {b1,b2,c1,-}; first used as s_rm
-    const size_t rm_bytes = (size_t)(BN / kChunk) * kTileRows * sizeof(float);
-    const size_t row_bytes = rm_bytes > (size_t)kWarps * kTileRows * sizeof(float4) ? rm_bytes : (size_t)kWarps * kTileRows * sizeof(float4);
-    float* s_raw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_row) + row_bytes);  // [2][raw_words]
-    __shared__ unsigned s_maxnb;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (blockIdx.x == 0 && tid == 0) *p.counter = 0u;
-
-    auto issue_prefetch = [&](int tile, int buf) {
-        const int cs = tile % p.CS, rb = (tile / p.CS) % p.RB, b = tile / (p.CS * p.RB);
-        const float* gA = p.A + (size_t)b * p.N * 3;
-        const float* gB = p.Bp + (size_t)b * p.M * 3;
-        float* dst = s_raw + (size_t)buf * raw_words;
-        const int col0 = cs * BN, row0 = rb * kTileRows;
-        stage_words(dst, gB + (size_t)col0 * 3, (long)(p.M - col0) * 3, BN * 3, pp_.vec16 != 0, tid);
-        stage_words(dst + BN * 3, gA + (size_t)row0 * 3, (long)(p.N - row0) * 3, kTileRows * 3, pp_.vec16 != 0, tid);
-        if (warp == 0) {  // the 32 + 32 strided centre samples of this batch element
-            const int ia = (int)(((long)lane * p.N) >> 5), ib = (int)(((long)lane * p.M) >> 5);
-            float* c = dst + BN * 3 + kTileRows * 3;
-#pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                cp_async4(c + lane * 3 + e, gA + 3 * (size_t)ia + e);
-                cp_async4(c + 96 + lane * 3 + e, gB + 3 * (size_t)ib + e);
-            }
-        }
-        cp_async_commit();
-    };
-
-#ifdef F3D_EXP_CLOCK
-    long long acc_wait = 0, acc_xf = 0, acc_loop = 0, acc_epi = 0, t_start = clock64(), tq = 0;
-#define PT(var) do { if (tid == 0) { long long n_ = clock64(); var += n_ - tq; tq = n_; } } while (0)
-#else
-#define PT(var)
-#endif
-    int tile = blockIdx.x;
-    if (tile < pp_.tiles) issue_prefetch(tile, 0);
-    for (int it = 0; tile < pp_.tiles; ++it, tile += gridDim.x) {
-#ifdef F3D_EXP_CLOCK
-        if (tid == 0) tq = clock64();
-#endif
-        const int buf = it & 1;
-        const int next = tile + gridDim.x;
-        if (next < pp_.tiles) { issue_prefetch(next, buf ^ 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        if (tid == 0) s_maxnb = 0u;
-        __syncthreads();  // tile `tile` is in s_raw[buf]; the previous tile's s_xy/s_zn/s_row readers are done
-        PT(acc_wait);
-
-        const int cs = tile % p.CS, rb = (tile / p.CS) % p.RB, b = tile / (p.CS * p.RB);
-        const int col0 = cs * BN, row0 = rb * kTileRows;
-        const float* raw = s_raw + (size_t)buf * raw_words;
-        // ---- centre (every warp, same operations => same bits everywhere) --------------------------------------
-        float cx, cy, cz;
-        {
-            const float* c = raw + BN * 3 + kTileRows * 3;
-            cx = c[lane * 3] + c[96 + lane * 3];
-            cy = c[lane * 3 + 1] + c[96 + lane * 3 + 1];
-            cz = c[lane * 3 + 2] + c[96 + lane * 3 + 2];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                cx += __shfl_xor_sync(0xffffffffu, cx, o);
-                cy += __shfl_xor_sync(0xffffffffu, cy, o);
-                cz += __shfl_xor_sync(0xffffffffu, cz, o);
-            }
-            cx *= (1.0f / 64.0f); cy *= (1.0f / 64.0f); cz *= (1.0f / 64.0f);
-            if (tid == 0 && cs == 0 && rb == 0) { p.centre[4 * b] = cx; p.centre[4 * b + 1] = cy; p.centre[4 * b + 2] = cz; }
-        }
-        // ---- transform the column tile: centred, pre-scaled by -2, with |b'|² -------------------------------------
-        {
-            float mynb = 0.0f;
-            for (int q = tid; q < BN / 2; q += kThreads) {
-                const int j = col0 + 2 * q;
-                const float* c = raw + 6 * q;
-                float x0 = 0.f, y0 = 0.f, z0 = 0.f, n0 = kPadF, x1 = 0.f, y1 = 0.f, z1 = 0.f, n1 = kPadF;
-                if (j < p.M) {
-                    x0 = c[0] - cx; y0 = c[1] - cy; z0 = c[2] - cz;
-                    n0 = fmaf(z0, z0, fmaf(y0, y0, x0 * x0));
-                    mynb = fmaxf(mynb, n0);
-                }
-                if (j + 1 < p.M) {
-                    x1 = c[3] - cx; y1 = c[4] - cy; z1 = c[5] - cz;
-                    n1 = fmaf(z1, z1, fmaf(y1, y1, x1 * x1));
-                    mynb = fmaxf(mynb, n1);
-                }
-                s_xy[q] = make_float4(-2.0f * x0, -2.0f * x1, -2.0f * y0, -2.0f * y1);
-                s_zn[q] = make_float4(-2.0f * z0, -2.0f * z1, n0, n1);
-            }
-            mynb = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mynb)));  // norms are >= 0
-            if (lane == 0) atomicMax(&s_maxnb, __float_as_uint(mynb));
-        }
-        // ---- this lane's 8 rows ------------------------------------------------------------------------------------
-        float ax[kRowsPerLane], ay[kRowsPerLane], az[kRowsPerLane], na[kRowsPerLane];
-        float myna = 0.0f;
-        {
-            const float* rr = raw + BN * 3 + lane * kRowsPerLane * 3;
-#pragma unroll
-            for (int r = 0; r < kRowsPerLane; ++r) {
-                const int i = row0 + lane * kRowsPerLane + r;
-                if (i < p.N) {
-                    ax[r] = rr[3 * r] - cx; ay[r] = rr[3 * r + 1] - cy; az[r] = rr[3 * r + 2] - cz;
-                    na[r] = fmaf(az[r], az[r], fmaf(ay[r], ay[r], ax[r] * ax[r]));
-                    myna = fmaxf(myna, na[r]);
-                } else {
-                    ax[r] = 0.f; ay[r] = 0.f; az[r] = 0.f; na[r] = kPadF;
-                }
-            }
-        }
-        const float maxna = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(myna)));
-        __syncthreads();
-        const float maxnb = __uint_as_float(s_maxnb);
-        if (tid == 0) {
-            p.maxnb[(size_t)b * p.CS + cs] = maxnb;
-            if (cs == 0) p.maxna[(size_t)b * p.RB + rb] = maxna;
-        }
-        const float wt = kBallotAbs * (maxna + maxnb);
-        PT(acc_xf);
-
-        const int wp0 = warp * (p.cols_per_warp / 2);
-        const int nchunks = p.cols_per_warp / kChunk;
-        const int gchunk0 = (col0 + warp * p.cols_per_warp) / kChunk;
-        uint4* __restrict__ gcol4 = reinterpret_cast<uint4*>(p.colpart + ((size_t)b * p.RB + rb) * p.Mpad + col0);
-        float* s_rm = reinterpret_cast<float*>(s_row) + (size_t)warp * nchunks * kTileRows;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            float rm[kRowsPerLane];
-#pragma unroll
-            for (int r = 0; r < kRowsPerLane; ++r) rm[r] = INFINITY;
-#pragma unroll 2
-            for (int q = 0; q < kChunk / 2; ++q) {
-                const int pp = wp0 + ch * (kChunk / 2) + q;
-                const float4 xy = s_xy[pp];
-                const float4 zn = s_zn[pp];
-                const u64 X2 = pack2(xy.x, xy.y), Y2 = pack2(xy.z, xy.w), Z2 = pack2(zn.x, zn.y), NB = pack2(zn.z, zn.w);
-                u64 t[kRowsPerLane];
-#pragma unroll
-                for (int r = 0; r < kRowsPerLane; ++r) t[r] = fma2(X2, pack2(ax[r], ax[r]), NB);
-#pragma unroll
-                for (int r = 0; r < kRowsPerLane; ++r) t[r] = fma2(Y2, pack2(ay[r], ay[r]), t[r]);
-#pragma unroll
-                for (int r = 0; r < kRowsPerLane; ++r) t[r] = fma2(Z2, pack2(az[r], az[r]), t[r]);
-                float c0 = INFINITY, c1v = INFINITY;
-#pragma unroll
-                for (int r = 0; r < kRowsPerLane; ++r) {
-                    float f0, f1;
-                    unpack2(add2(t[r], pack2(na[r], na[r])), f0, f1);
-                    rm[r] = fminf(rm[r], fminf(f0, f1));
-                    c0 = fminf(c0, f0);
-                    c1v = fminf(c1v, f1);
-                }
-                const int m0 = __reduce_min_sync(0xffffffffu, __float_as_int(c0));
-                const int m1 = __reduce_min_sync(0xffffffffu, __float_as_int(c1v));
-                const unsigned bal0 = __ballot_sync(0xffffffffu, c0 <= fmaf(__int_as_float(m0), kBallotRel, wt));
-                const unsigned bal1 = __ballot_sync(0xffffffffu, c1v <= fmaf(__int_as_float(m1), kBallotRel, wt));
-                if (lane == 0) gcol4[pp] = make_uint4((unsigned)m0, bal0, (unsigned)m1, bal1);
-            }
-#pragma unroll
-            for (int r = 0; r < kRowsPerLane; ++r) s_rm[(ch * kRowsPerLane + r) * 32 + lane] = rm[r];
-        }
-        PT(acc_loop);
-        // ---- (b1, c1, b2) per row over this warp's chunks --------------------------------------------------------
-        float b1[kRowsPerLane], b2[kRowsPerLane];
-        int c1[kRowsPerLane];
-#pragma unroll
-        for (int r = 0; r < kRowsPerLane; ++r) { b1[r] = INFINITY; b2[r] = INFINITY; c1[r] = 0; }
-        for (int ch = 0; ch < nchunks; ++ch) {
-#pragma unroll
-            for (int r = 0; r < kRowsPerLane; ++r) {
-                const float cm = s_rm[(ch * kRowsPerLane + r) * 32 + lane];
-                b2[r] = fminf(b2[r], fmaxf(b1[r], cm));
-                if (cm < b1[r]) c1[r] = gchunk0 + ch;
-                b1[r] = fminf(b1[r], cm);
-            }
-        }
-        __syncthreads();  // s_row below aliases the s_rm regions of all warps
-#pragma unroll
-        for (int r = 0; r < kRowsPerLane; ++r)
-            s_row[warp * kTileRows + lane * kRowsPerLane + r] = make_float4(b1[r], b2[r], __int_as_float(c1[r]), 0.f);
-        __syncthreads();
-        {
-            const size_t base = ((size_t)b * p.CS + cs) * p.Npad + row0;
-            for (int rr = tid; rr < kTileRows; rr += kThreads) {
-                float4 best = s_row[rr];
-#pragma unroll
-                for (int w = 1; w < kWarps; ++w) {
-                    const float4 o = s_row[w * kTileRows + rr];
-                    if (o.x < best.x) { best.y = fminf(best.x, o.y); best.x = o.x; best.z = o.z; }
-                    else best.y = fminf(best.y, o.x);
-                }
-                p.rowpart[base + rr] = best;
-            }
-        }
-        // the loop-top __syncthreads orders these s_row / s_xy reads before the next tile's writes
-        PT(acc_epi);
-    }
-#ifdef F3D_EXP_CLOCK
-    if (tid == 0 && blockIdx.x < 8192) { long long* d = g_dbg + blockIdx.x * 8; d[0] = acc_wait; d[1] = acc_xf; d[2] = acc_loop; d[3] = acc_epi; d[4] = clock64() - t_start; }
-#endif
-}
-
 // ---- finalize for the filtered sweep: certify, rescan exactly, reduce the loss ------------------------------
 struct FiltFinalizeParams {
     const float* A;
@@ -1055,32 +809,10 @@ struct FiltPlan {
     size_t off_rowpart, off_colpart, off_maxna, off_maxnb, off_centre, off_partial, off_counter, total;
 };
 
-int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
-        else { (void)cudaGetLastError(); return 148; }  // no device (host-only callers of the size query): B200 value
-    }
-    return n;
-}
-
-constexpr int kPersCtasPerSm = 4;
-
 FiltPlan make_filt_plan(int B, int N, int M) {
     FiltPlan pl;
-    // Tile width: 4 warps x cpw columns.  Narrower tiles cut the wave-quantisation loss of the persistent grid
-    // (ceil(T/P) P / T), wider ones amortise the fixed per-tile cost (~70 columns' worth of transform + epilogue).
-    const int RBn = (N + kTileRows - 1) / kTileRows;
-    const long P = (long)sm_count() * kPersCtasPerSm;
-    int cpw = kChunk;
-    double best_cost = 1e300;
-    for (int cand = 64; cand <= kMaxColsPerWarp; cand *= 2) {
-        const int c = std::max(kChunk, std::min(cand, (int)align_up((size_t)(M + kWarps - 1) / kWarps, kChunk)));
-        const long BNc = (long)kWarps * c, CSc = (M + BNc - 1) / BNc, T = (long)B * RBn * CSc;
-        const double cost = (double)((T + P - 1) / P) * (double)(BNc + 70);
-        if (cost < best_cost) { best_cost = cost; cpw = c; }
-    }
+    int cpw = (int)align_up((size_t)(M + kWarps - 1) / kWarps, kChunk);
+    if (cpw > kMaxColsPerWarp) cpw = kMaxColsPerWarp;
     pl.cols_per_warp = cpw;
     pl.BN = kWarps * cpw;
     pl.CS = (M + pl.BN - 1) / pl.BN;
@@ -1099,13 +831,6 @@ FiltPlan make_filt_plan(int B, int N, int M) {
     pl.off_counter = o; o = align_up(o + sizeof(unsigned), 256);
     pl.total = o;
     return pl;
-}
-
-size_t pers_smem_bytes(int BN) {
-    const size_t rm_bytes = (size_t)(BN / kChunk) * kTileRows * sizeof(float);
-    const size_t row_bytes = std::max(rm_bytes, (size_t)kWarps * kTileRows * sizeof(float4));
-    const size_t raw_words = (size_t)BN * 3 + kTileRows * 3 + 64 * 3;
-    return (size_t)(BN / 2) * (2 * sizeof(float4)) + row_bytes + 2 * raw_words * sizeof(float);
 }
 
 size_t filt_smem_bytes(int BN) {
@@ -1145,7 +870,7 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
     if (!fma && !(flags & F3D_FLAG_EXACT_SWEEP)) {
         // ---- default: filtered sweep + certified exact finalize (bit-identical results, ~half the FP32 work) ----
         FiltPlan fl = make_filt_plan(B, N, M);
-        if ((long)B * fl.RB * fl.CS > 0x7fffffffL) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: problem too large");
+        if (fl.RB > 65535) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: N too large");
         FiltParams sp;
         sp.A = A; sp.Bp = Bp; sp.N = N; sp.M = M;
         sp.cols_per_warp = fl.cols_per_warp; sp.CS = fl.CS; sp.RB = fl.RB; sp.Npad = fl.Npad; sp.Mpad = fl.Mpad;
@@ -1155,15 +880,10 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
         sp.maxnb = reinterpret_cast<float*>(w + fl.off_maxnb);
         sp.centre = reinterpret_cast<float*>(w + fl.off_centre);
         sp.counter = reinterpret_cast<unsigned*>(w + fl.off_counter);
-        PersParams pp;
-        pp.f = sp;
-        pp.tiles = B * fl.RB * fl.CS;
-        pp.vec16 = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bp)) % 16 == 0 && N % 4 == 0 && M % 4 == 0) ? 1 : 0;
-        const size_t smem = pers_smem_bytes(fl.BN);
-        F3D_CUDA(cudaFuncSetAttribute(chamfer_filter_sweep_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = (int)std::min<long>(pp.tiles, (long)sm_count() * kPersCtasPerSm);
-        chamfer_filter_sweep_persistent_kernel<<<grid, kThreads, smem, stream>>>(pp);
-        F3D_CHECK_LAUNCH("chamfer_filter_sweep_persistent_kernel");
+        const size_t smem = filt_smem_bytes(fl.BN);
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_filter_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chamfer_filter_sweep_kernel<<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
+        F3D_CHECK_LAUNCH("chamfer_filter_sweep_kernel");
         if (flags & F3D_FLAG_SWEEP_ONLY) return F3D_OK;
         FiltFinalizeParams fp;
         fp.A = A; fp.Bp = Bp; fp.B = B; fp.N = N; fp.M = M;
