@@ -8,14 +8,20 @@
 // query itself, or its lowest-indexed exact duplicate — is dropped BY POSITION as dgcnn.jl:6 does.
 // Distances are s = 0; s = s + (a_d - b_d)^2 for d = 1..F, every operation separately rounded.
 //
-// Shape of the work: B*N query rows, each against the N candidates of its cloud.  One warp owns
-// kQPW queries; a CTA (8 warps) owns 8*kQPW consecutive queries of one cloud and streams the cloud
-// through shared memory in tiles of kTileC candidates (rows padded to Fp+4 floats so that LDS.128 is
-// bank-conflict-free for row-per-lane access).  Each lane evaluates kCPL candidates x kQPW queries in
-// registers.  The running (K+1)-best list of a query lives in registers distributed over the warp
-// (element e in lane e%32, slot e/32) as 64-bit keys (distance bits << 32 | index): distances are
-// >= 0, so unsigned integer order on the key IS the (distance, index) order.  A candidate is
-// inserted only if its key is below the current (K+1)-th key (ballot), by a shuffle-shift.
+// Shape of the work: B*N query rows, each against the N candidates of its cloud.  The N^2 distances are cheap
+// (33.5 M pairs at cfg3); SELECTION is what costs, so it is done in bulk, not one insertion at a time:
+//   * a warp owns kQW = 2 queries; a CTA (8 warps) owns 16 consecutive queries of one cloud and streams the cloud
+//     through shared memory in tiles of 128 candidates (rows padded to Fp+4 floats: LDS.128 is conflict-free
+//     for row-per-lane access).  Every lane keeps the distances of ITS 32 candidates of the current
+//     1024-candidate block in registers (d[2][32]) — each distance is evaluated exactly once, also for F = 64.
+//   * per block and query: (1) per-lane two smallest distances; (2) a 64-key warp bitonic sort of those gives
+//     T = the (K+1)-th smallest of them — an upper bound of the (K+1)-th smallest distance of the block, because
+//     they are a subset; (3) every candidate with d <= T (typically K+1 .. K+4 of them) is compacted into shared
+//     memory as a 64-bit key (distance bits << 32 | index; distances are >= 0 so unsigned order on the key IS
+//     the (distance, index) order); (4) those <= 64 keys are bitonic-sorted and bitonic-merged into the running
+//     sorted list (register-distributed over the warp: element e in lane e%32, slot e/32).
+//   * if more than 64 candidates tie below T (lattice-like inputs) the block falls back to one-at-a-time
+//     shuffle insertion, which is always correct.
 #include "f3d_common.cuh"
 
 namespace f3d {
@@ -23,10 +29,13 @@ namespace {
 
 constexpr int kWarpsK = 8;
 constexpr int kThreadsK = 32 * kWarpsK;
-constexpr int kQPW = 4;                   // queries per warp
-constexpr int kQPC = kWarpsK * kQPW;      // queries per CTA (32)
+constexpr int kQW = 2;                    // queries per warp
+constexpr int kQPC = kWarpsK * kQW;       // queries per CTA (16)
 constexpr int kCPL = 4;                   // candidates per lane per tile
-constexpr int kTileC = 32 * kCPL;         // candidates per tile (128)
+constexpr int kTileC = 32 * kCPL;         // candidates per staged tile (128)
+constexpr int kSPL = 32;                  // candidate slots per lane per selection block
+constexpr int kBlockC = 32 * kSPL;        // candidates per selection block (1024)
+constexpr int kTilesPerBlock = kBlockC / kTileC;  // 8
 constexpr u64 kKeyInf = ~0ull;
 
 struct KnnParams {
@@ -73,91 +82,219 @@ struct TopList {
     }
 };
 
+// ---- warp bitonic networks over 64 keys (2 per lane; element e = slot*32 + lane), ascending -----------------
+template <typename T>
+__device__ __forceinline__ T shfl_xor_t(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <>
+__device__ __forceinline__ u64 shfl_xor_t<u64>(u64 v, int m) {
+    return (u64)__shfl_xor_sync(0xffffffffu, (unsigned long long)v, m);
+}
+template <typename T>
+__device__ __forceinline__ void cmpx_lane(T& v, int j, bool keep_min) {
+    const T o = shfl_xor_t<T>(v, j);
+    const bool less = o < v;
+    v = (less == keep_min) ? o : v;  // keep_min: take the smaller of (v, o); else the larger
+}
+// sort the 32 keys of one slot ascending (asc = true) or descending
+template <typename T>
+__device__ __forceinline__ void bitonic_sort32(T& v, int lane, bool asc) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool up = (((lane & k) == 0) || k == 32) == asc;   // direction of this lane's k-block
+            cmpx_lane(v, j, ((lane & j) == 0) == up);
+        }
+    }
+}
+// the 5 half-cleaner stages that turn a bitonic 32-sequence (per slot) into an ascending one
+template <typename T>
+__device__ __forceinline__ void bitonic_merge32(T& v, int lane) {
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) cmpx_lane(v, j, (lane & j) == 0);
+}
+template <typename T>
+__device__ __forceinline__ void bitonic_sort64(T& v0, T& v1, int lane) {
+    bitonic_sort32(v0, lane, true);
+    bitonic_sort32(v1, lane, false);       // (v0 asc, v1 desc) is a bitonic 64-sequence
+    const T lo = v0 < v1 ? v0 : v1, hi = v0 < v1 ? v1 : v0;
+    v0 = lo; v1 = hi;
+    bitonic_merge32(v0, lane);
+    bitonic_merge32(v1, lane);
+}
+
 template <int kSlots>
-__global__ void __launch_bounds__(kThreadsK) knn_graph_kernel(KnnParams p) {
+__global__ void __launch_bounds__(kThreadsK, 2) knn_graph_kernel(KnnParams p) {
     extern __shared__ __align__(16) float smem_k[];
     const int stride = p.Fp + 4;           // floats per staged row
     float* s_q = smem_k;                   // [kQPC][stride]
     float* s_c = s_q + kQPC * stride;      // [kTileC][stride]
+    __shared__ u64 s_buf[kWarpsK][64];     // per-warp compaction buffer
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
     const int q0 = blockIdx.x * kQPC;
     const float* Xb = p.X + (size_t)b * p.N * p.F;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int q4 = p.Fp >> 2;
+    const unsigned long long q4_inv = (0x100000000ull / (unsigned)q4) + 1ull;
+    const bool vec4 = (p.F & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0;
 
-    // ---- stage this CTA's queries (zero-padded to Fp, rows past N replicate row N-1: never stored)
+    // ---- stage this CTA's queries (zero-padded to Fp; rows past N replicate row N-1 and are never stored) ----
     for (int t = tid; t < kQPC * p.Fp; t += kThreadsK) {
         int r = t / p.Fp, d = t - r * p.Fp;
         int qi = min(q0 + r, p.N - 1);
         s_q[r * stride + d] = (d < p.F) ? __ldg(Xb + (size_t)qi * p.F + d) : 0.0f;
     }
 
-    TopList<kSlots> top[kQPW];
-    u64 thr[kQPW];
+    TopList<kSlots> top[kQW];
+    u64 thr[kQW];
 #pragma unroll
-    for (int q = 0; q < kQPW; ++q) { top[q].init(); thr[q] = kKeyInf; }
+    for (int q = 0; q < kQW; ++q) { top[q].init(); thr[q] = kKeyInf; }
+    const float* qrow = s_q + (warp * kQW) * stride;
 
-    const float* qrow = s_q + (warp * kQPW) * stride;
-    for (int c0 = 0; c0 < p.N; c0 += kTileC) {
-        __syncthreads();  // previous tile fully consumed (and s_q visible on the first pass)
-        const int nc = min(kTileC, p.N - c0);
-        for (int t = tid; t < kTileC * p.Fp; t += kThreadsK) {
-            int r = t / p.Fp, d = t - r * p.Fp;
-            float v = 0.0f;
-            if (r < nc && d < p.F) v = __ldg(Xb + (size_t)(c0 + r) * p.F + d);
-            s_c[r * stride + d] = v;
-        }
-        __syncthreads();
-
-        float acc[kQPW][kCPL];
+    for (int blk0 = 0; blk0 < p.N; blk0 += kBlockC) {
+        float dist[kQW][kSPL];
 #pragma unroll
-        for (int q = 0; q < kQPW; ++q)
-#pragma unroll
-            for (int c = 0; c < kCPL; ++c) acc[q][c] = 0.0f;
-
-        for (int d = 0; d < p.Fp; d += 4) {
-            float4 cv[kCPL], qv[kQPW];
-#pragma unroll
-            for (int c = 0; c < kCPL; ++c) cv[c] = *reinterpret_cast<const float4*>(s_c + (c * 32 + lane) * stride + d);
-#pragma unroll
-            for (int q = 0; q < kQPW; ++q) qv[q] = *reinterpret_cast<const float4*>(qrow + q * stride + d);
-#pragma unroll
-            for (int q = 0; q < kQPW; ++q)
-#pragma unroll
-                for (int c = 0; c < kCPL; ++c) {
-                    float t;
-                    t = __fsub_rn(qv[q].x, cv[c].x); acc[q][c] = __fadd_rn(acc[q][c], __fmul_rn(t, t));
-                    t = __fsub_rn(qv[q].y, cv[c].y); acc[q][c] = __fadd_rn(acc[q][c], __fmul_rn(t, t));
-                    t = __fsub_rn(qv[q].z, cv[c].z); acc[q][c] = __fadd_rn(acc[q][c], __fmul_rn(t, t));
-                    t = __fsub_rn(qv[q].w, cv[c].w); acc[q][c] = __fadd_rn(acc[q][c], __fmul_rn(t, t));
+        for (int t = 0; t < kTilesPerBlock; ++t) {
+            const int c0 = blk0 + t * kTileC;
+            if (c0 < p.N) {  // CTA-uniform
+                __syncthreads();  // previous tile fully consumed (and s_q visible on the first pass)
+                const int nc = min(kTileC, p.N - c0);
+                // stage 128 candidate rows as float4 quads; row = e / q4 by multiply-shift (exact for e < 2^16)
+                for (int e = tid; e < kTileC * q4; e += kThreadsK) {
+                    const int r = (int)(((unsigned long long)(unsigned)e * q4_inv) >> 32), c4 = e - r * q4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < nc) {
+                        const float* src = Xb + (size_t)(c0 + r) * p.F + 4 * c4;
+                        if (vec4) v = __ldg(reinterpret_cast<const float4*>(src));
+                        else {
+                            const int d = 4 * c4;
+                            if (d < p.F) v.x = __ldg(src);
+                            if (d + 1 < p.F) v.y = __ldg(src + 1);
+                            if (d + 2 < p.F) v.z = __ldg(src + 2);
+                            if (d + 3 < p.F) v.w = __ldg(src + 3);
+                        }
+                    }
+                    *reinterpret_cast<float4*>(s_c + r * stride + 4 * c4) = v;
                 }
+                __syncthreads();
+                float acc[kQW][kCPL];
+#pragma unroll
+                for (int q = 0; q < kQW; ++q)
+#pragma unroll
+                    for (int c = 0; c < kCPL; ++c) acc[q][c] = 0.0f;
+                for (int d = 0; d < p.Fp; d += 4) {
+                    float4 cv[kCPL], qv[kQW];
+#pragma unroll
+                    for (int c = 0; c < kCPL; ++c) cv[c] = *reinterpret_cast<const float4*>(s_c + (c * 32 + lane) * stride + d);
+#pragma unroll
+                    for (int q = 0; q < kQW; ++q) qv[q] = *reinterpret_cast<const float4*>(qrow + q * stride + d);
+#pragma unroll
+                    for (int q = 0; q < kQW; ++q)
+#pragma unroll
+                        for (int c = 0; c < kCPL; ++c) {
+                            float u;
+                            u = __fsub_rn(qv[q].x, cv[c].x); acc[q][c] = __fadd_rn(acc[q][c], __fmul_rn(u, u));
+                            u = __fsub_rn(qv[q].y, cv[c].y); acc[q][c] = __fadd_rn(acc[q][c], __fmul_rn(u, u));
+                            u = __fsub_rn(qv[q].z, cv[c].z); acc[q][c] = __fadd_rn(acc[q][c], __fmul_rn(u, u));
+                            u = __fsub_rn(qv[q].w, cv[c].w); acc[q][c] = __fadd_rn(acc[q][c], __fmul_rn(u, u));
+                        }
+                }
+#pragma unroll
+                for (int q = 0; q < kQW; ++q)
+#pragma unroll
+                    for (int c = 0; c < kCPL; ++c) dist[q][t * kCPL + c] = (c0 + c * 32 + lane < p.N) ? acc[q][c] : INFINITY;
+            } else {
+#pragma unroll
+                for (int q = 0; q < kQW; ++q)
+#pragma unroll
+                    for (int c = 0; c < kCPL; ++c) dist[q][t * kCPL + c] = INFINITY;
+            }
         }
 
-        // ---- threshold-filtered insertion into the distributed sorted lists ------------------------
+        // ---- bulk selection of this block's candidates, per query ------------------------------------------------
 #pragma unroll
-        for (int q = 0; q < kQPW; ++q) {
+        for (int q = 0; q < kQW; ++q) {
+            // (1) this lane's two smallest distances
+            float m1 = INFINITY, m2 = INFINITY;
 #pragma unroll
-            for (int c = 0; c < kCPL; ++c) {
-                const int j = c0 + c * 32 + lane;
-                const u64 key = (j < p.N) ? (((u64)__float_as_uint(acc[q][c]) << 32) | (unsigned)j) : kKeyInf;
-                unsigned m = __ballot_sync(0xffffffffu, key < thr[q]);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const u64 kk = __shfl_sync(0xffffffffu, key, src);
-                    if (kk < thr[q]) {  // warp-uniform; thr may have tightened since the ballot
-                        top[q].insert(kk, lane);
-                        thr[q] = top[q].get(p.K);
+            for (int s = 0; s < kSPL; ++s) {
+                const float v = dist[q][s];
+                m2 = fminf(m2, fmaxf(m1, v));
+                m1 = fminf(m1, v);
+            }
+            // (2) T = (K+1)-th smallest of the 64 local minima: an upper bound of the block's (K+1)-th smallest
+            //     distance; the running list's (K+1)-th distance bounds the union as well
+            unsigned u0 = __float_as_uint(m1), u1 = __float_as_uint(m2);  // >= 0 (or +inf): bit order == value order
+            bitonic_sort64(u0, u1, lane);
+            const unsigned tsel = __shfl_sync(0xffffffffu, (p.K >> 5) ? u1 : u0, p.K & 31);
+            const float T = fminf(__uint_as_float(tsel), __uint_as_float((unsigned)(thr[q] >> 32)));
+            // (3) compact every candidate with d <= T into this warp's buffer
+            int count = 0;
+            u64* buf = s_buf[warp];
+#pragma unroll
+            for (int s = 0; s < kSPL; ++s) {
+                const float v = dist[q][s];
+                const bool pass = v <= T;  // padded slots hold +inf and T is finite whenever K+1 <= block size...
+                const unsigned bal = __ballot_sync(0xffffffffu, pass && v < INFINITY);
+                if (bal) {
+                    const int pos = count + __popc(bal & lt_mask);
+                    const int j = blk0 + (s / kCPL) * kTileC + (s % kCPL) * 32 + lane;
+                    if (pass && v < INFINITY && pos < 64) buf[pos] = ((u64)__float_as_uint(v) << 32) | (unsigned)j;
+                    count += __popc(bal);
+                }
+            }
+            __syncwarp();
+            if (count <= 64) {
+                // (4) sort the collected keys and merge them into the running sorted list
+                u64 n0 = (lane < count) ? buf[lane] : kKeyInf;
+                u64 n1 = (32 + lane < count) ? buf[32 + lane] : kKeyInf;
+                if (count <= 32) { bitonic_sort32(n0, lane, true); }
+                else bitonic_sort64(n0, n1, lane);
+                if (kSlots == 1) {
+                    const u64 r0 = shfl_xor_t<u64>(n0, 31);      // n0 reversed: lane l gets element 31-l
+                    u64 x = top[q].v[0] < r0 ? top[q].v[0] : r0;  // bitonic, holds the 32 smallest of the union
+                    bitonic_merge32(x, lane);
+                    top[q].v[0] = x;
+                } else {
+                    const u64 r1 = shfl_xor_t<u64>(n1, 31), r0 = shfl_xor_t<u64>(n0, 31);
+                    u64 x0 = top[q].v[0] < r1 ? top[q].v[0] : r1;   // list[i] vs new[63-i]
+                    u64 x1 = top[q].v[kSlots - 1] < r0 ? top[q].v[kSlots - 1] : r0;
+                    const u64 lo = x0 < x1 ? x0 : x1, hi = x0 < x1 ? x1 : x0;
+                    x0 = lo; x1 = hi;
+                    bitonic_merge32(x0, lane);
+                    bitonic_merge32(x1, lane);
+                    top[q].v[0] = x0; top[q].v[kSlots - 1] = x1;
+                }
+            } else {
+                // more than 64 candidates within T (heavy ties): one-at-a-time insertion, always correct
+#pragma unroll
+                for (int s = 0; s < kSPL; ++s) {  // unrolled: dist[][] must stay in registers (static indices only)
+                    const float v = dist[q][s];
+                    const int j = blk0 + (s / kCPL) * kTileC + (s % kCPL) * 32 + lane;
+                    const u64 key = (v < INFINITY) ? (((u64)__float_as_uint(v) << 32) | (unsigned)j) : kKeyInf;
+                    unsigned m = __ballot_sync(0xffffffffu, key < thr[q]);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const u64 kk = __shfl_sync(0xffffffffu, key, src);
+                        if (kk < thr[q]) {
+                            top[q].insert(kk, lane);
+                            thr[q] = top[q].get(p.K);
+                        }
                     }
                 }
             }
+            thr[q] = top[q].get(p.K);
+            __syncwarp();  // buf is reused by the next query
         }
     }
 
     // ---- emit ranks 1..K of each query (rank 0 dropped by position, dgcnn.jl:6) --------------------
 #pragma unroll
-    for (int q = 0; q < kQPW; ++q) {
-        const int qi = q0 + warp * kQPW + q;
+    for (int q = 0; q < kQW; ++q) {
+        const int qi = q0 + warp * kQW + q;
         if (qi >= p.N) continue;  // warp-uniform
         const size_t obase = ((size_t)b * p.N + qi) * p.K;
 #pragma unroll
@@ -169,19 +306,48 @@ __global__ void __launch_bounds__(kThreadsK) knn_graph_kernel(KnnParams p) {
                 if (p.dist) p.dist[obase + e - 1] = __uint_as_float((unsigned)(key >> 32));
             }
         }
+        // gathered (F,K,N,B) and edge features (2F,K,N,B): the K*F (K*2F) floats of a query are contiguous, so lanes
+        // walk the flat index (coalesced stores); the neighbour id of rank k+1 comes from the list by shuffle
         if (p.gathered || p.edge) {
             const float* xi = Xb + (size_t)qi * p.F;
-            for (int k = 0; k < p.K; ++k) {
-                const int j = (int)(unsigned)(top[q].get(k + 1) & 0xffffffffu);
-                const float* xj = Xb + (size_t)j * p.F;
-                for (int d = lane; d < p.F; d += 32) {
-                    const float vj = __ldg(xj + d);
-                    if (p.gathered) p.gathered[(obase + k) * p.F + d] = vj;
-                    if (p.edge) {  // cat(X, KNNGraph - X; dims=1)  dgcnn.jl:45
-                        const float vi = __ldg(xi + d);
-                        float* o = p.edge + (obase + k) * 2 * p.F;
-                        o[d] = vi;
-                        o[p.F + d] = __fsub_rn(vj, vi);
+            const int W = p.edge ? 2 * p.F : p.F;               // floats per (query, k) in the widest output
+            const unsigned long long w_inv = (0x100000000ull / (unsigned)W) + 1ull;  // e / W by multiply-shift, e < 2^16
+            const int total = p.K * W;
+            if (W >= 32) {
+                // wide rows: one neighbour at a time, lanes across the row (coalesced), one list lookup per neighbour
+                for (int k = 0; k < p.K; ++k) {
+                    const float* xj = Xb + (size_t)(unsigned)(top[q].get(k + 1) & 0xffffffffu) * p.F;
+                    for (int c = lane; c < p.F; c += 32) {
+                        const float vj = __ldg(xj + c);
+                        if (p.gathered) p.gathered[(obase + k) * p.F + c] = vj;
+                        if (p.edge) {  // cat(X, KNNGraph - X; dims=1)  dgcnn.jl:45
+                            const float vi = __ldg(xi + c);
+                            float* o = p.edge + (obase + k) * 2 * p.F;
+                            o[c] = vi;
+                            o[p.F + c] = __fsub_rn(vj, vi);
+                        }
+                    }
+                }
+            } else {
+                // narrow rows (F = 3: 6 floats per neighbour): lanes walk the flat K*W index
+                for (int e0 = 0; e0 < total; e0 += 32) {
+                    const int e = e0 + lane;
+                    const int k = min((int)(((unsigned long long)(unsigned)e * w_inv) >> 32), p.K - 1), c = e - k * W;
+                    u64 key = 0;
+#pragma unroll
+                    for (int s = 0; s < kSlots; ++s) {
+                        const u64 t = __shfl_sync(0xffffffffu, top[q].v[s], (k + 1) & 31);
+                        if (((k + 1) >> 5) == s) key = t;
+                    }
+                    if (e < total) {
+                        const float* xj = Xb + (size_t)(unsigned)(key & 0xffffffffu) * p.F;
+                        if (p.edge) {  // cat(X, KNNGraph - X; dims=1)  dgcnn.jl:45
+                            const float v = (c < p.F) ? __ldg(xi + c) : __fsub_rn(__ldg(xj + c - p.F), __ldg(xi + c - p.F));
+                            p.edge[obase * 2 * p.F + e] = v;
+                            if (p.gathered && c >= p.F) p.gathered[(obase + k) * p.F + c - p.F] = __ldg(xj + c - p.F);
+                        } else {
+                            p.gathered[obase * p.F + e] = __ldg(xj + c);
+                        }
                     }
                 }
             }

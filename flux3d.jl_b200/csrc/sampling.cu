@@ -79,6 +79,7 @@ __device__ void build_cdf(const float* __restrict__ V, const int32_t* __restrict
     //    sum of <2^29 binary32 values of comparable exponent exactly, so the order of this reduction does
     //    not show in the result for real meshes.
     double mine = 0.0;
+#pragma unroll 4
     for (int f = tid; f < nF; f += kST) {
         const double a = (double)face_area(V, Fc, f);
         cdf[f] = (unsigned long long)__double_as_longlong(a);
@@ -217,8 +218,9 @@ extern "C" int32_t f3d_sample_points(const float* verts_padded, const int32_t* f
     p.Vmax = Vmax; p.Fmax = Fmax; p.S = S; p.eps = eps; p.seed = seed; p.offset = offset;
     p.inj_face = inj_face; p.inj_r1 = inj_r1; p.inj_r2 = inj_r2;
     p.samples = samples; p.face_idx_out = face_idx_out; p.cdf_ws = nullptr;
-    // enough CTAs to cover the chip about twice, at least one kST-wide pass of samples each
-    int chunks = std::max(1, std::min((S + kST - 1) / kST, (2 * 148 + Nmesh - 1) / Nmesh));
+    // one sample per thread: the draw path is a chain of dependent loads (CDF search -> face ids -> vertices), so
+    // the latency is paid once per CTA, not once per sample; rebuilding the CDF per CTA costs nF/256 areas per thread
+    int chunks = std::min((S + kST - 1) / kST, 65535);
     p.samples_per_cta = (S + chunks - 1) / chunks;
     chunks = (S + p.samples_per_cta - 1) / p.samples_per_cta;
     const size_t cdf_bytes = sizeof(unsigned long long) * (size_t)Fmax;
