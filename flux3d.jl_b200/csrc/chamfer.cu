@@ -369,7 +369,9 @@ struct FiltParams {
     float* maxna;      // [B][RB]  max |a'|² over the valid rows of the block
     float* maxnb;      // [B][CS]  max |b'|² over the valid columns of the tile
     float* centre;     // [B][4]   the centre used for this batch element (finalize recomputes |a'|², |b'|² with it)
-    unsigned* counter;
+    unsigned* counter;  // [0] finalize's block counter; zeroed by a memset node before every sweep, with:
+    int* rowdone;       // [B][RB]  tiles of the row block that have published their partials (target CS)
+    int* coldone;       // [B][CS]  tiles of the column split that have published their partials (target RB)
 };
 
 // The centre of a batch element is the mean of 32 + 32 strided sample points.  ANY point works (the bound uses the
@@ -402,7 +404,9 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
     const float* gB = p.Bp + (size_t)b * p.M * 3;
 
     DBG_T(0);
-    if (tid == 0 && cs == 0 && rb == 0 && b == 0) *p.counter = 0u;
+    // Programmatic dependent launch: let the finalize grid become resident as soon as every CTA of this grid has been
+    // dispatched; its blocks wait on rowdone/coldone, so they soak up the SM slots the last partial wave leaves idle.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) s_maxnb = 0u;
 
     // ---- prologue: issue EVERY global load first (centre samples, this thread's column pairs, this lane's rows),
@@ -438,7 +442,9 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
         cz += __shfl_xor_sync(0xffffffffu, cz, o);
     }
     cx *= (1.0f / 64.0f); cy *= (1.0f / 64.0f); cz *= (1.0f / 64.0f);
-    if (tid == 0 && cs == 0 && rb == 0) { p.centre[4 * b] = cx; p.centre[4 * b + 1] = cy; p.centre[4 * b + 2] = cz; }
+    // every tile publishes the (identical) centre and its norm maxima: a finalize block may only rely on the tiles
+    // of ITS row block / column split having finished
+    if (tid == 0) { p.centre[4 * b] = cx; p.centre[4 * b + 1] = cy; p.centre[4 * b + 2] = cz; }
     __syncthreads();  // s_maxnb = 0 visible
 
     // ---- stage the column tile: centred, pre-scaled by -2, with |b'|² -----------------------------------
@@ -485,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
     const float maxnb = __uint_as_float(s_maxnb);
     if (tid == 0) {
         p.maxnb[(size_t)b * p.CS + cs] = maxnb;
-        if (cs == 0) p.maxna[(size_t)b * p.RB + rb] = maxna;
+        p.maxna[(size_t)b * p.RB + rb] = maxna;
     }
     const float wt = kBallotAbs * (maxna + maxnb);
 
@@ -581,6 +587,13 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
             p.rowpart[base + rr] = best;
         }
     }
+    // publish: all of this tile's partials are in global memory before the counters move (release)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd(p.rowdone + (size_t)b * p.RB + rb, 1);
+        atomicAdd(p.coldone + (size_t)b * p.CS + cs, 1);
+    }
     DBG_T(3);
 }
 
@@ -594,6 +607,8 @@ struct FiltFinalizeParams {
     const float* maxna;
     const float* maxnb;
     const float* centre;
+    const int* rowdone;
+    const int* coldone;
     int32_t* nnA;
     int32_t* nnB;
     double* partial;
@@ -604,6 +619,12 @@ struct FiltFinalizeParams {
     float* loss;
     float* terms;
 };
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // exact (reference-arithmetic) argmin of |q - P[j]|² over j in [j0, j1), cooperatively by one warp, merged into the
 // running (dmin, jmin) with the lowest-index tie rule.  q is warp-uniform; the result is valid in every lane.
@@ -670,6 +691,13 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_filter_finalize_kernel(Fi
     bool amb = false;
     if (valid) {
         b = (int)(t / Q); q = (int)(t - (long)b * Q);
+        // wait until every sweep tile of this item's row block / column split has published (this grid is launched
+        // programmatically and may be resident while the sweep's last wave is still running)
+        {
+            const int* flag = rows ? p.rowdone + (size_t)b * p.RB + q / kTileRows : p.coldone + (size_t)b * p.CS + q / p.BN;
+            const int target = rows ? p.CS : p.RB;
+            while (ld_acquire(flag) < target) __nanosleep(200);
+        }
         const float* c = p.centre + 4 * b;
         const float* pt = gQ + ((size_t)b * Q + q) * 3;
         const float x = __ldg(pt) - __ldcg(c), y = __ldg(pt + 1) - __ldcg(c + 1), z = __ldg(pt + 2) - __ldcg(c + 2);
@@ -806,7 +834,7 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_filter_finalize_kernel(Fi
 
 struct FiltPlan {
     int cols_per_warp, BN, CS, RB, Npad, Mpad, nbA, nbB;
-    size_t off_rowpart, off_colpart, off_maxna, off_maxnb, off_centre, off_partial, off_counter, total;
+    size_t off_rowpart, off_colpart, off_maxna, off_maxnb, off_centre, off_partial, off_counter, counter_bytes, total;
 };
 
 FiltPlan make_filt_plan(int B, int N, int M) {
@@ -828,7 +856,9 @@ FiltPlan make_filt_plan(int B, int N, int M) {
     pl.off_maxnb = o;   o = align_up(o + sizeof(float) * (size_t)B * pl.CS, 256);
     pl.off_centre = o;  o = align_up(o + sizeof(float) * 4 * (size_t)B, 256);
     pl.off_partial = o; o = align_up(o + sizeof(double) * (size_t)(pl.nbA + pl.nbB), 256);
-    pl.off_counter = o; o = align_up(o + sizeof(unsigned), 256);
+    // [0..63] finalize block counter | rowdone [B][RB] | coldone [B][CS]  — one memset zeroes all of it per call
+    pl.counter_bytes = 256 + sizeof(int) * ((size_t)B * pl.RB + (size_t)B * pl.CS);
+    pl.off_counter = o; o = align_up(o + pl.counter_bytes, 256);
     pl.total = o;
     return pl;
 }
@@ -880,6 +910,9 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
         sp.maxnb = reinterpret_cast<float*>(w + fl.off_maxnb);
         sp.centre = reinterpret_cast<float*>(w + fl.off_centre);
         sp.counter = reinterpret_cast<unsigned*>(w + fl.off_counter);
+        sp.rowdone = reinterpret_cast<int*>(w + fl.off_counter + 256);
+        sp.coldone = sp.rowdone + (size_t)B * fl.RB;
+        F3D_CUDA(cudaMemsetAsync(w + fl.off_counter, 0, fl.counter_bytes, stream));
         const size_t smem = filt_smem_bytes(fl.BN);
         F3D_CUDA(cudaFuncSetAttribute(chamfer_filter_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         chamfer_filter_sweep_kernel<<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
@@ -888,7 +921,7 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
         FiltFinalizeParams fp;
         fp.A = A; fp.Bp = Bp; fp.B = B; fp.N = N; fp.M = M;
         fp.CS = fl.CS; fp.RB = fl.RB; fp.Npad = fl.Npad; fp.Mpad = fl.Mpad; fp.BN = fl.BN;
-        fp.rowpart = sp.rowpart; fp.colpart = sp.colpart; fp.maxna = sp.maxna; fp.maxnb = sp.maxnb; fp.centre = sp.centre;
+        fp.rowpart = sp.rowpart; fp.colpart = sp.colpart; fp.maxna = sp.maxna; fp.maxnb = sp.maxnb; fp.centre = sp.centre; fp.rowdone = sp.rowdone; fp.coldone = sp.coldone;
         fp.nnA = nnA_dev; fp.nnB = nnB_dev;
         fp.partial = reinterpret_cast<double*>(w + fl.off_partial);
         fp.counter = sp.counter;
@@ -897,7 +930,16 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
         fp.denomA = (double)N * (double)B_total;
         fp.denomB = (double)M * (double)B_total;
         fp.loss = loss_dev; fp.terms = terms_dev;
-        chamfer_filter_finalize_kernel<<<fl.nbA + fl.nbB, kFinThreads, 0, stream>>>(fp);
+        {
+            // programmatic dependent launch: blocks may start while the sweep's last wave is still running
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(fl.nbA + fl.nbB); cfg.blockDim = dim3(kFinThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_filter_finalize_kernel, fp));
+        }
         F3D_CHECK_LAUNCH("chamfer_filter_finalize_kernel");
         return F3D_OK;
     }
