@@ -37,8 +37,10 @@ SIGNATURES = {
     "f3d_edge_loss": (C.c_int32, [_f32p, _i32p, C.c_int32, C.c_int32, C.c_float, _f32p, _vp, C.c_size_t, _vp]),
     "f3d_sample_points_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "f3d_sample_points": (C.c_int32, [_f32p, _i32p, _i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                      C.c_double, C.c_uint64, C.c_uint64, _i32p, _f32p, _f32p, _f32p, _i32p,
+                                      C.c_double, C.c_uint64, C.c_uint64, _i32p, _f32p, _f32p, _f32p, _i32p, _f32p,
                                       _vp, C.c_size_t, _vp]),
+    "f3d_sample_points_bwd": (C.c_int32, [_f32p, _i32p, _f32p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _vp]),
+    "f3d_edge_loss_bwd": (C.c_int32, [_f32p, _i32p, _i32p, C.c_int32, C.c_int32, C.c_float, _f32p, _f32p, _vp]),
     "f3d_comm_unique_id_host": (C.c_int32, [_vp]),
     "f3d_comm_init": (C.c_int32, [C.c_int32, C.c_int32, _vp, C.POINTER(C.c_void_p)]),
     "f3d_allreduce_sum_f32": (C.c_int32, [_vp, _f32p, C.c_int32, _vp]),

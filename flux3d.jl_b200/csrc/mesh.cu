@@ -222,6 +222,27 @@ __global__ void __launch_bounds__(kMT) edge_loss_kernel(const float* __restrict_
     block_reduce_finish(mine, ws, denom, loss);
 }
 
+// edge_loss pullback, gathered per vertex over its neighbours (the Laplacian's off-diagonal columns)
+__global__ void __launch_bounds__(kMT) edge_loss_bwd_kernel(const float* __restrict__ verts, const int32_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ colidx, int nV, float scale, float target,
+                                                            const float* __restrict__ gout, float* __restrict__ gverts) {
+    const int i = blockIdx.x * kMT + threadIdx.x;
+    if (i >= nV) return;
+    const float xi = __ldg(verts + 3 * (size_t)i), yi = __ldg(verts + 3 * (size_t)i + 1), zi = __ldg(verts + 3 * (size_t)i + 2);
+    float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+    const int p0 = __ldg(rowptr + i), p1 = __ldg(rowptr + i + 1);
+    for (int p = p0; p < p1; ++p) {
+        const int j = __ldg(colidx + p);
+        if (j == i) continue;
+        const float dx = xi - __ldg(verts + 3 * (size_t)j), dy = yi - __ldg(verts + 3 * (size_t)j + 1), dz = zi - __ldg(verts + 3 * (size_t)j + 2);
+        const float n = norm3(dx, dy, dz);
+        const float c = n > 0.0f ? (n - target) / n : 0.0f;
+        gx += c * dx; gy += c * dy; gz += c * dz;
+    }
+    const float s = __ldg(gout) * scale;
+    gverts[3 * (size_t)i] = s * gx; gverts[3 * (size_t)i + 1] = s * gy; gverts[3 * (size_t)i + 2] = s * gz;
+}
+
 size_t reduce_ws_bytes(int n) {
     const int blocks = (n + kMT - 1) / kMT;
     return align_up(sizeof(double) * (size_t)blocks, 256) + 256;
@@ -313,6 +334,17 @@ extern "C" int32_t f3d_edge_loss(const float* verts, const int32_t* edges, int32
     F3D_CUDA(cudaMemsetAsync(r.counter, 0, sizeof(unsigned), stream));
     edge_loss_kernel<<<(nE + kMT - 1) / kMT, kMT, 0, stream>>>(verts, edges, nE, target, (double)nE_total, r, loss_dev);
     F3D_CHECK_LAUNCH("edge_loss_kernel");
+    return F3D_OK;
+}
+
+extern "C" int32_t f3d_edge_loss_bwd(const float* verts, const int32_t* rowptr, const int32_t* colidx, int32_t nV,
+                                     int32_t nE_total, float target, const float* gout_dev, float* gverts,
+                                     f3d_stream_t stream_) {
+    if (!verts || !rowptr || !colidx || !gout_dev || !gverts) return fail(F3D_ERR_INVALID, "f3d_edge_loss_bwd: null pointer");
+    if (nV <= 0 || nE_total <= 0) return fail(F3D_ERR_INVALID, "f3d_edge_loss_bwd: nV and nE_total must be positive (got %d, %d)", nV, nE_total);
+    edge_loss_bwd_kernel<<<(nV + kMT - 1) / kMT, kMT, 0, static_cast<cudaStream_t>(stream_)>>>(
+        verts, rowptr, colidx, nV, 2.0f / (float)nE_total, target, gout_dev, gverts);
+    F3D_CHECK_LAUNCH("edge_loss_bwd_kernel");
     return F3D_OK;
 }
 

@@ -49,6 +49,7 @@ struct SampleParams {
     const float* inj_r2;
     float* samples;          // [Nmesh][S][3]
     int32_t* face_idx_out;   // [Nmesh][S] or null
+    float* bary_out;         // [Nmesh][S][3] or null
     unsigned long long* cdf_ws;  // [Nmesh][Fmax] (two-pass path only)
     int samples_per_cta;
 };
@@ -146,6 +147,7 @@ __device__ __forceinline__ void draw_and_emit(const SampleParams& p, int mesh, i
     if (nF <= 0 || face < 0 || face >= nF) {  // empty mesh / bad injected id: defined output, flagged by -1
         out[0] = out[1] = out[2] = 0.0f;
         if (p.face_idx_out) p.face_idx_out[o] = -1;
+        if (p.bary_out) { p.bary_out[3 * o] = 0.f; p.bary_out[3 * o + 1] = 0.f; p.bary_out[3 * o + 2] = 0.f; }
         return;
     }
     const float* v1 = V + 3 * (size_t)__ldg(Fc + 3 * (size_t)face);
@@ -159,6 +161,7 @@ __device__ __forceinline__ void draw_and_emit(const SampleParams& p, int mesh, i
     for (int d = 0; d < 3; ++d)                           // :71
         out[d] = __fadd_rn(__fadd_rn(__fmul_rn(w1, __ldg(v1 + d)), __fmul_rn(w2, __ldg(v2 + d))), __fmul_rn(w3, __ldg(v3 + d)));
     if (p.face_idx_out) p.face_idx_out[o] = face;
+    if (p.bary_out) { p.bary_out[3 * o] = w1; p.bary_out[3 * o + 1] = w2; p.bary_out[3 * o + 2] = w3; }
 }
 
 // fused: grid (chunks, Nmesh); dynamic smem = 8*Fmax bytes (0 when the draws are injected)
@@ -190,6 +193,29 @@ __global__ void __launch_bounds__(kST) sample_points_draw_kernel(SampleParams p)
     for (int s = s0 + threadIdx.x; s < s1; s += kST) draw_and_emit(p, mesh, nF, V, Fc, p.cdf_ws + (size_t)mesh * p.Fmax, s);
 }
 
+// pullback: one thread per (sample, corner-coordinate triple)
+__global__ void __launch_bounds__(kST) sample_points_bwd_kernel(const float* __restrict__ g, const int32_t* __restrict__ fidx,
+                                                                const float* __restrict__ bary, const int32_t* __restrict__ faces,
+                                                                int Vmax, int Fmax, int S, long total, float* __restrict__ gv) {
+    const long o = (long)blockIdx.x * kST + threadIdx.x;
+    if (o >= total) return;
+    const int mesh = (int)(o / S);
+    const int face = __ldg(fidx + o);
+    if (face < 0 || face >= Fmax) return;
+    const float gx = __ldg(g + 3 * o), gy = __ldg(g + 3 * o + 1), gz = __ldg(g + 3 * o + 2);
+    const int32_t* fc = faces + ((size_t)mesh * Fmax + face) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int v = __ldg(fc + k);
+        if (v < 0 || v >= Vmax) continue;
+        const float w = __ldg(bary + 3 * o + k);
+        float* dst = gv + ((size_t)mesh * Vmax + v) * 3;
+        atomicAdd(dst, w * gx);
+        atomicAdd(dst + 1, w * gy);
+        atomicAdd(dst + 2, w * gz);
+    }
+}
+
 }  // namespace
 }  // namespace f3d
 
@@ -205,7 +231,7 @@ extern "C" int32_t f3d_sample_points(const float* verts_padded, const int32_t* f
                                      const int32_t* faces_len, int32_t Nmesh, int32_t Vmax, int32_t Fmax, int32_t S,
                                      double eps, uint64_t seed, uint64_t offset, const int32_t* inj_face,
                                      const float* inj_r1, const float* inj_r2, float* samples, int32_t* face_idx_out,
-                                     void* ws, size_t ws_bytes, f3d_stream_t stream_) {
+                                     float* bary_out, void* ws, size_t ws_bytes, f3d_stream_t stream_) {
     (void)verts_len;  // faces only reference valid vertices; kept in the ABI to mirror verts[:, 1:_verts_len[i], i] (:52)
     if (!verts_padded || !faces_padded || !faces_len || !samples) return fail(F3D_ERR_INVALID, "f3d_sample_points: null pointer");
     if (Nmesh <= 0 || Vmax <= 0 || Fmax <= 0 || S <= 0) return fail(F3D_ERR_INVALID, "f3d_sample_points: Nmesh, Vmax, Fmax, S must be positive (got %d, %d, %d, %d)", Nmesh, Vmax, Fmax, S);
@@ -217,7 +243,7 @@ extern "C" int32_t f3d_sample_points(const float* verts_padded, const int32_t* f
     p.verts = verts_padded; p.faces = faces_padded; p.faces_len = faces_len;
     p.Vmax = Vmax; p.Fmax = Fmax; p.S = S; p.eps = eps; p.seed = seed; p.offset = offset;
     p.inj_face = inj_face; p.inj_r1 = inj_r1; p.inj_r2 = inj_r2;
-    p.samples = samples; p.face_idx_out = face_idx_out; p.cdf_ws = nullptr;
+    p.samples = samples; p.face_idx_out = face_idx_out; p.bary_out = bary_out; p.cdf_ws = nullptr;
     // one sample per thread: the draw path is a chain of dependent loads (CDF search -> face ids -> vertices), so
     // the latency is paid once per CTA, not once per sample; rebuilding the CDF per CTA costs nF/256 areas per thread
     int chunks = std::min((S + kST - 1) / kST, 65535);
@@ -238,5 +264,17 @@ extern "C" int32_t f3d_sample_points(const float* verts_padded, const int32_t* f
         sample_points_draw_kernel<<<dim3(chunks, Nmesh), kST, 0, stream>>>(p);
         F3D_CHECK_LAUNCH("sample_points_draw_kernel");
     }
+    return F3D_OK;
+}
+
+extern "C" int32_t f3d_sample_points_bwd(const float* gsamples, const int32_t* face_idx, const float* bary,
+                                         const int32_t* faces_padded, int32_t Nmesh, int32_t Vmax, int32_t Fmax, int32_t S,
+                                         float* gverts_padded, f3d_stream_t stream_) {
+    if (!gsamples || !face_idx || !bary || !faces_padded || !gverts_padded) return fail(F3D_ERR_INVALID, "f3d_sample_points_bwd: null pointer");
+    if (Nmesh <= 0 || Vmax <= 0 || Fmax <= 0 || S <= 0) return fail(F3D_ERR_INVALID, "f3d_sample_points_bwd: Nmesh, Vmax, Fmax, S must be positive (got %d, %d, %d, %d)", Nmesh, Vmax, Fmax, S);
+    const long total = (long)Nmesh * S;
+    sample_points_bwd_kernel<<<(unsigned)((total + kST - 1) / kST), kST, 0, static_cast<cudaStream_t>(stream_)>>>(
+        gsamples, face_idx, bary, faces_padded, Vmax, Fmax, S, total, gverts_padded);
+    F3D_CHECK_LAUNCH("sample_points_bwd_kernel");
     return F3D_OK;
 }

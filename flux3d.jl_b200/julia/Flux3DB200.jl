@@ -166,9 +166,9 @@ function Flux3D.sample_points(m::TriMesh{Float32,R,CuArray}, num_samples::Int = 
     ws = workspace((:sample, m.N, m.F), nws)
     check(ccall((:f3d_sample_points, LIB), Int32,
         (Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Int32, Int32, Int32, Float64, UInt64, UInt64,
-         Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+         Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
         devptr(verts), devptr(faces), devptr(vlen), devptr(flen), m.N, m.V, m.F, num_samples, Float64(eps), seed, offset,
-        C_NULL, C_NULL, C_NULL, devptr(samples), C_NULL, devptr(ws), length(ws), cur_stream()))
+        C_NULL, C_NULL, C_NULL, devptr(samples), C_NULL, C_NULL, devptr(ws), length(ws), cur_stream()))
     return samples
 end
 

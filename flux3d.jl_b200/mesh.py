@@ -352,16 +352,36 @@ def laplacian_loss(m: TriMesh, *, verts_total: int = 0) -> torch.Tensor:
     return _LaplacianLossFn.apply(m.get_verts_packed().contiguous(), m, int(verts_total))
 
 
+class _EdgeLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, mesh, target, edges_total):
+        L = _lib.lib()
+        edges = mesh._topo_device("edges")
+        nE = int(edges.shape[0])
+        dev = verts.device
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(("edge", nE), L.f3d_edge_loss_workspace_bytes(nE), dev)
+            _lib.check(L.f3d_edge_loss(_lib.ptr(verts), _lib.ptr(edges), nE, int(edges_total), float(target),
+                                       _lib.ptr(loss), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+        ctx.save_for_backward(verts)
+        ctx.mesh, ctx.target, ctx.total = mesh, float(target), int(edges_total) or nE
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        (verts,) = ctx.saved_tensors
+        L, mesh = _lib.lib(), ctx.mesh
+        g = gout.to(torch.float32).reshape(1).contiguous()
+        gverts = torch.empty_like(verts)
+        with torch.cuda.device(verts.device):
+            _lib.check(L.f3d_edge_loss_bwd(_lib.ptr(verts), _lib.ptr(mesh._topo_device("rowptr")),
+                                           _lib.ptr(mesh._topo_device("colidx")), verts.shape[0], ctx.total, ctx.target,
+                                           _lib.ptr(g), _lib.ptr(gverts), _lib.stream_ptr(verts.device)))
+        return gverts, None, None, None
+
+
 def edge_loss(m: TriMesh, target_length: float = 0.0, *, edges_total: int = 0) -> torch.Tensor:
-    """edge_loss(m, target_length=0.0) — src/metrics/mesh.jl:24-32 (forward)."""
-    L = _lib.lib()
-    verts = m.get_verts_packed().detach().contiguous()
-    edges = m._topo_device("edges")
-    nE = int(edges.shape[0])
-    dev = verts.device
-    loss = torch.empty(1, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        ws = _lib.workspace(("edge", nE), L.f3d_edge_loss_workspace_bytes(nE), dev)
-        _lib.check(L.f3d_edge_loss(_lib.ptr(verts), _lib.ptr(edges), nE, int(edges_total), float(target_length),
-                                   _lib.ptr(loss), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
-    return loss.reshape(())
+    """edge_loss(m, target_length=0.0) — src/metrics/mesh.jl:24-32: mean over the unique edges of
+    (‖v1 - v2‖ - target)², differentiable w.r.t. the vertices."""
+    return _EdgeLossFn.apply(m.get_verts_packed().contiguous(), m, float(target_length), int(edges_total))

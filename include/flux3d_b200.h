@@ -158,6 +158,12 @@ F3D_API int32_t f3d_laplacian_loss_bwd(const float* verts, const int32_t* lap_ro
 F3D_API size_t f3d_edge_loss_workspace_bytes(int32_t nE);
 F3D_API int32_t f3d_edge_loss(const float* verts, const int32_t* edges, int32_t nE, int32_t nE_total,
                       float target, float* loss_dev, void* ws, size_t ws_bytes, f3d_stream_t stream);
+/* Pullback: gverts[i] = gout * Σ_{j ∈ N(i)} (2/nE_total) (‖v_i - v_j‖ - target) (v_i - v_j)/‖v_i - v_j‖   (0 where the
+ * norm is 0), gathered over the vertex's neighbours = the off-diagonal columns of the Laplacian CSR
+ * (deterministic, no atomics).  nE_total: the edge count of the mean (0 = the nE implied by the CSR). */
+F3D_API int32_t f3d_edge_loss_bwd(const float* verts, const int32_t* lap_rowptr, const int32_t* lap_colidx,
+                          int32_t nV, int32_t nE_total, float target, const float* gout_dev,
+                          float* gverts, f3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * sample_points — replaces sample_points/_sample_points/_rand_barycentric_coords
@@ -168,6 +174,8 @@ F3D_API int32_t f3d_edge_loss(const float* verts, const int32_t* edges, int32_t 
  *   (seed, offset) — counter (s, mesh) — unless inj_face/inj_r1/inj_r2 ([Nmesh][S], device) are given,
  *   in which case the face ids and the two uniforms are taken from them (bit-parity mode; the
  *   reference's own draws come from Julia's global RNG and cannot be reproduced).
+ *   bary_out [Nmesh][S][3] (optional) receives the barycentric weights (w1,w2,w3) of every sample — with
+ *   face_idx_out it is what the pullback needs.
  *   ws: f3d_sample_points_workspace_bytes(Nmesh, Fmax).
  * ---------------------------------------------------------------------------------------------- */
 F3D_API size_t f3d_sample_points_workspace_bytes(int32_t Nmesh, int32_t Fmax);
@@ -175,8 +183,15 @@ F3D_API int32_t f3d_sample_points(const float* verts_padded, const int32_t* face
                           const int32_t* verts_len, const int32_t* faces_len, int32_t Nmesh,
                           int32_t Vmax, int32_t Fmax, int32_t S, double eps, uint64_t seed,
                           uint64_t offset, const int32_t* inj_face, const float* inj_r1,
-                          const float* inj_r2, float* samples, int32_t* face_idx_out, void* ws,
-                          size_t ws_bytes, f3d_stream_t stream);
+                          const float* inj_r2, float* samples, int32_t* face_idx_out, float* bary_out,
+                          void* ws, size_t ws_bytes, f3d_stream_t stream);
+/* Pullback of _sample_points (src/transforms/mesh_func.jl:60-73; the face draws are constants, :47 is @ignore):
+ *   gverts_padded[mesh][faces[face][k]] += w_k * gsamples[mesh][s]   for the three corners k of every sample.
+ * gverts_padded [Nmesh][Vmax][3] is ACCUMULATED into (zero it first); float RED.ADD, so the summation order —
+ * and with it the last bit — may vary from run to run. */
+F3D_API int32_t f3d_sample_points_bwd(const float* gsamples, const int32_t* face_idx, const float* bary,
+                              const int32_t* faces_padded, int32_t Nmesh, int32_t Vmax, int32_t Fmax,
+                              int32_t S, float* gverts_padded, f3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU: the batch axis is sharded across ranks (one process per GPU); the only data-path

@@ -22,7 +22,7 @@ def _declared_symbols():
 
 def test_header_symbols_exported_and_bound(f3d):
     declared = _declared_symbols()
-    assert len(declared) >= 21
+    assert len(declared) >= 23
     out = subprocess.check_output(["nm", "-D", "--defined-only", f3d.LIB_PATH], text=True)
     exported = set(re.findall(r"\bT (f3d_\w+)", out))
     assert set(declared) <= exported, sorted(set(declared) - exported)
@@ -66,7 +66,7 @@ def test_argument_errors_are_status_codes(f3d):
     assert L.f3d_knn_graph(dummy, 1, 10, 3, 10, dummy, None, None, None, None, 0, 0, None) == 1  # K >= N
     assert L.f3d_knn_graph(dummy, 1, 100, 3, 64, dummy, None, None, None, None, 0, 0, None) == 1  # K > 63
     assert L.f3d_verts_normals(dummy, dummy, dummy, dummy, 4, 4, 7, dummy, None) == 1  # unknown mode
-    assert L.f3d_sample_points(dummy, dummy, None, dummy, 1, 4, 4, 0, 1e-6, 0, 0, None, None, None, dummy, None, None, 0, None) == 1
+    assert L.f3d_sample_points(dummy, dummy, None, dummy, 1, 4, 4, 0, 1e-6, 0, 0, None, None, None, dummy, None, None, None, 0, None) == 1
     assert L.f3d_laplacian_loss(dummy, dummy, dummy, dummy, 4, 0, dummy, None, 0, None) == 3
     with pytest.raises(f3d.Flux3DB200Error):
         f3d._lib.check(1)

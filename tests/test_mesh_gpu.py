@@ -96,3 +96,39 @@ def test_laplacian_sharded_sum(f3d, oracle, golden_dir):
     tot = sum(v.shape[0] for v in vl)
     parts = [float(f3d.laplacian_loss(f3d.TriMesh(vl[a:b], fl[a:b]), verts_total=tot).item()) for a, b in ((0, 2), (2, 4))]
     assert abs(sum(parts) - full) <= 1e-6 * full
+
+
+def test_edge_loss_backward(f3d, oracle, golden_dir):
+    """edge_loss pullback vs float64 torch autograd of the same expression (reference: `gradient(...) isa Tuple`)."""
+    vt, ft = oracle.load_obj(os.path.join(golden_dir, "teapot.obj"))
+    m = f3d.TriMesh([vt], [ft])
+    for target in (0.0, 0.05):
+        verts = m.get_verts_packed().clone().requires_grad_(True)
+        (f3d.edge_loss(f3d.TriMesh._from_packed(m, verts), target) * 2.5).backward()
+        e = torch.from_numpy(m.get_edges_packed().astype(np.int64))
+        x = torch.from_numpy(vt.astype(np.float64)).requires_grad_(True)
+        ((((x[e[:, 0]] - x[e[:, 1]]).norm(dim=1) - target) ** 2).mean() * 2.5).backward()
+        assert torch.allclose(verts.grad.cpu().double(), x.grad, rtol=1e-4, atol=1e-8)
+
+
+def test_fit_mesh_step(f3d, oracle, golden_dir):
+    """The reference's training objective (examples/fit_mesh.jl:78-84): chamfer(sample(src + offset), sample(tgt)) +
+    0.1 laplacian + edge loss, differentiated w.r.t. the offsets — a few SGD steps on the device must lower it."""
+    vs, fs = oracle.load_obj(os.path.join(golden_dir, "sphere.obj"))
+    vt, ft = oracle.load_obj(os.path.join(golden_dir, "teapot.obj"))
+    vt = (vt - vt.mean(0)) / np.abs(vt - vt.mean(0)).max()
+    src, tgt = f3d.TriMesh([vs], [fs]), f3d.TriMesh([vt.astype(np.float32)], [ft])
+    offs = torch.zeros_like(src.get_verts_packed(), requires_grad=True)
+    opt = torch.optim.SGD([offs], lr=1.0, momentum=0.9)
+    losses = []
+    for it in range(12):
+        opt.zero_grad()
+        m = f3d.offset(src, offs)
+        a = f3d.sample_points(m, 5000, seed=100 + it)
+        b = f3d.sample_points(tgt, 5000, seed=200 + it)
+        loss = f3d.chamfer_distance(a, b) + 0.1 * f3d.laplacian_loss(m) + f3d.edge_loss(m)
+        loss.backward()
+        assert torch.isfinite(offs.grad).all() and float(offs.grad.abs().max()) > 0
+        opt.step()
+        losses.append(float(loss.item()))
+    assert losses[-1] < 0.8 * losses[0], losses

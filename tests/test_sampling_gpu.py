@@ -80,3 +80,32 @@ def test_mesh_chamfer(f3d, golden_dir):
     m = f3d.load_trimesh([os.path.join(golden_dir, "teapot.obj"), os.path.join(golden_dir, "sphere.obj")])
     loss = f3d.chamfer_distance(m, m)
     assert 0.0 <= float(loss.item()) <= 1e-2
+
+
+def test_sample_points_backward(f3d, oracle, golden_dir):
+    """Pullback of the barycentric combination: gverts[face corner k] += w_k * gsample.  Injected draws make the
+    weights known analytically; the float64 restatement goes through torch autograd (atomics: rtol 1e-4)."""
+    vt, ft = oracle.load_obj(os.path.join(golden_dir, "teapot.obj"))
+    vs, fs = oracle.load_obj(os.path.join(golden_dir, "sphere.obj"))
+    m0 = f3d.TriMesh([vt, vs], [ft, fs])
+    verts = m0.get_verts_packed().clone().requires_grad_(True)
+    m = f3d.TriMesh._from_packed(m0, verts)
+    rng = np.random.default_rng(8)
+    S = 3000
+    jf = np.stack([rng.integers(0, n, S) for n in (ft.shape[0], fs.shape[0])]).astype(np.int32)
+    r1 = rng.random((2, S), dtype=np.float32)
+    r2 = rng.random((2, S), dtype=np.float32)
+    pts = f3d.sample_points(m, S, inj_face=torch.from_numpy(jf), inj_r1=torch.from_numpy(r1), inj_r2=torch.from_numpy(r2))
+    w = torch.randn_like(pts)
+    (pts * w).sum().backward()
+    x = m0.get_verts_padded().double().clone().requires_grad_(True)
+    fp = torch.from_numpy(m0.get_faces_padded().astype(np.int64)).cuda()
+    u = torch.from_numpy(np.sqrt(r1.astype(np.float64))).cuda()
+    v = torch.from_numpy(r2.astype(np.float64)).cuda()
+    wts = torch.stack([1 - u, u * (1 - v), u * v], dim=-1)                                  # (N, S, 3)
+    tri = torch.stack([x[i][fp[i][torch.from_numpy(jf[i].astype(np.int64)).cuda()]] for i in range(2)])  # (N, S, 3, 3)
+    ref_pts = (wts.unsqueeze(-1) * tri).sum(2)
+    assert torch.allclose(pts.double(), ref_pts, rtol=1e-5, atol=1e-6)
+    (ref_pts * w.double()).sum().backward()
+    g_ref = torch.cat([x.grad[0, :vt.shape[0]], x.grad[1, :vs.shape[0]]])
+    assert torch.allclose(verts.grad.double(), g_ref, rtol=1e-4, atol=1e-5)
