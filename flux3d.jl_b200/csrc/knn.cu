@@ -358,12 +358,16 @@ __global__ void __launch_bounds__(kThreadsK, 2) knn_graph_kernel(KnnParams p) {
 size_t knn_smem_bytes(int Fp) { return sizeof(float) * (size_t)(kQPC + kTileC) * (Fp + 4); }
 
 }  // namespace
+
+// knn_tc.cu: the tensor-core (tcgen05) path for N <= 1024, F <= 64
+bool knn_tc_supported(int N, int F, int K);
+int32_t knn_tc_launch(const float* X, int B, int N, int F, int K, int32_t* idx, float* dist, float* gathered, float* edge, unsigned* stats, cudaStream_t stream);
 }  // namespace f3d
 
-extern "C" size_t f3d_knn_graph_workspace_bytes(int32_t, int32_t, int32_t, int32_t) { return 0; }
+extern "C" size_t f3d_knn_graph_workspace_bytes(int32_t, int32_t, int32_t, int32_t) { return 256; }
 
 extern "C" int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F, int32_t K, int32_t* idx,
-                                 float* dist, float* gathered, float* edge_feat, void* /*ws*/, size_t /*ws_bytes*/,
+                                 float* dist, float* gathered, float* edge_feat, void* ws, size_t ws_bytes,
                                  int32_t flags, f3d_stream_t stream_) {
     using namespace f3d;
     if (!X || !idx) return fail(F3D_ERR_INVALID, "f3d_knn_graph: null X/idx pointer");
@@ -372,8 +376,12 @@ extern "C" int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F
     if (K > 63) return fail(F3D_ERR_INVALID, "f3d_knn_graph: K must be <= 63 (got %d)", K);
     if (F > 256) return fail(F3D_ERR_INVALID, "f3d_knn_graph: F must be <= 256 (got %d)", F);
     if (B > 65535) return fail(F3D_ERR_INVALID, "f3d_knn_graph: B must be <= 65535 per call");
-    if (flags != F3D_FLAG_NONE) return fail(F3D_ERR_INVALID, "f3d_knn_graph: no flags are defined for this call");
+    if (flags & ~(F3D_FLAG_EXACT_SWEEP | F3D_FLAG_TENSOR)) return fail(F3D_ERR_INVALID, "f3d_knn_graph: only F3D_FLAG_EXACT_SWEEP / F3D_FLAG_TENSOR are defined for this call");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    // default for wide features (F >= 16, where evaluating the distances dominates): Gram matrix on the tensor cores
+    // as a filter + exact re-evaluation (bit-identical results); narrow features are selection-bound and stay on the CUDA cores;
+    // F3D_FLAG_EXACT_SWEEP or shapes outside that path: every pair in the reference arithmetic on the CUDA cores
+    if (!(flags & F3D_FLAG_EXACT_SWEEP) && (F >= 16 || (flags & F3D_FLAG_TENSOR)) && knn_tc_supported(N, F, K)) return knn_tc_launch(X, B, N, F, K, idx, dist, gathered, edge_feat, (ws && ws_bytes >= 8) ? static_cast<unsigned*>(ws) : nullptr, stream);
     KnnParams p;
     p.X = X; p.N = N; p.F = F; p.Fp = (F + 3) / 4 * 4; p.K = K;
     p.idx = idx; p.dist = dist; p.gathered = gathered; p.edge = edge_feat;

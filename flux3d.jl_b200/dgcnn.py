@@ -12,7 +12,8 @@ from . import _lib
 from .pcloud import as_f32_tensor
 
 
-def knn_graph(X, K: int, *, want_dist: bool = False, want_gathered: bool = False, want_edge: bool = False):
+def knn_graph(X, K: int, *, want_dist: bool = False, want_gathered: bool = False, want_edge: bool = False, flags: int = 0,
+              want_stats: bool = False):
     """For every point of every cloud the K nearest OTHER points, sorted ascending by (distance, index);
     the first hit of the (K+1)-list is dropped by position exactly as dgcnn.jl:6 does.
     X: (B, N, F) or (N, F).  Returns dict(idx (B,N,K) int32 [, dist (B,N,K)] [, gathered (B,N,K,F)]
@@ -29,10 +30,13 @@ def knn_graph(X, K: int, *, want_dist: bool = False, want_gathered: bool = False
     dist = torch.empty((B, N, K), dtype=torch.float32, device=dev) if want_dist else None
     gat = torch.empty((B, N, K, F), dtype=torch.float32, device=dev) if want_gathered else None
     edge = torch.empty((B, N, K, 2 * F), dtype=torch.float32, device=dev) if want_edge else None
+    stats = torch.zeros(16, dtype=torch.int32, device=dev) if want_stats else None
     with torch.cuda.device(dev):
         _lib.check(L.f3d_knn_graph(_lib.ptr(X), B, N, F, K, _lib.ptr(idx), _lib.ptr(dist), _lib.ptr(gat), _lib.ptr(edge),
-                                   None, 0, 0, _lib.stream_ptr(dev)))
+                                   _lib.ptr(stats), 64 if want_stats else 0, int(flags), _lib.stream_ptr(dev)))
     out = {"idx": idx}
+    if want_stats:
+        out["stats"] = stats  # [queries that fell back to an exact scan, candidates re-evaluated exactly]
     if want_dist:
         out["dist"] = dist
     if want_gathered:

@@ -60,7 +60,11 @@ enum {
     /* f3d_chamfer_fwd: evaluate EVERY pair in the reference arithmetic (the original exact sweep) instead
        of the default filter + certified exact re-evaluation.  Both produce bit-identical results; this
        one does not depend on the filter's error bound and is kept as the cross-check. */
-    F3D_FLAG_EXACT_SWEEP = 4
+    F3D_FLAG_EXACT_SWEEP = 4,
+    /* f3d_knn_graph: take the tensor-core (tcgen05) filter path whenever the shape allows it (N <= 1024, F <= 64,
+       K <= 31), also for narrow features (F < 16) where the CUDA-core kernel is the default because the work is
+       selection-bound.  Results are identical either way. */
+    F3D_FLAG_TENSOR = 8
 };
 
 enum {
@@ -105,6 +109,11 @@ F3D_API int32_t f3d_chamfer_bwd(const float* A, const float* Bp, int32_t B, int3
  *   idx [B][N][K] (required); dist [B][N][K] (optional squared distances);
  *   gathered [B][N][K][F] (optional; == the Julia (F,K,N,B) KNNGraph tensor of :36);
  *   edge_feat [B][N][K][2F] (optional; == cat(X, KNNGraph - X; dims=1) of :45).
+ *   N <= 1024, 16 <= F <= 64, K <= 31 run the Gram matrix on the tensor cores (tcgen05, TF32) as a filter and re-evaluate the
+ *   surviving candidates in the reference arithmetic — results are bit-identical to the all-exact CUDA-core kernel,
+ *   which F3D_FLAG_EXACT_SWEEP (or any larger shape) selects.  ws is optional: when >= 8 bytes are given, two
+ *   uint32 diagnostics are written to it — queries whose candidate set overflowed to an exact scan of the cloud,
+ *   and the number of candidates re-evaluated exactly.
  * ---------------------------------------------------------------------------------------------- */
 F3D_API size_t f3d_knn_graph_workspace_bytes(int32_t B, int32_t N, int32_t F, int32_t K);
 F3D_API int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F, int32_t K, int32_t* idx,

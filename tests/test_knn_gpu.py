@@ -22,10 +22,11 @@ def _normalized(rng, B, N):
     (3, 2, 3, 1),        # smallest legal problem
     (1, 257, 130, 9),    # wide features
 ])
-def test_knn_parity(f3d, oracle, B, N, F, K):
+@pytest.mark.parametrize("flags", [0, 4, 8])  # 0: default dispatch; 4: all-exact CUDA-core kernel; 8: tensor-core filter wherever the shape allows
+def test_knn_parity(f3d, oracle, B, N, F, K, flags):
     rng = np.random.default_rng(301 + N + F + K)
     X = _normalized(rng, B, N) if F == 3 else rng.standard_normal((B, N, F)).astype(np.float32)
-    out = f3d.knn_graph(torch.from_numpy(X).cuda(), K, want_dist=True, want_gathered=True, want_edge=True)
+    out = f3d.knn_graph(torch.from_numpy(X).cuda(), K, want_dist=True, want_gathered=True, want_edge=True, flags=flags)
     torch.cuda.synchronize()
     idx, dist, gat = oracle.knn_graph(X, K, want_dist=True, want_gathered=True)
     assert np.array_equal(out["idx"].cpu().numpy(), idx)
@@ -45,6 +46,24 @@ def test_knn_duplicates_and_ties(f3d, oracle):
     assert np.all(out[0, 60:, 0] == np.arange(60) + 60)
     Lt = rng.integers(0, 3, size=(2, 300, 3)).astype(np.float32)
     assert np.array_equal(f3d.knn_graph(torch.from_numpy(Lt).cuda(), 20)["idx"].cpu().numpy(), oracle.knn_graph(Lt, 20))
+    assert np.array_equal(f3d.knn_graph(torch.from_numpy(Lt).cuda(), 20, flags=4)["idx"].cpu().numpy(), oracle.knn_graph(Lt, 20))
+    assert np.array_equal(f3d.knn_graph(torch.from_numpy(Lt).cuda(), 20, flags=8)["idx"].cpu().numpy(), oracle.knn_graph(Lt, 20))
+
+
+def test_knn_filter_adversarial(f3d, oracle):
+    """Inputs that stress the TF32 filter's error bound: features far from the origin (cancellation in |x|²+|y|²-2x.y),
+    wildly different scales, near-duplicates, high-dimensional clustered features."""
+    rng = np.random.default_rng(11)
+    base = rng.standard_normal((2, 700, 3)).astype(np.float32)
+    for X in (base + np.float32(100.0),                       # offset 100: d~ loses ~4 digits
+              base * np.float32(1e-4), base * np.float32(1e4),
+              (base + rng.standard_normal(base.shape).astype(np.float32) * np.float32(1e-6)).astype(np.float32)):
+        got = f3d.knn_graph(torch.from_numpy(np.ascontiguousarray(X)).cuda(), 20, want_dist=True, flags=8)
+        idx, dist = oracle.knn_graph(X, 20, want_dist=True)
+        assert np.array_equal(got["idx"].cpu().numpy(), idx) and np.array_equal(got["dist"].cpu().numpy(), dist)
+    C = (rng.integers(0, 5, (2, 900, 1)) * 3.0 + rng.standard_normal((2, 900, 64)) * 0.05).astype(np.float32)
+    got = f3d.knn_graph(torch.from_numpy(C).cuda(), 16)["idx"].cpu().numpy()
+    assert np.array_equal(got, oracle.knn_graph(C, 16))
 
 
 def test_create_single_knn_graph_shapes(f3d, oracle):
@@ -71,3 +90,14 @@ def test_knn_properties_large(f3d):
     assert bool((srt[..., 1:] != srt[..., :-1]).all())
     ref = torch.cdist(X.double(), X.double()).pow(2).topk(21, largest=False).values[..., 1:]
     assert torch.allclose(dist.double(), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_knn_tensor_path_is_a_real_filter(f3d):
+    """The tensor-core path must actually filter: on random clouds (almost) no query may fall back to the exact scan of
+    the whole cloud, and the number of exactly re-evaluated candidates per query must stay close to K+1."""
+    for F, K in ((3, 20), (64, 20), (16, 10)):
+        X = torch.randn((8, 1024, F), device="cuda")
+        st = f3d.knn_graph(X, K, want_stats=True, flags=8)["stats"].cpu().numpy()
+        queries = 8 * 1024
+        assert st[0] == 0, (F, K, st)                          # nobody overflows to the exact scan on random clouds
+        assert (K + 1) * queries <= st[1] <= 4 * (K + 1) * queries, (F, K, st)
