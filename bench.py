@@ -12,7 +12,8 @@ configs[4] (B=32 per GPU, N=M=8192).
 value      device-timed (CUDA events around every step, summed; inputs resident in HBM; L2 flushed between steps
            outside the event pairs), max over ranks.
 e2e        the same step through the public API flux3d_b200.chamfer_distance with PINNED HOST inputs: H2D of
-           both clouds and the D2H read of the loss are inside the timed region.
+           both clouds and the D2H read of the loss are inside the timed region (C ABI: f3d_chamfer_pipe_run —
+           the batch crosses PCIe in 4 chunks, chunk k+1 in flight while chunk k is swept).
 roofline   the dominant kernel (chamfer_filter_sweep_kernel) timed alone, live, with CUDA events on its launch stream
            (F3D_FLAG_SWEEP_ONLY).  The binding roof is FP32 issue, not HBM (0.006 algorithmic bytes per pair):
            achieved = ALGORITHMIC 8 lane-instructions/pair (3 FSUB, 3 FMUL, 2 FADD: the reference's bit-exact direct
@@ -204,10 +205,9 @@ def run_b200(args):
     # end to end through the public API: pinned host inputs → H2D → kernels → D2H of the loss
     def e2e_step():
         with torch.no_grad():
+            # host arrays in: f3d_chamfer_pipe_run uploads chunk k+1 while chunk k is swept (one C call per step)
             if multi:
-                a = pA.to(dev, non_blocking=True)
-                b = pB.to(dev, non_blocking=True)
-                return float(f3d.chamfer_distance_sharded(a, b, B_total).item())
+                return float(f3d.chamfer_distance_sharded(pA, pB, B_total).item())
             return float(f3d.chamfer_distance(pA, pB).item())
     for _ in range(3):
         e2e_step()

@@ -44,6 +44,17 @@ constexpr int kMaxColsPerWarp = F3D_MAXCPW;
 constexpr float kPadA = 1.0e18f;   // padded rows / columns sit ~1e18 apart from everything:
 constexpr float kPadB = -1.0e18f;  // d ≈ 1e37 (finite), never a minimum for in-contract inputs
 
+// Upload chunks of the host-array pipeline: sizes 1, 2, 4, ..., 2^m, 2^m, ... (the last one takes the remainder) — small
+// first so the sweep starts after ~100 KB has crossed PCIe, doubling because the sweep of what has landed hides the
+// next, larger copy.  Chunk c <= m starts at batch element 2^c - 1; chunk c > m at 2^(m+1) - 1 + (c - m - 1) 2^m.
+__host__ __device__ __forceinline__ int arrive_chunk_of(int b, int m, int nchunks) {
+    const unsigned x = (unsigned)b + 1u;
+    int c = 0;
+    if (x < (2u << m)) { while ((2u << c) <= x) ++c; }  // floor(log2(x)), x < 2^(m+1): at most m steps
+    else c = m + 1 + (int)((x - (2u << m)) >> m);
+    return c < nchunks - 1 ? c : nchunks - 1;
+}
+
 struct SweepParams {
     const float* A;   // [B][N][3]
     const float* Bp;  // [B][M][3]
@@ -372,7 +383,19 @@ struct FiltParams {
     unsigned* counter;  // [0] finalize's block counter; zeroed by a memset node before every sweep, with:
     int* rowdone;       // [B][RB]  tiles of the row block that have published their partials (target CS)
     int* coldone;       // [B][CS]  tiles of the column split that have published their partials (target RB)
+    // host-array pipeline (chamfer_pipe.cu): the clouds are still crossing PCIe when the grid starts.  arrive[c] != 0
+    // once upload chunk c has landed (written by the copy engine, in stream order behind the chunk's data); null when
+    // the inputs are resident.  Batch element b belongs to chunk arrive_chunk_of(b, arr_m, arr_n).
+    const unsigned* arrive;
+    int arr_m, arr_n;
+    unsigned* arrive_timeout;  // set if a CTA gave up waiting (the finalize then reports NaN instead of a wrong loss)
 };
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // The centre of a batch element is the mean of 32 + 32 strided sample points.  ANY point works (the bound uses the
 // norms actually obtained); every warp of every CTA of the element computes the same value with the same operations.
@@ -380,8 +403,11 @@ struct FiltParams {
 #ifdef F3D_EXP_CLOCK
 __device__ long long g_dbg[8 * 8192];
 #define DBG_T(k) do { if (tid == 0) { long long c_ = clock64(); unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); int id_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; if (id_ < 8192) { g_dbg[id_ * 8 + (k)] = c_; if ((k) == 0) { g_dbg[id_ * 8 + 4] = (long long)g_; unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_dbg[id_ * 8 + 6] = sm_; } if ((k) == 3) g_dbg[id_ * 8 + 5] = (long long)g_; } } } while (0)
+__device__ long long g_dbgf[8 * 2048];  // finalize: per block, globaltimer at 6 phase boundaries + smid
+#define DBG_F(k) do { if (threadIdx.x == 0 && blockIdx.x < 2048) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); g_dbgf[blockIdx.x * 8 + (k)] = (long long)g_; if ((k) == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_dbgf[blockIdx.x * 8 + 7] = sm_; } } } while (0)
 #else
 #define DBG_T(k)
+#define DBG_F(k)
 #endif
 #ifndef F3D_FILT_MINB
 #define F3D_FILT_MINB 4
@@ -408,6 +434,25 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
     // dispatched; its blocks wait on rowdone/coldone, so they soak up the SM slots the last partial wave leaves idle.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) s_maxnb = 0u;
+    if (p.arrive) {
+        // wait until this batch element's upload chunk has landed.  CTAs are dispatched in batch order and the copy
+        // engine needs no SM, so spinning CTAs cannot starve the copies; the bounded wait (2 s) turns a lost copy into
+        // a reported error instead of a hung device.
+        if (tid == 0) {
+            const unsigned* f = p.arrive + arrive_chunk_of(b, p.arr_m, p.arr_n);
+            unsigned long long t0 = 0;
+            for (unsigned spins = 0; ld_acquire_sys(f) == 0u; ++spins) {
+                __nanosleep(100);
+                if ((spins & 1023u) == 1023u) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > 2000000000ull) { atomicExch(p.arrive_timeout, 1u); break; }
+                }
+            }
+        }
+        __syncthreads();
+    }
 
     // ---- prologue: issue EVERY global load first (centre samples, this thread's column pairs, this lane's rows),
     // so the CTA pays one memory latency instead of one per dependent step -------------------------------------
@@ -618,6 +663,7 @@ struct FiltFinalizeParams {
     double denomA, denomB;
     float* loss;
     float* terms;
+    const unsigned* arrive_timeout;  // null unless the sweep waited for uploads
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -626,181 +672,264 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
     return v;
 }
 
-// exact (reference-arithmetic) argmin of |q - P[j]|² over j in [j0, j1), cooperatively by one warp, merged into the
-// running (dmin, jmin) with the lowest-index tie rule.  q is warp-uniform; the result is valid in every lane.
-__device__ __forceinline__ void warp_exact_scan(const float* __restrict__ P, int j0, int j1, float qx, float qy, float qz,
-                                                bool q_is_row, int lane, float& dmin, int& jmin) {
-    float best = INFINITY;
-    int bj = 0x7fffffff;
-    // 4 candidates per lane per trip, all 12 loads issued before the arithmetic (this loop is latency-bound:
-    // the warps that hit an ambiguous item set the kernel's tail)
-    for (int j = j0 + lane; j < j1; j += 128) {
-        float px[4], py[4], pz[4];
+// exact (reference-arithmetic) argmin of |q - P[j]|² over j in [j0, j1), cooperatively by the whole block: thread t takes
+// candidates j0 + 4t .. j0 + 4t + 3 (+ 4·kFinThreads per further trip) and merges them into ITS running (dmin, jmin); a
+// thread's candidates ascend, so '<' keeps the lowest index.  Four points are 48 bytes: three 16-byte loads when the
+// cloud is 16-byte aligned there (N, M multiples of 4), twelve scalar loads otherwise — all issued before any arithmetic.
+template <bool kQIsRow>
+__device__ __forceinline__ void block_exact_scan(const float* __restrict__ P, int j0, int j1, float qx, float qy, float qz,
+                                                 int tid, float& dmin, int& jmin) {
+    for (int jb = j0 + 4 * tid; jb < j1; jb += 4 * kFinThreads) {
+        const float* pp = P + 3 * (size_t)jb;
+        float c[12];
+        if (jb + 4 <= j1 && (reinterpret_cast<uintptr_t>(pp) & 15u) == 0) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(pp));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(pp) + 1);
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(pp) + 2);
+            c[0] = v0.x; c[1] = v0.y; c[2] = v0.z; c[3] = v0.w; c[4] = v1.x; c[5] = v1.y;
+            c[6] = v1.z; c[7] = v1.w; c[8] = v2.x; c[9] = v2.y; c[10] = v2.z; c[11] = v2.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int jj = min(j + 32 * k, j1 - 1);  // clamped duplicates are harmless (same value, higher or equal index)
-            px[k] = __ldg(P + 3 * (size_t)jj); py[k] = __ldg(P + 3 * (size_t)jj + 1); pz[k] = __ldg(P + 3 * (size_t)jj + 2);
+            for (int k = 0; k < 4; ++k) {
+                const int jj = min(jb + k, j1 - 1);  // clamped duplicates are harmless (same value, same index)
+                c[3 * k] = __ldg(P + 3 * (size_t)jj); c[3 * k + 1] = __ldg(P + 3 * (size_t)jj + 1); c[3 * k + 2] = __ldg(P + 3 * (size_t)jj + 2);
+            }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             // operand order of the reference: (a - b) with a from the first cloud
-            const float d = q_is_row ? sqdist3<false>(qx, qy, qz, px[k], py[k], pz[k]) : sqdist3<false>(px[k], py[k], pz[k], qx, qy, qz);
-            const int jj = min(j + 32 * k, j1 - 1);
-            if (d < best || (d == best && jj < bj)) { best = d; bj = jj; }
+            const float d = kQIsRow ? sqdist3<false>(qx, qy, qz, c[3 * k], c[3 * k + 1], c[3 * k + 2])
+                                    : sqdist3<false>(c[3 * k], c[3 * k + 1], c[3 * k + 2], qx, qy, qz);
+            if (d < dmin) { dmin = d; jmin = min(jb + k, j1 - 1); }
         }
-    }
-    const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(best));  // d >= 0: bit order == value order
-    const int cand = (__float_as_uint(best) == mb) ? bj : 0x7fffffff;
-    const int jm = __reduce_min_sync(0xffffffffu, cand);
-    const float dm = __uint_as_float(mb);
-    if (dm < dmin || (dm == dmin && jm < jmin)) { dmin = dm; jmin = jm; }
-}
-
-// (d, j) minimum over the 8 lanes of a group (lowest j on ties); every lane of the group gets the result
-__device__ __forceinline__ void group8_argmin(float& d, int& j) {
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-        const float od = __shfl_xor_sync(0xffffffffu, d, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, j, o);
-        if (od < d || (od == d && oj < j)) { d = od; j = oj; }
     }
 }
 
 // Block = 8 warps; a warp owns 32 consecutive items (rows of A, or columns = points of B).
 //   phase 1  lane <-> item: merge the sweep's partials, decide "certified" vs "ambiguous"
-//   phase 2  8 passes x 4 items: 8 lanes per item re-evaluate the located candidates exactly
-//   phase 3  the (rare) ambiguous items, one at a time, whole warp: exact scan of every tile within the window
+//   phase 2  lane <-> item: re-evaluate the located candidates exactly (16-byte loads, batched)
+//   phase 3  the (rare) ambiguous items, one at a time, whole block: exact scan of every tile within the window
 __global__ void __launch_bounds__(kFinThreads) chamfer_filter_finalize_kernel(FiltFinalizeParams p) {
     __shared__ double s_red[kFinThreads / 32];
     __shared__ bool s_last;
+    __shared__ unsigned s_amb[kFinThreads / 32], s_wd[kFinThreads / 32];  // phase 3: ambiguous-item queue, block argmin
+    __shared__ int s_wj[kFinThreads / 32], s_ib[kFinThreads], s_iq[kFinThreads];
+    __shared__ float s_ilim[kFinThreads];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int grp = lane >> 3, sub = lane & 7;
     const bool rows = (int)blockIdx.x < p.nbA;
     const long t = ((long)(rows ? blockIdx.x : blockIdx.x - p.nbA) * (kFinThreads / 32) + warp) * 32 + lane;
     const int Q = rows ? p.N : p.M;        // items per batch element (queries)
     const int R = rows ? p.M : p.N;        // points searched per query
     const float* gQ = rows ? p.A : p.Bp;   // queries
     const float* gP = rows ? p.Bp : p.A;   // searched cloud
+#ifdef F3D_EXP_FIN_EMPTY
+    if (blockIdx.x + threadIdx.x == 0) p.loss[0] = 0.f;
+    return;
+#endif
     const bool valid = t < (long)p.B * Q;
     double mine = 0.0;
+    DBG_F(0);
 
-    // ---- phase 1 -------------------------------------------------------------------------------------------------
+    // ---- phase 1: merge the sweep's partials ------------------------------------------------------------------------
+    // Everything here and in phase 2 is a chain of L2 round trips (≈ 0.4 µs each on B200), so the loads of a step are
+    // issued together: one dependent-issue load per loop trip made this kernel 45 µs; batches make it a handful of trips.
     int b = 0, q = 0, loc = 0;     // loc: chunk id (rows) or row block (columns)
     unsigned bal = 0u;             // columns: lane ballot of the located block
     float best = 0.0f, win = 0.0f; // clamped filter minimum and the certificate window
+    float qx = 0.f, qy = 0.f, qz = 0.f;  // the query point (raw coordinates)
     bool amb = false;
-    if (valid) {
-        b = (int)(t / Q); q = (int)(t - (long)b * Q);
+    if (valid) { b = (int)(t / Q); q = (int)(t - (long)b * Q); }
+    {
         // wait until every sweep tile of this item's row block / column split has published (this grid is launched
-        // programmatically and may be resident while the sweep's last wave is still running)
-        {
-            const int* flag = rows ? p.rowdone + (size_t)b * p.RB + q / kTileRows : p.coldone + (size_t)b * p.CS + q / p.BN;
-            const int target = rows ? p.CS : p.RB;
-            while (ld_acquire(flag) < target) __nanosleep(200);
-        }
+        // programmatically and may be resident while the sweep's last wave is still running).  The lanes of a warp
+        // almost always share one flag: one lane per distinct flag polls it.
+        const int* flag = !valid ? nullptr : (rows ? p.rowdone + (size_t)b * p.RB + q / kTileRows : p.coldone + (size_t)b * p.CS + q / p.BN);
+        const int target = rows ? p.CS : p.RB;
+        const unsigned peers = __match_any_sync(0xffffffffu, reinterpret_cast<unsigned long long>(flag));
+        if (flag && lane == __ffs(peers) - 1)
+            while (ld_acquire(flag) < target) __nanosleep(100);
+        __syncwarp();
+    }
+    DBG_F(1);
+    if (valid) {
         const float* c = p.centre + 4 * b;
         const float* pt = gQ + ((size_t)b * Q + q) * 3;
-        const float x = __ldg(pt) - __ldcg(c), y = __ldg(pt + 1) - __ldcg(c + 1), z = __ldg(pt + 2) - __ldcg(c + 2);
-        const float nq = fmaf(z, z, fmaf(y, y, x * x));  // the sweep's |a'|² / |b'|², bit for bit
+        const float cx = __ldcg(c), cy = __ldcg(c + 1), cz = __ldcg(c + 2);
+        qx = __ldg(pt); qy = __ldg(pt + 1); qz = __ldg(pt + 2);
         float second = INFINITY, other = 0.0f;
         best = INFINITY;
         if (rows) {
-            for (int cs = 0; cs < p.CS; ++cs) {
-                const float4 e = __ldcg(p.rowpart + ((size_t)b * p.CS + cs) * p.Npad + q);
-                const float e1 = fmaxf(e.x, 0.0f), e2 = fmaxf(e.y, 0.0f);
-                other = fmaxf(other, __ldcg(p.maxnb + (size_t)b * p.CS + cs));
-                if (e1 < best) { second = fminf(best, e2); best = e1; loc = __float_as_int(e.z); }
-                else second = fminf(second, e1);
+            for (int cs0 = 0; cs0 < p.CS; cs0 += 4) {
+                float4 e[4];
+                float mo[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int cs = min(cs0 + k, p.CS - 1);
+                    e[k] = __ldcg(p.rowpart + ((size_t)b * p.CS + cs) * p.Npad + q);
+                    mo[k] = __ldcg(p.maxnb + (size_t)b * p.CS + cs);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (cs0 + k < p.CS) {
+                        const float e1 = fmaxf(e[k].x, 0.0f), e2 = fmaxf(e[k].y, 0.0f);
+                        other = fmaxf(other, mo[k]);
+                        if (e1 < best) { second = fminf(best, e2); best = e1; loc = __float_as_int(e[k].z); }
+                        else second = fminf(second, e1);
+                    }
+                }
             }
         } else {
-            for (int rb = 0; rb < p.RB; ++rb) {
-                const uint2 e = __ldcg(p.colpart + ((size_t)b * p.RB + rb) * p.Mpad + q);
-                const float v = fmaxf(__uint_as_float(e.x), 0.0f);
-                other = fmaxf(other, __ldcg(p.maxna + (size_t)b * p.RB + rb));
-                if (v < best) { second = best; best = v; loc = rb; bal = e.y; }
-                else second = fminf(second, v);
+            for (int rb0 = 0; rb0 < p.RB; rb0 += 8) {
+                uint2 e[8];
+                float mo[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int rb = min(rb0 + k, p.RB - 1);
+                    e[k] = __ldcg(p.colpart + ((size_t)b * p.RB + rb) * p.Mpad + q);
+                    mo[k] = __ldcg(p.maxna + (size_t)b * p.RB + rb);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (rb0 + k < p.RB) {
+                        const float v = fmaxf(__uint_as_float(e[k].x), 0.0f);
+                        other = fmaxf(other, mo[k]);
+                        if (v < best) { second = best; best = v; loc = rb0 + k; bal = e[k].y; }
+                        else second = fminf(second, v);
+                    }
+                }
             }
         }
+        const float x = qx - cx, y = qy - cy, z = qz - cz;
+        const float nq = fmaf(z, z, fmaf(y, y, x * x));  // the sweep's |a'|² / |b'|², bit for bit
         win = fmaf(kWinRel, best, kWinAbs * (nq + other));
         // written so that NaN / inf / out-of-range norms can only make the item ambiguous, never certified
         amb = !(nq <= kNormLimit && other <= kNormLimit && second > best + win);
     }
 
-    // ---- phase 2: certified items, 4 per pass ---------------------------------------------------------------------
-    for (int pass = 0; pass < 8; ++pass) {
-        const int src = pass * 4 + grp;
-        const int bb = __shfl_sync(0xffffffffu, b, src), qq = __shfl_sync(0xffffffffu, q, src);
-        const int ll = __shfl_sync(0xffffffffu, loc, src);
-        unsigned bits = __shfl_sync(0xffffffffu, bal, src);
-        const bool go = __shfl_sync(0xffffffffu, (int)(valid && !amb), src) != 0;
-        const float* qp = gQ + ((size_t)bb * Q + qq) * 3;
-        const float* P = gP + (size_t)bb * R * 3;
-        float qx = 0.f, qy = 0.f, qz = 0.f;
-        if (go) { qx = __ldg(qp); qy = __ldg(qp + 1); qz = __ldg(qp + 2); }
+    DBG_F(2);
+    // ---- phase 2: certified items — each lane re-evaluates its own item's located candidates exactly -------------------
+    // rows: the 32 columns of the located chunk (384 contiguous bytes); columns: the 8 rows of every balloted lane (96
+    // contiguous bytes each, almost always one).  16-byte loads when the cloud is 16-byte aligned there (N, M % 4 == 0).
+#ifndef F3D_EXP_FIN_SKIP2
+    if (valid && !amb) {
+        const float* P = gP + (size_t)b * R * 3;
         float d = INFINITY;
         int j = 0x7fffffff;
         if (rows) {
-            if (go) {
+            const int j0 = loc * kChunk, j1 = min(j0 + kChunk, R);
+            const float* pp = P + 3 * (size_t)j0;
+            if ((kChunk % 8) == 0 && j0 + kChunk <= R && (reinterpret_cast<uintptr_t>(pp) & 15u) == 0) {
 #pragma unroll
-                for (int k = 0; k < kChunk / 8; ++k) {
-                    const int jj = ll * kChunk + sub * (kChunk / 8) + k;
-                    if (jj < R) {
-                        const float dd = sqdist3<false>(qx, qy, qz, __ldg(P + 3 * (size_t)jj), __ldg(P + 3 * (size_t)jj + 1),
-                                                        __ldg(P + 3 * (size_t)jj + 2));
-                        if (dd < d) { d = dd; j = jj; }
+                for (int h = 0; h < kChunk / 8; ++h) {  // 8 candidates = six 16-byte loads per trip
+                    float4 v[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(pp) + h * 6 + i);
+                    const float c[24] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w, v[2].x, v[2].y, v[2].z, v[2].w,
+                                         v[3].x, v[3].y, v[3].z, v[3].w, v[4].x, v[4].y, v[4].z, v[4].w, v[5].x, v[5].y, v[5].z, v[5].w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float dd = sqdist3<false>(qx, qy, qz, c[3 * k], c[3 * k + 1], c[3 * k + 2]);
+                        if (dd < d) { d = dd; j = j0 + h * 8 + k; }  // ascending candidates: '<' keeps the lowest index
                     }
+                }
+            } else {
+#pragma unroll 4
+                for (int jj = j0; jj < j1; ++jj) {
+                    const float dd = sqdist3<false>(qx, qy, qz, __ldg(P + 3 * (size_t)jj), __ldg(P + 3 * (size_t)jj + 1), __ldg(P + 3 * (size_t)jj + 2));
+                    if (dd < d) { d = dd; j = jj; }
                 }
             }
         } else {
-            if (!go) bits = 0u;
-            while (__any_sync(0xffffffffu, bits != 0u)) {  // one ballot bit (8 rows) per trip; almost always one trip
-                if (bits) {
-                    const int ii = ll * kTileRows + (__ffs(bits) - 1) * kRowsPerLane + sub;
-                    bits &= bits - 1;
-                    if (ii < R) {
-                        const float dd = sqdist3<false>(__ldg(P + 3 * (size_t)ii), __ldg(P + 3 * (size_t)ii + 1),
-                                                        __ldg(P + 3 * (size_t)ii + 2), qx, qy, qz);
-                        if (dd < d) { d = dd; j = ii; }  // candidates of one lane ascend, so '<' keeps the lowest index
+            for (unsigned bits = bal; bits; bits &= bits - 1) {  // ascending lanes => ascending row indices
+                const int i0 = loc * kTileRows + (__ffs(bits) - 1) * kRowsPerLane, i1 = min(i0 + kRowsPerLane, R);
+                const float* pp = P + 3 * (size_t)i0;
+                if (kRowsPerLane == 8 && i0 + 8 <= R && (reinterpret_cast<uintptr_t>(pp) & 15u) == 0) {
+                    float4 v[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(pp) + i);
+                    const float c[24] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w, v[2].x, v[2].y, v[2].z, v[2].w,
+                                         v[3].x, v[3].y, v[3].z, v[3].w, v[4].x, v[4].y, v[4].z, v[4].w, v[5].x, v[5].y, v[5].z, v[5].w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        // operand order of the reference: (a - b) with a from the first cloud
+                        const float dd = sqdist3<false>(c[3 * k], c[3 * k + 1], c[3 * k + 2], qx, qy, qz);
+                        if (dd < d) { d = dd; j = i0 + k; }
+                    }
+                } else {
+                    for (int ii = i0; ii < i1; ++ii) {
+                        const float dd = sqdist3<false>(__ldg(P + 3 * (size_t)ii), __ldg(P + 3 * (size_t)ii + 1), __ldg(P + 3 * (size_t)ii + 2), qx, qy, qz);
+                        if (dd < d) { d = dd; j = ii; }
                     }
                 }
             }
         }
-        group8_argmin(d, j);
-        if (go && sub == 0) {
-            int32_t* nn = rows ? p.nnA : p.nnB;
-            if (nn) nn[(size_t)bb * Q + qq] = j;
-            mine += (double)d;
+        int32_t* nn = rows ? p.nnA : p.nnB;
+        if (nn) nn[t] = j;
+        mine += (double)d;
+    }
+#endif
+
+    DBG_F(3);
+    // ---- phase 3: ambiguous items, one at a time, by the WHOLE BLOCK -------------------------------------------
+    // An ambiguous item needs an exact scan of every tile within its window (up to BN = 1024 candidates each).  Done by
+    // the owning warp alone that is a chain of dependent L2 round trips, and the few warps that own two or three such
+    // items set the kernel's tail; spread over the block every thread takes 4 candidates of a tile, all loads of a
+    // tile are in flight at once, and an item costs about one memory latency.  The order of the queue is fixed (warp,
+    // lane), each owner adds its own item's distance: the block's partial sum stays run-to-run deterministic.
+    {
+#ifdef F3D_EXP_FIN_SKIP3
+        const unsigned ambmask = 0u;
+#else
+        const unsigned ambmask = __ballot_sync(0xffffffffu, valid && amb);
+#endif
+        if (lane == 0) s_amb[warp] = ambmask;
+        if (valid && amb) { s_ib[tid] = b; s_iq[tid] = q; s_ilim[tid] = best + win; }
+        __syncthreads();
+        for (int w = 0; w < kFinThreads / 32; ++w) {
+            for (unsigned rem = s_amb[w]; rem; rem &= rem - 1) {
+                const int src = w * 32 + __ffs(rem) - 1;
+                const int bb = s_ib[src], qq = s_iq[src];
+                const float lim = s_ilim[src];  // NaN/inf → scan everything (comparison below)
+                const float* qp = gQ + ((size_t)bb * Q + qq) * 3;
+                const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+                const float* P = gP + (size_t)bb * R * 3;
+                float d = INFINITY;
+                int j = 0x7fffffff;
+                if (rows) {
+                    for (int cs = 0; cs < p.CS; ++cs) {
+                        const float e1 = fmaxf(__ldcg(&p.rowpart[((size_t)bb * p.CS + cs) * p.Npad + qq].x), 0.0f);
+                        if (!(e1 > lim)) block_exact_scan<true>(P, cs * p.BN, min((cs + 1) * p.BN, R), qx, qy, qz, tid, d, j);
+                    }
+                } else {
+                    for (int rb = 0; rb < p.RB; ++rb) {
+                        const float v = fmaxf(__uint_as_float(__ldcg(&p.colpart[((size_t)bb * p.RB + rb) * p.Mpad + qq].x)), 0.0f);
+                        if (!(v > lim)) block_exact_scan<false>(P, rb * kTileRows, min((rb + 1) * kTileRows, R), qx, qy, qz, tid, d, j);
+                    }
+                }
+                // (d, j) minimum over the block, lowest j on ties (d >= 0 or +inf: bit order == value order)
+                const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(d));
+                const int jm = __reduce_min_sync(0xffffffffu, (__float_as_uint(d) == mb) ? j : 0x7fffffff);
+                if (lane == 0) { s_wd[warp] = mb; s_wj[warp] = jm; }
+                __syncthreads();
+                if (tid == src) {
+                    unsigned bd = s_wd[0];
+                    int bj = s_wj[0];
+#pragma unroll
+                    for (int k = 1; k < kFinThreads / 32; ++k) {
+                        const unsigned od = s_wd[k];
+                        const int oj = s_wj[k];
+                        if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+                    }
+                    int32_t* nn = rows ? p.nnA : p.nnB;
+                    if (nn) nn[(size_t)bb * Q + qq] = bj;
+                    mine += (double)__uint_as_float(bd);
+                }
+                __syncthreads();  // s_wd / s_wj are reused by the next item
+            }
         }
     }
 
-    // ---- phase 3: ambiguous items --------------------------------------------------------------------------------
-    for (unsigned rem = __ballot_sync(0xffffffffu, valid && amb); rem; rem &= rem - 1) {
-        const int src = __ffs(rem) - 1;
-        const int bb = __shfl_sync(0xffffffffu, b, src), qq = __shfl_sync(0xffffffffu, q, src);
-        const float lim = __shfl_sync(0xffffffffu, best + win, src);  // NaN/inf → scan everything (comparison below)
-        const float* qp = gQ + ((size_t)bb * Q + qq) * 3;
-        const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
-        const float* P = gP + (size_t)bb * R * 3;
-        float d = INFINITY;
-        int j = 0x7fffffff;
-        if (rows) {
-            for (int cs = 0; cs < p.CS; ++cs) {
-                const float e1 = fmaxf(__ldcg(&p.rowpart[((size_t)bb * p.CS + cs) * p.Npad + qq].x), 0.0f);
-                if (!(e1 > lim)) warp_exact_scan(P, cs * p.BN, min((cs + 1) * p.BN, R), qx, qy, qz, true, lane, d, j);
-            }
-        } else {
-            for (int rb = 0; rb < p.RB; ++rb) {
-                const float v = fmaxf(__uint_as_float(__ldcg(&p.colpart[((size_t)bb * p.RB + rb) * p.Mpad + qq].x)), 0.0f);
-                if (!(v > lim)) warp_exact_scan(P, rb * kTileRows, min((rb + 1) * kTileRows, R), qx, qy, qz, false, lane, d, j);
-            }
-        }
-        if (lane == 0) {
-            int32_t* nn = rows ? p.nnA : p.nnB;
-            if (nn) nn[(size_t)bb * Q + qq] = j;
-            mine += (double)d;
-        }
-    }
-
+    DBG_F(4);
     // ---- block partial sum → last block reduces in a fixed order (deterministic) ------------------------------
     mine = warp_sum(mine);
     if (lane == 0) s_red[warp] = mine;
@@ -813,6 +942,7 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_filter_finalize_kernel(Fi
         s_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
     }
     __syncthreads();
+    DBG_F(5);
     if (!s_last) return;
     __threadfence();
     double sa = 0.0, sb = 0.0;
@@ -828,7 +958,9 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_filter_finalize_kernel(Fi
         for (int w = 0; w < kFinThreads / 32; ++w) { ta += s_a[w]; tb += s_b[w]; }
         const float dAB = (float)(ta / p.denomA), dBA = (float)(tb / p.denomB);  // pcloud.jl:47-48
         if (p.terms) { p.terms[0] = dAB; p.terms[1] = dBA; }
-        p.loss[0] = __fadd_rn(__fmul_rn(p.w1, dAB), __fmul_rn(p.w2, dBA));      // pcloud.jl:50
+        float l = __fadd_rn(__fmul_rn(p.w1, dAB), __fmul_rn(p.w2, dBA));          // pcloud.jl:50
+        if (p.arrive_timeout && __ldcg(p.arrive_timeout) != 0u) l = __int_as_float(0x7fc00000);  // an upload never landed
+        p.loss[0] = l;
     }
 }
 
@@ -856,7 +988,8 @@ FiltPlan make_filt_plan(int B, int N, int M) {
     pl.off_maxnb = o;   o = align_up(o + sizeof(float) * (size_t)B * pl.CS, 256);
     pl.off_centre = o;  o = align_up(o + sizeof(float) * 4 * (size_t)B, 256);
     pl.off_partial = o; o = align_up(o + sizeof(double) * (size_t)(pl.nbA + pl.nbB), 256);
-    // [0..63] finalize block counter | rowdone [B][RB] | coldone [B][CS]  — one memset zeroes all of it per call
+    // [0..63] finalize block counter | [64..127] upload-arrival flags (kArriveMaxChunks words) | [128..131] arrival
+    // timeout flag | rowdone [B][RB] | coldone [B][CS]  — one memset zeroes all of it per call
     pl.counter_bytes = 256 + sizeof(int) * ((size_t)B * pl.RB + (size_t)B * pl.CS);
     pl.off_counter = o; o = align_up(o + pl.counter_bytes, 256);
     pl.total = o;
@@ -873,6 +1006,7 @@ size_t filt_smem_bytes(int BN) {
 
 #ifdef F3D_EXP_CLOCK
 extern "C" __attribute__((visibility("default"))) int f3d_debug_read(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, f3d::g_dbg, nbytes); }
+extern "C" __attribute__((visibility("default"))) int f3d_debug_read_fin(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, f3d::g_dbgf, nbytes); }
 #endif
 
 extern "C" size_t f3d_chamfer_workspace_bytes(int32_t B, int32_t N, int32_t M) {
@@ -884,6 +1018,13 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
                                    float w1, float w2, int32_t B_total, float* loss_dev,
                                    float* terms_dev, int32_t* nnA_dev, int32_t* nnB_dev, void* ws,
                                    size_t ws_bytes, int32_t flags, f3d_stream_t stream_) {
+    return f3d::chamfer_fwd_launch(A, Bp, B, N, M, w1, w2, B_total, loss_dev, terms_dev, nnA_dev, nnB_dev, ws, ws_bytes, flags,
+                                   static_cast<cudaStream_t>(stream_), nullptr);
+}
+
+int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M, float w1, float w2,
+                                int32_t B_total, float* loss_dev, float* terms_dev, int32_t* nnA_dev, int32_t* nnB_dev,
+                                void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream, ChamferArrive* arrive) {
     using namespace f3d;
     if (!A || !Bp || !loss_dev) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: null A/B/loss pointer");
     if (B <= 0 || N <= 0 || M <= 0) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: B, N, M must be positive (got %d, %d, %d)", B, N, M);
@@ -893,9 +1034,10 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
     const size_t need = f3d_chamfer_workspace_bytes(B, N, M);
     if (!ws || ws_bytes < need) return fail(F3D_ERR_WORKSPACE, "f3d_chamfer_fwd: workspace %zu < required %zu bytes", ws_bytes, need);
     if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0) return fail(F3D_ERR_MISALIGNED, "f3d_chamfer_fwd: workspace must be 256-byte aligned");
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     unsigned char* w = static_cast<unsigned char*>(ws);
     const bool fma = (flags & F3D_FLAG_FMA) != 0;
+    if (arrive && (fma || (flags & (F3D_FLAG_EXACT_SWEEP | F3D_FLAG_SWEEP_ONLY))))
+        return fail(F3D_ERR_INVALID, "chamfer_fwd_launch: upload-arrival flags exist only for the default (filtered) sweep");
 
     if (!fma && !(flags & F3D_FLAG_EXACT_SWEEP)) {
         // ---- default: filtered sweep + certified exact finalize (bit-identical results, ~half the FP32 work) ----
@@ -913,6 +1055,14 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
         sp.rowdone = reinterpret_cast<int*>(w + fl.off_counter + 256);
         sp.coldone = sp.rowdone + (size_t)B * fl.RB;
         F3D_CUDA(cudaMemsetAsync(w + fl.off_counter, 0, fl.counter_bytes, stream));
+        sp.arrive = nullptr; sp.arr_m = 0; sp.arr_n = 1;
+        sp.arrive_timeout = reinterpret_cast<unsigned*>(w + fl.off_counter + 128);
+        if (arrive) {
+            if (arrive->nchunks < 1 || arrive->nchunks > kArriveMaxChunks) return fail(F3D_ERR_INVALID, "chamfer_fwd_launch: bad chunk count %d", arrive->nchunks);
+            F3D_CUDA(cudaEventRecord(arrive->reset_done, stream));  // the flags are zero from here on: uploads may raise them
+            arrive->flags_dev = reinterpret_cast<unsigned*>(w + fl.off_counter + 64);
+            sp.arrive = arrive->flags_dev; sp.arr_m = arrive->m; sp.arr_n = arrive->nchunks;
+        }
         const size_t smem = filt_smem_bytes(fl.BN);
         F3D_CUDA(cudaFuncSetAttribute(chamfer_filter_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         chamfer_filter_sweep_kernel<<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
@@ -930,13 +1080,18 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
         fp.denomA = (double)N * (double)B_total;
         fp.denomB = (double)M * (double)B_total;
         fp.loss = loss_dev; fp.terms = terms_dev;
+        fp.arrive_timeout = arrive ? sp.arrive_timeout : nullptr;
         {
             // programmatic dependent launch: blocks may start while the sweep's last wave is still running
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(fl.nbA + fl.nbB); cfg.blockDim = dim3(kFinThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+#ifdef F3D_EXP_NOPDL
+            attr[0].val.programmaticStreamSerializationAllowed = 0;
+#else
             attr[0].val.programmaticStreamSerializationAllowed = 1;
+#endif
             cfg.attrs = attr; cfg.numAttrs = 1;
             F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_filter_finalize_kernel, fp));
         }

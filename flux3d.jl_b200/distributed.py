@@ -73,7 +73,11 @@ def chamfer_distance_sharded(A_shard, B_shard, batch_total: int, *, w1: float = 
     (b_local, M, 3) and the GLOBAL batch size; the per-shard partial losses (already divided by the global
     N*B_total / M*B_total) are summed with one all-reduce, so every rank returns the reference's value for
     the whole batch.  A rank with an empty shard contributes 0."""
-    from .metrics import chamfer_forward_raw
+    from .metrics import chamfer_forward_host, chamfer_forward_raw
+    if not (isinstance(A_shard, torch.Tensor) and A_shard.is_cuda) and len(A_shard) > 0:
+        # host shards: upload pipelined against the sweep (f3d_chamfer_pipe_run), then the same one all-reduce
+        loss = chamfer_forward_host(A_shard, B_shard, w1, w2, batch_total=batch_total, flags=flags)
+        return allreduce_loss_(loss, comm).reshape(())
     if A_shard.shape[0] == 0:
         loss = torch.zeros(1, dtype=torch.float32, device=A_shard.device)
     else:

@@ -46,6 +46,61 @@ def chamfer_forward_raw(A: torch.Tensor, B: torch.Tensor, w1: float, w2: float, 
     return loss, terms, nnA, nnB
 
 
+_pipes: dict = {}
+_inflight: list = []  # (event, A, B) of host-array calls whose uploads may still be running
+
+
+def _is_host(x) -> bool:
+    return not (isinstance(x, torch.Tensor) and x.is_cuda)
+
+
+def chamfer_forward_host(A, B, w1: float = 1.0, w2: float = 1.0, *, batch_total: int = 0, chunks: int = 0,
+                         flags: int = FLAG_NONE, device="cuda", to_host: bool = False) -> torch.Tensor:
+    """One call of f3d_chamfer_pipe_run: HOST arrays A (B,N,3), B (B,M,3) → the loss.  The sweep grid starts at once and
+    consumes the batch while it is still crossing PCIe (page-locked inputs make the uploads asynchronous).
+    ``to_host=False``: loss[1] on ``device``, no host synchronisation.  ``to_host=True``: a 0-dim CPU tensor — the
+    kernel stores the loss into mapped host memory and the call returns when it has landed (no D2H copy).
+    ``chunks``: upper bound on the number of upload chunks (0 = 16, 1 = upload everything, then sweep)."""
+    L = _lib.lib()
+    A = as_f32_tensor(A)
+    B = as_f32_tensor(B)
+    if A.is_cuda or B.is_cuda:
+        raise ValueError("chamfer_forward_host takes host arrays; use chamfer_forward_raw for device tensors")
+    if A.dim() != 3 or B.dim() != 3 or A.shape[2] != 3 or B.shape[2] != 3:
+        raise ValueError("expected (B, N, 3) and (B, M, 3) point arrays")
+    if A.shape[0] != B.shape[0]:
+        raise ValueError(f"batch sizes differ: {A.shape[0]} vs {B.shape[0]}")
+    Bn, N, M = A.shape[0], A.shape[1], B.shape[1]
+    dev = torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    chunks = 16 if chunks <= 0 else min(int(chunks), 16)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        key = (dev.index, chunks)
+        h = _pipes.get(key)
+        if h is None:
+            h = _lib.C.c_void_p()
+            _lib.check(L.f3d_chamfer_pipe_create(chunks, _lib.C.byref(h)))
+            _pipes[key] = h
+        ws = _workspace(("chamfer_pipe", Bn, N, M, chunks), L.f3d_chamfer_pipe_workspace_bytes(Bn, N, M, chunks), dev)
+        if to_host:
+            out = _lib.C.c_float()
+            _lib.check(L.f3d_chamfer_pipe_run(h, _lib.ptr(A), _lib.ptr(B), Bn, N, M, w1, w2, batch_total, None,
+                                              _lib.C.byref(out), _lib.ptr(ws), ws.numel(), flags,
+                                              _lib.C.c_void_p(stream.cuda_stream)))
+            return torch.tensor(out.value, dtype=torch.float32)  # the call returned after the loss landed
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.check(L.f3d_chamfer_pipe_run(h, _lib.ptr(A), _lib.ptr(B), Bn, N, M, w1, w2, batch_total, _lib.ptr(loss),
+                                          None, _lib.ptr(ws), ws.numel(), flags, _lib.C.c_void_p(stream.cuda_stream)))
+        # the uploads read A and B asynchronously: keep them alive until the stream has consumed them
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        _inflight[:] = [e for e in _inflight if not e[0].query()]
+        _inflight.append((ev, A, B))
+    return loss
+
+
 class _ChamferFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, B, w1, w2, batch_total, flags):
@@ -75,7 +130,9 @@ def chamfer_distance(A, B, num_samples: int = 5000, *, w1: float = 1.0, w2: floa
     chamfer_distance(m1, m2, num_samples=5000; w1, w2) — src/metrics/mesh.jl:34-44.
 
     A, B: PointCloud, or arrays/tensors of shape (N,3) / (B,N,3) (== Julia (3,N) / (3,N,B)).  Host inputs
-    are copied to ``device``.  Returns a 0-dim float32 CUDA tensor (differentiable w.r.t. A and B)."""
+    are copied to ``device``.  Returns a 0-dim float32 CUDA tensor (differentiable w.r.t. A and B) — except when both
+    clouds are host arrays and nothing needs a gradient: then, like the reference on ``Array``s, the scalar comes back
+    on the host (0-dim CPU tensor; f3d_chamfer_pipe_run: uploads overlapped with the sweep, no D2H copy)."""
     from .mesh import TriMesh  # local import: mesh.py imports this module's helpers
     if isinstance(A, TriMesh) and isinstance(B, TriMesh):
         from .sampling import sample_points
@@ -85,6 +142,16 @@ def chamfer_distance(A, B, num_samples: int = 5000, *, w1: float = 1.0, w2: floa
         A = A.points
     if isinstance(B, PointCloud):
         B = B.points
+    needs_grad = torch.is_grad_enabled() and any(isinstance(x, torch.Tensor) and x.requires_grad for x in (A, B))
+    if _is_host(A) and _is_host(B) and not needs_grad:
+        # both clouds on the host, nothing to differentiate: upload pipelined against the sweep, one C call
+        A, B = as_f32_tensor(A), as_f32_tensor(B)
+        if A.dim() == 2:
+            A = A.unsqueeze(0)
+        if B.dim() == 2:
+            B = B.unsqueeze(0)
+        return chamfer_forward_host(A, B, float(w1), float(w2), batch_total=int(batch_total), flags=int(flags),
+                                    device=device, to_host=True)
     A = as_f32_tensor(A, None if (isinstance(A, torch.Tensor) and A.is_cuda) else device)
     B = as_f32_tensor(B, A.device)
     if A.dim() == 2:

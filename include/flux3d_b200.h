@@ -94,6 +94,27 @@ F3D_API int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, int3
                         int32_t* nnA_dev, int32_t* nnB_dev, void* ws, size_t ws_bytes,
                         int32_t flags, f3d_stream_t stream);
 
+/* chamfer_distance on HOST arrays — the array entry points chamfer_distance(A::AbstractArray, B::AbstractArray; w1, w2)
+ * (src/metrics/pcloud.jl:28-37) called with `Array`s: upload, sweep and loss read-back as ONE call, with the upload
+ * pipelined against the sweep.  The batch is cut into <= `chunks` pieces; piece k+1 crosses PCIe on a copy stream while
+ * piece k is swept, pieces alternate between two compute streams, and the per-piece partial losses (each already
+ * divided by N*B_total / M*B_total) are added in index order.  The result equals f3d_chamfer_fwd's up to the rounding of
+ * that final sum (<= 1 ulp per piece).
+ *   f3d_chamfer_pipe_create: streams + events only (no device memory); one handle per (device, host thread).
+ *   A_host [B][N][3], B_host [B][M][3]: HOST arrays; page-locked memory makes the copies asynchronous.
+ *   loss_dev (optional, 1 float): device copy of the loss, valid in `stream` order.
+ *   loss_host (optional): when given, the loss is copied back and `stream` is SYNCHRONISED before returning —
+ *     the one entry point of this ABI that may block, because a host scalar was asked for.
+ *   ws: f3d_chamfer_pipe_workspace_bytes(B, N, M, chunks) device bytes (staging copies of both clouds, two sweep
+ *     workspaces, partial losses), 256-byte aligned, owned by the caller. */
+F3D_API int32_t f3d_chamfer_pipe_create(int32_t chunks, void** pipe);
+F3D_API size_t f3d_chamfer_pipe_workspace_bytes(int32_t B, int32_t N, int32_t M, int32_t chunks);
+F3D_API int32_t f3d_chamfer_pipe_run(void* pipe, const float* A_host, const float* B_host, int32_t B, int32_t N,
+                             int32_t M, float w1, float w2, int32_t B_total, float* loss_dev,
+                             float* loss_host, void* ws, size_t ws_bytes, int32_t flags,
+                             f3d_stream_t stream);
+F3D_API int32_t f3d_chamfer_pipe_destroy(void* pipe);
+
 /* Pullback of src/metrics/pcloud.jl:47-50 (indices constant, :45 is @ignore):
  *   gA = gout*( 2w1/(N*B_total) (A - B[nnA])  -  scatter_add_{nnB}( 2w2/(M*B_total) (B - A[nnB]) ) ), gB symmetric.
  * gout_dev: 1 float (upstream gradient of the scalar loss).  gA/gB are fully overwritten. */

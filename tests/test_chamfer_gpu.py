@@ -185,3 +185,92 @@ def test_filter_sorted_and_structured(f3d, oracle):
     plane = rng.random((2, 2500, 3), dtype=np.float32)
     plane[..., 2] = 0.25
     _check(f3d, oracle, line, plane)
+
+
+# ---- host-array entry point (f3d_chamfer_pipe_*): upload pipelined against the sweep -------------------------------
+@pytest.mark.parametrize("B,N,M,chunks", [
+    (8, 1024, 1024, 4),    # 4 chunks of 2
+    (5, 700, 333, 4),      # ragged split: 2, 2, 1
+    (1, 257, 33, 4),       # a single batch element: one chunk
+    (3, 512, 640, 1),      # pipelining off
+    (32, 1024, 1024, 16),  # the maximum number of chunks
+])
+def test_host_pipeline_parity(f3d, oracle, B, N, M, chunks):
+    """chamfer_distance on HOST arrays (src/metrics/pcloud.jl:28-37 called with Arrays): same loss as the oracle within
+    1e-5 and as the single-call device path within the rounding of the per-chunk sum."""
+    rng = np.random.default_rng(1000 + B)
+    A = rng.random((B, N, 3), dtype=np.float32)
+    Bc = rng.random((B, M, 3), dtype=np.float32)
+    ol = float(oracle.chamfer_distance(A, Bc, 0.7, 1.3))
+    pA, pB = torch.from_numpy(A).pin_memory(), torch.from_numpy(Bc).pin_memory()
+    lh = f3d.chamfer_forward_host(pA, pB, 0.7, 1.3, chunks=chunks)
+    ld, *_ = _run(f3d, A, Bc, 0.7, 1.3)
+    lh2 = f3d.chamfer_forward_host(A, Bc, 0.7, 1.3, chunks=chunks)  # pageable numpy memory, workspace reused
+    lh3 = f3d.chamfer_forward_host(pA, pB, 0.7, 1.3, chunks=chunks, to_host=True)
+    lx = f3d.chamfer_forward_host(pA, pB, 0.7, 1.3, chunks=chunks, to_host=True, flags=f3d.FLAG_EXACT_SWEEP)
+    torch.cuda.synchronize()
+    assert lh.is_cuda and lh.shape == (1,) and not lh3.is_cuda and lh3.dim() == 0
+    assert abs(lh.item() - ol) <= RTOL * ol
+    # the same kernels on the same bytes: identical to the resident-input call, wherever the host bytes live and
+    # however the upload was cut
+    assert lh.item() == ld and lh2.item() == ld and lh3.item() == ld and lx.item() == ld
+
+
+def test_host_pipeline_repeated_and_interleaved(f3d, oracle):
+    """Back-to-back runs on one workspace with different data (flag reset between runs), interleaved with other work
+    on the same stream: every result must match its own inputs."""
+    rng = np.random.default_rng(77)
+    sets = [(rng.random((9, 900, 3), dtype=np.float32), rng.random((9, 900, 3), dtype=np.float32)) for _ in range(4)]
+    want = [float(oracle.chamfer_distance(a, b)) for a, b in sets]
+    pinned = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in sets]
+    junk = torch.zeros(1 << 22, device="cuda")
+    got_dev = []
+    for rep in range(3):
+        for a, b in pinned:
+            junk.add_(1.0)  # unrelated work queued ahead on the caller's stream
+            got_dev.append(f3d.chamfer_forward_host(a, b))
+    torch.cuda.synchronize()
+    for i, g in enumerate(got_dev):
+        assert abs(g.item() - want[i % 4]) <= RTOL * want[i % 4]
+    for rep in range(3):
+        for (a, b), w in zip(pinned, want):
+            assert abs(f3d.chamfer_distance(a, b).item() - w) <= RTOL * w
+
+
+def test_host_pipeline_public_api_and_sharding(f3d, oracle):
+    """chamfer_distance(host, host) takes the pipelined path; with batch_total the shard losses add up."""
+    A = np.random.default_rng(5).random((6, 600, 3), dtype=np.float32)
+    B = np.random.default_rng(6).random((6, 500, 3), dtype=np.float32)
+    ol = float(oracle.chamfer_distance(A, B))
+    with torch.no_grad():
+        full = f3d.chamfer_distance(A, B)
+        parts = [f3d.chamfer_distance(A[s], B[s], batch_total=6) for s in (slice(0, 4), slice(4, 6))]
+    assert not full.is_cuda and full.dim() == 0 and full.dtype == torch.float32  # host arrays in, host scalar out
+    assert abs(full.item() - ol) <= RTOL * ol
+    assert abs(sum(p.item() for p in parts) - ol) <= RTOL * ol
+    # a host tensor that requires grad still goes through the differentiable device path
+    tA = torch.from_numpy(A).requires_grad_(True)
+    f3d.chamfer_distance(tA, B).backward()
+    assert tA.grad is not None and tA.grad.shape == tA.shape
+
+
+def test_host_pipeline_errors(f3d):
+    import ctypes as C
+    L = f3d._lib.lib()
+    h = C.c_void_p()
+    assert L.f3d_chamfer_pipe_create(0, C.byref(h)) == 1
+    assert L.f3d_chamfer_pipe_create(17, C.byref(h)) == 1
+    assert L.f3d_chamfer_pipe_create(2, C.byref(h)) == 0
+    A = torch.zeros((2, 8, 3)).pin_memory()
+    ws = torch.empty(L.f3d_chamfer_pipe_workspace_bytes(2, 8, 8, 2), dtype=torch.uint8, device="cuda")
+    loss = torch.empty(1, device="cuda")
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = f3d._lib.ptr
+    assert L.f3d_chamfer_pipe_run(None, P(A), P(A), 2, 8, 8, 1.0, 1.0, 0, P(loss), None, P(ws), ws.numel(), 0, s) == 1
+    assert L.f3d_chamfer_pipe_run(h, None, P(A), 2, 8, 8, 1.0, 1.0, 0, P(loss), None, P(ws), ws.numel(), 0, s) == 1
+    assert L.f3d_chamfer_pipe_run(h, P(A), P(A), 2, 8, 8, 1.0, 1.0, 0, P(loss), None, P(ws), 16, 0, s) == 3
+    assert "workspace" in f3d._lib.last_error()
+    host = (C.c_float * 1)(-1.0)
+    assert L.f3d_chamfer_pipe_run(h, P(A), P(A), 2, 8, 8, 1.0, 1.0, 0, None, host, P(ws), ws.numel(), 0, s) == 0
+    assert host[0] == 0.0  # loss_host given: copied back and synchronised inside the call
+    assert L.f3d_chamfer_pipe_destroy(h) == 0
