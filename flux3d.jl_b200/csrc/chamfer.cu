@@ -41,19 +41,10 @@ constexpr int kChunk = F3D_CHUNK;  // columns per argmin-locator chunk
 #define F3D_MAXCPW 256
 #endif
 constexpr int kMaxColsPerWarp = F3D_MAXCPW;
+// header of the counter region (ints): every word that many CTAs hit at once has its own 128-byte line
+constexpr int kHdrStarted = 32, kHdrTimeout = 128, kHdrInts = 256;
 constexpr float kPadA = 1.0e18f;   // padded rows / columns sit ~1e18 apart from everything:
 constexpr float kPadB = -1.0e18f;  // d ≈ 1e37 (finite), never a minimum for in-contract inputs
-
-// Upload chunks of the host-array pipeline: sizes 1, 2, 4, ..., 2^m, 2^m, ... (the last one takes the remainder) — small
-// first so the sweep starts after ~100 KB has crossed PCIe, doubling because the sweep of what has landed hides the
-// next, larger copy.  Chunk c <= m starts at batch element 2^c - 1; chunk c > m at 2^(m+1) - 1 + (c - m - 1) 2^m.
-__host__ __device__ __forceinline__ int arrive_chunk_of(int b, int m, int nchunks) {
-    const unsigned x = (unsigned)b + 1u;
-    int c = 0;
-    if (x < (2u << m)) { while ((2u << c) <= x) ++c; }  // floor(log2(x)), x < 2^(m+1): at most m steps
-    else c = m + 1 + (int)((x - (2u << m)) >> m);
-    return c < nchunks - 1 ? c : nchunks - 1;
-}
 
 struct SweepParams {
     const float* A;   // [B][N][3]
@@ -370,6 +361,16 @@ constexpr float kBallotRel = 1.0000007f;  // >= 1 + 10.01u
 constexpr float kPadF = 3.0e38f;     // padded rows / columns: filter value ~3e38 (or +inf), never a minimum
 constexpr float kNormLimit = 1.0e29f;  // above this the filter arithmetic could overflow: certify nothing
 
+#ifdef F3D_EXP_CLOCK
+__device__ long long g_dbg[8 * 8192];
+#define DBG_T(k) do { if (tid == 0) { long long c_ = clock64(); unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); int id_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; if (id_ < 8192) { g_dbg[id_ * 8 + (k)] = c_; if ((k) == 0) { g_dbg[id_ * 8 + 4] = (long long)g_; unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_dbg[id_ * 8 + 6] = sm_; } if ((k) == 3) g_dbg[id_ * 8 + 5] = (long long)g_; } } } while (0)
+__device__ long long g_dbgf[8 * 2048];  // finalize: per block, globaltimer at 6 phase boundaries + smid
+#define DBG_F(k) do { if (threadIdx.x == 0 && blockIdx.x < 2048) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); g_dbgf[blockIdx.x * 8 + (k)] = (long long)g_; if ((k) == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_dbgf[blockIdx.x * 8 + 7] = sm_; } } } while (0)
+#else
+#define DBG_T(k)
+#define DBG_F(k)
+#endif
+
 struct FiltParams {
     const float* A;
     const float* Bp;
@@ -383,32 +384,72 @@ struct FiltParams {
     unsigned* counter;  // [0] finalize's block counter; zeroed by a memset node before every sweep, with:
     int* rowdone;       // [B][RB]  tiles of the row block that have published their partials (target CS)
     int* coldone;       // [B][CS]  tiles of the column split that have published their partials (target RB)
-    // host-array pipeline (chamfer_pipe.cu): the clouds are still crossing PCIe when the grid starts.  arrive[c] != 0
-    // once upload chunk c has landed (written by the copy engine, in stream order behind the chunk's data); null when
-    // the inputs are resident.  Batch element b belongs to chunk arrive_chunk_of(b, arr_m, arr_n).
-    const unsigned* arrive;
-    int arr_m, arr_n;
-    unsigned* arrive_timeout;  // set if a CTA gave up waiting (the finalize then reports NaN instead of a wrong loss)
+    // host-array pipeline (chamfer_pipe.cu): the first up.U CTAs of the grid (by start ticket) do not sweep — they pull the
+    // clouds out of page-locked HOST memory over PCIe (up.hA / up.hB, device-accessible) into A / Bp, batch element by
+    // batch element, and count each element's arrival in up.arrived[b]; a sweeping CTA waits for its element.
+    struct Upload {
+        const float* hA;     // [B][N][3] host; null when the inputs are resident (U = 0)
+        const float* hB;     // [B][M][3] host
+        float* dA;           // == A, writable
+        float* dB;           // == Bp, writable
+        unsigned* arrived;   // [B]  uploader CTAs that have delivered their share of the element (target U)
+        unsigned* timeout;   // set if a CTA gave up waiting (the loss is then reported as NaN, never a wrong number)
+        int U;
+    } up;
+    int B;  // batch elements of this call (upload mode: how many elements the uploaders deliver)
 };
 
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
-// The centre of a batch element is the mean of 32 + 32 strided sample points.  ANY point works (the bound uses the
-// norms actually obtained); every warp of every CTA of the element computes the same value with the same operations.
+// ---- upload mode: pull both clouds out of page-locked host memory, batch element by batch element -----------------
+// U CTAs x 128 threads stream the element with 16-byte loads, four per thread in flight (≈ 256 KB outstanding over
+// PCIe), into the staging copy the sweep reads; each CTA then counts the element as delivered (release).  A chunked
+// cudaMemcpyAsync schedule does the same job with ~3.5 µs of HOST time per call (profiles/r01g: 12 chunk copies + 6
+// flag writes = 131 µs against 67 µs for two plain copies) — here the host launches one grid and the copy paces itself.
+__device__ __forceinline__ float4 ld_host_f4(const float* p) {
+    float4 v;  // volatile: never served from a stale cache line of a previous step's bytes at the same host address
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_host_f1(const float* p) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+// floats [s, e) of src -> dst (same index space, both bases 16-byte aligned): scalar head/tail, 16-byte body
+__device__ __forceinline__ void upload_span(const float* __restrict__ src, float* __restrict__ dst, size_t s, size_t e, int u, int U, int tid) {
+    size_t s4 = (s + 3) & ~(size_t)3, e4 = e & ~(size_t)3;
+    if (s4 > e4) s4 = e4 = e;  // fewer than one aligned quad: everything is "head"
+    if (u == 0) {
+        if (s + tid < s4) dst[s + tid] = ld_host_f1(src + s + tid);    // < 4 floats each
+        if (e4 + tid < e && e4 >= s4) dst[e4 + tid] = ld_host_f1(src + e4 + tid);
+    }
+    const size_t n4 = (e4 - s4) >> 2, stride = (size_t)U * kThreads;
+    for (size_t i = (size_t)u * kThreads + tid; i < n4; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i + k * stride < n4) v[k] = ld_host_f4(src + s4 + 4 * (i + k * stride));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i + k * stride < n4) __stcg(reinterpret_cast<float4*>(dst + s4) + i + k * stride, v[k]);
+    }
+}
+__device__ void upload_clouds(const FiltParams& p, const int u, const int tid) {
+    const size_t ea = (size_t)p.N * 3, eb = (size_t)p.M * 3;
+    for (int b = 0; b < p.B; ++b) {
+        upload_span(p.up.hA, p.up.dA, b * ea, (b + 1) * ea, u, p.up.U, tid);
+        upload_span(p.up.hB, p.up.dB, b * eb, (b + 1) * eb, u, p.up.U, tid);
+        __threadfence();   // this thread's stores are visible device-wide ...
+        __syncthreads();   // ... for every thread of the CTA ...
+        if (tid == 0) atomicAdd(p.up.arrived + b, 1u);  // ... before the element counts as delivered by this CTA
+    }
+}
 
-#ifdef F3D_EXP_CLOCK
-__device__ long long g_dbg[8 * 8192];
-#define DBG_T(k) do { if (tid == 0) { long long c_ = clock64(); unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); int id_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; if (id_ < 8192) { g_dbg[id_ * 8 + (k)] = c_; if ((k) == 0) { g_dbg[id_ * 8 + 4] = (long long)g_; unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_dbg[id_ * 8 + 6] = sm_; } if ((k) == 3) g_dbg[id_ * 8 + 5] = (long long)g_; } } } while (0)
-__device__ long long g_dbgf[8 * 2048];  // finalize: per block, globaltimer at 6 phase boundaries + smid
-#define DBG_F(k) do { if (threadIdx.x == 0 && blockIdx.x < 2048) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); g_dbgf[blockIdx.x * 8 + (k)] = (long long)g_; if ((k) == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_dbgf[blockIdx.x * 8 + 7] = sm_; } } } while (0)
-#else
-#define DBG_T(k)
-#define DBG_F(k)
-#endif
 #ifndef F3D_FILT_MINB
 #define F3D_FILT_MINB 4
 #endif
@@ -422,37 +463,49 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
     float4* s_zn = s_xy + BN / 2;                                // [BN/2] {-2z0,-2z1,nb0,nb1}
     float4* s_row = s_zn + BN / 2;                               // [kWarps][kTileRows] {b1,b2,c1,-}; first used as s_rm
     __shared__ unsigned s_maxnb;
+    __shared__ int s_ticket;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cs = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
-    const int col0 = cs * BN, row0 = rb * kTileRows;
-    const float* gA = p.A + (size_t)b * p.N * 3;
-    const float* gB = p.Bp + (size_t)b * p.M * 3;
+    int cs = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
 
     DBG_T(0);
     // Programmatic dependent launch: let the finalize grid become resident as soon as every CTA of this grid has been
     // dispatched; its blocks wait on rowdone/coldone, so they soak up the SM slots the last partial wave leaves idle.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) s_maxnb = 0u;
-    if (p.arrive) {
-        // wait until this batch element's upload chunk has landed.  CTAs are dispatched in batch order and the copy
-        // engine needs no SM, so spinning CTAs cannot starve the copies; the bounded wait (2 s) turns a lost copy into
-        // a reported error instead of a hung device.
+    if (p.up.U) {
+        // Upload mode (1-D grid of U + tiles CTAs).  Roles go by START order, not by blockIdx: the first U CTAs to start
+        // are the uploaders, so every CTA that waits for data below started after the CTAs that deliver it — forward
+        // progress needs no assumption about the dispatch order.  The others take tiles in batch order.
+        if (tid == 0) s_ticket = (int)atomicAdd(p.counter + kHdrStarted, 1u);
+        __syncthreads();
+        const int ticket = s_ticket;
+        if (ticket < p.up.U) {
+            upload_clouds(p, ticket, tid);
+            return;
+        }
+        const int tile = ticket - p.up.U;
+        cs = tile % p.CS; rb = (tile / p.CS) % p.RB; b = tile / (p.CS * p.RB);
+        // wait until this batch element has landed; the bounded wait (2 s) turns a lost upload into a reported error
+        // instead of a hung device
         if (tid == 0) {
-            const unsigned* f = p.arrive + arrive_chunk_of(b, p.arr_m, p.arr_n);
+            const int* f = reinterpret_cast<const int*>(p.up.arrived) + b;
             unsigned long long t0 = 0;
-            for (unsigned spins = 0; ld_acquire_sys(f) == 0u; ++spins) {
+            for (unsigned spins = 0; ld_acquire(f) < p.up.U; ++spins) {
                 __nanosleep(100);
                 if ((spins & 1023u) == 1023u) {
                     unsigned long long now;
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                     if (t0 == 0) t0 = now;
-                    else if (now - t0 > 2000000000ull) { atomicExch(p.arrive_timeout, 1u); break; }
+                    else if (now - t0 > 2000000000ull) { atomicExch(p.up.timeout, 1u); break; }
                 }
             }
         }
         __syncthreads();
     }
+    const int col0 = cs * BN, row0 = rb * kTileRows;
+    const float* gA = p.A + (size_t)b * p.N * 3;
+    const float* gB = p.Bp + (size_t)b * p.M * 3;
 
     // ---- prologue: issue EVERY global load first (centre samples, this thread's column pairs, this lane's rows),
     // so the CTA pays one memory latency instead of one per dependent step -------------------------------------
@@ -663,14 +716,9 @@ struct FiltFinalizeParams {
     double denomA, denomB;
     float* loss;
     float* terms;
-    const unsigned* arrive_timeout;  // null unless the sweep waited for uploads
+    const unsigned* upload_timeout;  // null unless the sweep ran in upload mode
 };
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // exact (reference-arithmetic) argmin of |q - P[j]|² over j in [j0, j1), cooperatively by the whole block: thread t takes
 // candidates j0 + 4t .. j0 + 4t + 3 (+ 4·kFinThreads per further trip) and merges them into ITS running (dmin, jmin); a
@@ -959,7 +1007,7 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_filter_finalize_kernel(Fi
         const float dAB = (float)(ta / p.denomA), dBA = (float)(tb / p.denomB);  // pcloud.jl:47-48
         if (p.terms) { p.terms[0] = dAB; p.terms[1] = dBA; }
         float l = __fadd_rn(__fmul_rn(p.w1, dAB), __fmul_rn(p.w2, dBA));          // pcloud.jl:50
-        if (p.arrive_timeout && __ldcg(p.arrive_timeout) != 0u) l = __int_as_float(0x7fc00000);  // an upload never landed
+        if (p.upload_timeout && __ldcg(p.upload_timeout) != 0u) l = __int_as_float(0x7fc00000);  // an upload never landed
         p.loss[0] = l;
     }
 }
@@ -988,9 +1036,9 @@ FiltPlan make_filt_plan(int B, int N, int M) {
     pl.off_maxnb = o;   o = align_up(o + sizeof(float) * (size_t)B * pl.CS, 256);
     pl.off_centre = o;  o = align_up(o + sizeof(float) * 4 * (size_t)B, 256);
     pl.off_partial = o; o = align_up(o + sizeof(double) * (size_t)(pl.nbA + pl.nbB), 256);
-    // [0..63] finalize block counter | [64..127] upload-arrival flags (kArriveMaxChunks words) | [128..131] arrival
-    // timeout flag | rowdone [B][RB] | coldone [B][CS]  — one memset zeroes all of it per call
-    pl.counter_bytes = 256 + sizeof(int) * ((size_t)B * pl.RB + (size_t)B * pl.CS);
+    // header (kHdr*: finalize blocks done, CTAs started (upload mode), upload timeout flag) |
+    // rowdone [B][RB] | coldone [B][CS] | arrived [B] (upload mode)  — one memset zeroes all of it per call
+    pl.counter_bytes = sizeof(int) * kHdrInts + sizeof(int) * ((size_t)B * pl.RB + (size_t)B * pl.CS + (size_t)B);
     pl.off_counter = o; o = align_up(o + pl.counter_bytes, 256);
     pl.total = o;
     return pl;
@@ -1024,7 +1072,7 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
 
 int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M, float w1, float w2,
                                 int32_t B_total, float* loss_dev, float* terms_dev, int32_t* nnA_dev, int32_t* nnB_dev,
-                                void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream, ChamferArrive* arrive) {
+                                void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream, const ChamferUpload* upload) {
     using namespace f3d;
     if (!A || !Bp || !loss_dev) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: null A/B/loss pointer");
     if (B <= 0 || N <= 0 || M <= 0) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: B, N, M must be positive (got %d, %d, %d)", B, N, M);
@@ -1036,8 +1084,8 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
     if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0) return fail(F3D_ERR_MISALIGNED, "f3d_chamfer_fwd: workspace must be 256-byte aligned");
     unsigned char* w = static_cast<unsigned char*>(ws);
     const bool fma = (flags & F3D_FLAG_FMA) != 0;
-    if (arrive && (fma || (flags & (F3D_FLAG_EXACT_SWEEP | F3D_FLAG_SWEEP_ONLY))))
-        return fail(F3D_ERR_INVALID, "chamfer_fwd_launch: upload-arrival flags exist only for the default (filtered) sweep");
+    if (upload && (fma || (flags & (F3D_FLAG_EXACT_SWEEP | F3D_FLAG_SWEEP_ONLY))))
+        return fail(F3D_ERR_INVALID, "chamfer_fwd_launch: the in-grid upload exists only for the default (filtered) sweep");
 
     if (!fma && !(flags & F3D_FLAG_EXACT_SWEEP)) {
         // ---- default: filtered sweep + certified exact finalize (bit-identical results, ~half the FP32 work) ----
@@ -1052,20 +1100,33 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
         sp.maxnb = reinterpret_cast<float*>(w + fl.off_maxnb);
         sp.centre = reinterpret_cast<float*>(w + fl.off_centre);
         sp.counter = reinterpret_cast<unsigned*>(w + fl.off_counter);
-        sp.rowdone = reinterpret_cast<int*>(w + fl.off_counter + 256);
+        sp.rowdone = reinterpret_cast<int*>(w + fl.off_counter) + kHdrInts;
         sp.coldone = sp.rowdone + (size_t)B * fl.RB;
         F3D_CUDA(cudaMemsetAsync(w + fl.off_counter, 0, fl.counter_bytes, stream));
-        sp.arrive = nullptr; sp.arr_m = 0; sp.arr_n = 1;
-        sp.arrive_timeout = reinterpret_cast<unsigned*>(w + fl.off_counter + 128);
-        if (arrive) {
-            if (arrive->nchunks < 1 || arrive->nchunks > kArriveMaxChunks) return fail(F3D_ERR_INVALID, "chamfer_fwd_launch: bad chunk count %d", arrive->nchunks);
-            F3D_CUDA(cudaEventRecord(arrive->reset_done, stream));  // the flags are zero from here on: uploads may raise them
-            arrive->flags_dev = reinterpret_cast<unsigned*>(w + fl.off_counter + 64);
-            sp.arrive = arrive->flags_dev; sp.arr_m = arrive->m; sp.arr_n = arrive->nchunks;
+        sp.up.hA = nullptr; sp.up.hB = nullptr; sp.up.dA = nullptr; sp.up.dB = nullptr; sp.up.U = 0;
+        sp.up.arrived = reinterpret_cast<unsigned*>(sp.coldone + (size_t)B * fl.CS);
+        sp.up.timeout = sp.counter + kHdrTimeout;
+        if (upload) {
+            if (upload->uploaders < 1 || upload->uploaders > 1024) return fail(F3D_ERR_INVALID, "chamfer_fwd_launch: bad uploader count %d", upload->uploaders);
+            sp.up.hA = upload->A_host_dev; sp.up.hB = upload->B_host_dev;
+            sp.up.dA = const_cast<float*>(A); sp.up.dB = const_cast<float*>(Bp);
+            sp.up.U = upload->uploaders;
         }
         const size_t smem = filt_smem_bytes(fl.BN);
-        F3D_CUDA(cudaFuncSetAttribute(chamfer_filter_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        chamfer_filter_sweep_kernel<<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
+        {
+            // opt in to the largest tile's shared memory once per device (idempotent; racing threads at worst set it twice)
+            static unsigned char attr_done[256];
+            int dev = 0;
+            F3D_CUDA(cudaGetDevice(&dev));
+            if (dev < 0 || dev >= 256 || !attr_done[dev]) {
+                F3D_CUDA(cudaFuncSetAttribute(chamfer_filter_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)filt_smem_bytes(kWarps * kMaxColsPerWarp)));
+                if (dev >= 0 && dev < 256) attr_done[dev] = 1;
+            }
+        }
+        sp.B = B;
+        if (sp.up.U) chamfer_filter_sweep_kernel<<<dim3((unsigned)fl.CS * fl.RB * B + sp.up.U), kThreads, smem, stream>>>(sp);
+        else chamfer_filter_sweep_kernel<<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
         F3D_CHECK_LAUNCH("chamfer_filter_sweep_kernel");
         if (flags & F3D_FLAG_SWEEP_ONLY) return F3D_OK;
         FiltFinalizeParams fp;
@@ -1080,7 +1141,7 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
         fp.denomA = (double)N * (double)B_total;
         fp.denomB = (double)M * (double)B_total;
         fp.loss = loss_dev; fp.terms = terms_dev;
-        fp.arrive_timeout = arrive ? sp.arrive_timeout : nullptr;
+        fp.upload_timeout = upload ? sp.up.timeout : nullptr;
         {
             // programmatic dependent launch: blocks may start while the sweep's last wave is still running
             cudaLaunchConfig_t cfg = {};

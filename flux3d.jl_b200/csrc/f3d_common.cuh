@@ -27,20 +27,16 @@ int32_t cuda_fail(cudaError_t e, const char* what);
         if (e__ != cudaSuccess) return ::f3d::cuda_fail(e__, #call);  \
     } while (0)
 
-// ---- internal: f3d_chamfer_fwd with optional upload-arrival flags (chamfer_pipe.cu: the sweep starts while the clouds
-// are still crossing PCIe).  reset_done is recorded on `stream` once the flags are zeroed; flags_dev receives their
-// device address (kArriveMaxChunks words); chunk layout: arrive_chunk_of() in chamfer.cu / arrive_chunk_begin() below.
-constexpr int kArriveMaxChunks = 16;
-struct ChamferArrive {
-    int nchunks, m;
-    cudaEvent_t reset_done;
-    unsigned* flags_dev;
+// ---- internal: f3d_chamfer_fwd with the optional in-grid upload (chamfer_pipe.cu): A / Bp are then staging buffers that
+// the grid's first `uploaders` CTAs fill from page-locked host memory (device-accessible addresses) while the others sweep.
+struct ChamferUpload {
+    const float* A_host_dev;  // the host arrays as the device addresses them (cudaHostGetDevicePointer)
+    const float* B_host_dev;
+    int uploaders;
 };
 int32_t chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M, float w1, float w2,
                            int32_t B_total, float* loss_dev, float* terms_dev, int32_t* nnA_dev, int32_t* nnB_dev,
-                           void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream, ChamferArrive* arrive);
-// first batch element of upload chunk c: sizes 1, 2, 4, ..., 2^m, 2^m, ...
-static inline int arrive_chunk_begin(int c, int m) { return c <= m ? (1 << c) - 1 : (2 << m) - 1 + ((c - m - 1) << m); }
+                           void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream, const ChamferUpload* upload);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

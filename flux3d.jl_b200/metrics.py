@@ -54,13 +54,13 @@ def _is_host(x) -> bool:
     return not (isinstance(x, torch.Tensor) and x.is_cuda)
 
 
-def chamfer_forward_host(A, B, w1: float = 1.0, w2: float = 1.0, *, batch_total: int = 0, chunks: int = 0,
+def chamfer_forward_host(A, B, w1: float = 1.0, w2: float = 1.0, *, batch_total: int = 0, uploaders: int = 0,
                          flags: int = FLAG_NONE, device="cuda", to_host: bool = False) -> torch.Tensor:
-    """One call of f3d_chamfer_pipe_run: HOST arrays A (B,N,3), B (B,M,3) → the loss.  The sweep grid starts at once and
-    consumes the batch while it is still crossing PCIe (page-locked inputs make the uploads asynchronous).
-    ``to_host=False``: loss[1] on ``device``, no host synchronisation.  ``to_host=True``: a 0-dim CPU tensor — the
-    kernel stores the loss into mapped host memory and the call returns when it has landed (no D2H copy).
-    ``chunks``: upper bound on the number of upload chunks (0 = 16, 1 = upload everything, then sweep)."""
+    """One call of f3d_chamfer_pipe_run: HOST arrays A (B,N,3), B (B,M,3) → the loss.  With page-locked inputs the grid
+    pulls the batch over PCIe itself (its first ``uploaders`` CTAs; 0 = default) while the other CTAs sweep what has
+    landed; pageable inputs are copied first.  ``to_host=False``: loss[1] on ``device``, no host synchronisation.
+    ``to_host=True``: a 0-dim CPU tensor — the grid stores the loss into mapped host memory and the call returns when
+    it has landed (no D2H copy)."""
     L = _lib.lib()
     A = as_f32_tensor(A)
     B = as_f32_tensor(B)
@@ -74,16 +74,16 @@ def chamfer_forward_host(A, B, w1: float = 1.0, w2: float = 1.0, *, batch_total:
     dev = torch.device(device)
     if dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device())
-    chunks = 16 if chunks <= 0 else min(int(chunks), 16)
+    uploaders = max(0, min(int(uploaders), 1024))
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev)
-        key = (dev.index, chunks)
+        key = (dev.index, uploaders)
         h = _pipes.get(key)
         if h is None:
             h = _lib.C.c_void_p()
-            _lib.check(L.f3d_chamfer_pipe_create(chunks, _lib.C.byref(h)))
+            _lib.check(L.f3d_chamfer_pipe_create(uploaders, _lib.C.byref(h)))
             _pipes[key] = h
-        ws = _workspace(("chamfer_pipe", Bn, N, M, chunks), L.f3d_chamfer_pipe_workspace_bytes(Bn, N, M, chunks), dev)
+        ws = _workspace(("chamfer_pipe", Bn, N, M), L.f3d_chamfer_pipe_workspace_bytes(Bn, N, M), dev)
         if to_host:
             out = _lib.C.c_float()
             _lib.check(L.f3d_chamfer_pipe_run(h, _lib.ptr(A), _lib.ptr(B), Bn, N, M, w1, w2, batch_total, None,

@@ -96,19 +96,20 @@ F3D_API int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, int3
 
 /* chamfer_distance on HOST arrays — the array entry points chamfer_distance(A::AbstractArray, B::AbstractArray; w1, w2)
  * (src/metrics/pcloud.jl:28-37) called with `Array`s: upload, sweep and loss read-back as ONE call, with the upload
- * pipelined against the sweep.  The batch is cut into <= `chunks` pieces; piece k+1 crosses PCIe on a copy stream while
- * piece k is swept, pieces alternate between two compute streams, and the per-piece partial losses (each already
- * divided by N*B_total / M*B_total) are added in index order.  The result equals f3d_chamfer_fwd's up to the rounding of
- * that final sum (<= 1 ulp per piece).
- *   f3d_chamfer_pipe_create: streams + events only (no device memory); one handle per (device, host thread).
- *   A_host [B][N][3], B_host [B][M][3]: HOST arrays; page-locked memory makes the copies asynchronous.
+ * running inside the sweep grid.  When both arrays are page-locked (cudaHostAlloc / cudaHostRegister: the device can
+ * address them) and 16-byte aligned, the grid's first `uploaders` CTAs pull the clouds over PCIe batch element by batch
+ * element while the other CTAs sweep, each waiting only for its own element; otherwise the arrays are copied with
+ * cudaMemcpyAsync on `stream` first.  Either way the result is bit-identical to f3d_chamfer_fwd on resident inputs.
+ *   f3d_chamfer_pipe_create: uploaders = CTAs (x128 threads) that upload, 0 = default (32).  The handle owns 64 bytes of
+ *     mapped host memory (no device memory); one handle per (device, host thread).
+ *   A_host [B][N][3], B_host [B][M][3]: HOST arrays; they must stay valid until the call's work on `stream` is done.
  *   loss_dev (optional, 1 float): device copy of the loss, valid in `stream` order.
- *   loss_host (optional): when given, the loss is copied back and `stream` is SYNCHRONISED before returning —
- *     the one entry point of this ABI that may block, because a host scalar was asked for.
- *   ws: f3d_chamfer_pipe_workspace_bytes(B, N, M, chunks) device bytes (staging copies of both clouds, two sweep
- *     workspaces, partial losses), 256-byte aligned, owned by the caller. */
-F3D_API int32_t f3d_chamfer_pipe_create(int32_t chunks, void** pipe);
-F3D_API size_t f3d_chamfer_pipe_workspace_bytes(int32_t B, int32_t N, int32_t M, int32_t chunks);
+ *   loss_host (optional): when given, the grid stores the loss into mapped host memory and the call returns once it
+ *     has landed (no D2H copy) — the one entry point of this ABI that blocks, because a host scalar was asked for.
+ *   ws: f3d_chamfer_pipe_workspace_bytes(B, N, M) device bytes (staging copies of both clouds + the sweep workspace),
+ *     256-byte aligned, owned by the caller. */
+F3D_API int32_t f3d_chamfer_pipe_create(int32_t uploaders, void** pipe);
+F3D_API size_t f3d_chamfer_pipe_workspace_bytes(int32_t B, int32_t N, int32_t M);
 F3D_API int32_t f3d_chamfer_pipe_run(void* pipe, const float* A_host, const float* B_host, int32_t B, int32_t N,
                              int32_t M, float w1, float w2, int32_t B_total, float* loss_dev,
                              float* loss_host, void* ws, size_t ws_bytes, int32_t flags,

@@ -189,11 +189,11 @@ def test_filter_sorted_and_structured(f3d, oracle):
 
 # ---- host-array entry point (f3d_chamfer_pipe_*): upload pipelined against the sweep -------------------------------
 @pytest.mark.parametrize("B,N,M,chunks", [
-    (8, 1024, 1024, 4),    # 4 chunks of 2
-    (5, 700, 333, 4),      # ragged split: 2, 2, 1
-    (1, 257, 33, 4),       # a single batch element: one chunk
-    (3, 512, 640, 1),      # pipelining off
-    (32, 1024, 1024, 16),  # the maximum number of chunks
+    (8, 1024, 1024, 0),    # default number of uploader CTAs
+    (5, 700, 333, 3),      # 3M not a multiple of 4: elements start at unaligned floats (scalar head / tail)
+    (1, 257, 33, 1),       # a single batch element, a single uploader
+    (3, 1, 2, 7),          # spans shorter than one aligned quad
+    (32, 1024, 1024, 64),
 ])
 def test_host_pipeline_parity(f3d, oracle, B, N, M, chunks):
     """chamfer_distance on HOST arrays (src/metrics/pcloud.jl:28-37 called with Arrays): same loss as the oracle within
@@ -203,11 +203,11 @@ def test_host_pipeline_parity(f3d, oracle, B, N, M, chunks):
     Bc = rng.random((B, M, 3), dtype=np.float32)
     ol = float(oracle.chamfer_distance(A, Bc, 0.7, 1.3))
     pA, pB = torch.from_numpy(A).pin_memory(), torch.from_numpy(Bc).pin_memory()
-    lh = f3d.chamfer_forward_host(pA, pB, 0.7, 1.3, chunks=chunks)
+    lh = f3d.chamfer_forward_host(pA, pB, 0.7, 1.3, uploaders=chunks)
     ld, *_ = _run(f3d, A, Bc, 0.7, 1.3)
-    lh2 = f3d.chamfer_forward_host(A, Bc, 0.7, 1.3, chunks=chunks)  # pageable numpy memory, workspace reused
-    lh3 = f3d.chamfer_forward_host(pA, pB, 0.7, 1.3, chunks=chunks, to_host=True)
-    lx = f3d.chamfer_forward_host(pA, pB, 0.7, 1.3, chunks=chunks, to_host=True, flags=f3d.FLAG_EXACT_SWEEP)
+    lh2 = f3d.chamfer_forward_host(A, Bc, 0.7, 1.3, uploaders=chunks)  # pageable numpy memory, workspace reused
+    lh3 = f3d.chamfer_forward_host(pA, pB, 0.7, 1.3, uploaders=chunks, to_host=True)
+    lx = f3d.chamfer_forward_host(pA, pB, 0.7, 1.3, uploaders=chunks, to_host=True, flags=f3d.FLAG_EXACT_SWEEP)
     torch.cuda.synchronize()
     assert lh.is_cuda and lh.shape == (1,) and not lh3.is_cuda and lh3.dim() == 0
     assert abs(lh.item() - ol) <= RTOL * ol
@@ -258,11 +258,11 @@ def test_host_pipeline_errors(f3d):
     import ctypes as C
     L = f3d._lib.lib()
     h = C.c_void_p()
-    assert L.f3d_chamfer_pipe_create(0, C.byref(h)) == 1
-    assert L.f3d_chamfer_pipe_create(17, C.byref(h)) == 1
+    assert L.f3d_chamfer_pipe_create(-1, C.byref(h)) == 1
+    assert L.f3d_chamfer_pipe_create(1025, C.byref(h)) == 1
     assert L.f3d_chamfer_pipe_create(2, C.byref(h)) == 0
     A = torch.zeros((2, 8, 3)).pin_memory()
-    ws = torch.empty(L.f3d_chamfer_pipe_workspace_bytes(2, 8, 8, 2), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(L.f3d_chamfer_pipe_workspace_bytes(2, 8, 8), dtype=torch.uint8, device="cuda")
     loss = torch.empty(1, device="cuda")
     s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     P = f3d._lib.ptr

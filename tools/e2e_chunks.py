@@ -7,13 +7,13 @@ import flux3d_b200 as f3d
 B, N, M = 32, 4096, 4096
 A = torch.from_numpy(np.random.default_rng(201).random((B, N, 3), dtype=np.float32)).pin_memory()
 Bc = torch.from_numpy(np.random.default_rng(202).random((B, M, 3), dtype=np.float32)).pin_memory()
-for chunks in (1, 2, 4, 8, 16):
+for chunks in (4, 16, 32, 64):
     for _ in range(5):
-        f3d.chamfer_forward_host(A, Bc, chunks=chunks).item()
+        f3d.chamfer_forward_host(A, Bc, uploaders=chunks).item()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(200):
-        v = f3d.chamfer_forward_host(A, Bc, chunks=chunks).item()
+        v = f3d.chamfer_forward_host(A, Bc, uploaders=chunks).item()
     dt = (time.perf_counter() - t0) / 200
     print(f"chunks={chunks:2d}  {dt*1e6:7.1f} us/step  {B*N*M/dt:.3e} pairs/s  loss={v:.10f}")
 dA, dB = A.cuda(), Bc.cuda()

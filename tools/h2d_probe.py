@@ -43,12 +43,12 @@ def old_e2e():
     return f3d.chamfer_forward_raw(a, b, 1.0, 1.0, want_indices=False)[0].item()
 g, w = ev_time(old_e2e)
 print(f"old e2e (2 torch copies + fwd + item): {g:.1f} us gpu, {w:.1f} us wall")
-for chunks in (1, 4, 16):
-    g, w = ev_time(lambda: f3d.chamfer_forward_host(A, Bc, chunks=chunks))
+for chunks in (8, 32, 128):
+    g, w = ev_time(lambda: f3d.chamfer_forward_host(A, Bc, uploaders=chunks))
     print(f"pipe chunks={chunks} device loss, no sync: {g:.1f} us gpu, {w:.1f} us wall")
-    g, w = ev_time(lambda: f3d.chamfer_forward_host(A, Bc, chunks=chunks).item())
+    g, w = ev_time(lambda: f3d.chamfer_forward_host(A, Bc, uploaders=chunks).item())
     print(f"pipe chunks={chunks} + item: {g:.1f} us gpu, {w:.1f} us wall")
-    g, w = ev_time(lambda: f3d.chamfer_forward_host(A, Bc, chunks=chunks, to_host=True))
+    g, w = ev_time(lambda: f3d.chamfer_forward_host(A, Bc, uploaders=chunks, to_host=True))
     print(f"pipe chunks={chunks} to_host (mapped slot): {g:.1f} us gpu, {w:.1f} us wall")
 g, w = ev_time(lambda: f3d.chamfer_distance(A, Bc).item())
 print(f"public chamfer_distance(host, host).item(): {w:.1f} us wall")
@@ -56,7 +56,7 @@ print(f"public chamfer_distance(host, host).item(): {w:.1f} us wall")
 L = f3d._lib.lib()
 t0 = time.perf_counter()
 for _ in range(100):
-    x = f3d.chamfer_forward_host(A, Bc, chunks=16)
+    x = f3d.chamfer_forward_host(A, Bc, uploaders=0)
 t1 = time.perf_counter()
 torch.cuda.synchronize()
-print(f"pipe chunks=16 host-side issue time: {(t1-t0)/100*1e6:.1f} us/call")
+print(f"pipe uploaders=0 host-side issue time: {(t1-t0)/100*1e6:.1f} us/call")
