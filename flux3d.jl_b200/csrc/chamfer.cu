@@ -757,9 +757,14 @@ __device__ __forceinline__ void block_exact_scan(const float* __restrict__ P, in
 //   phase 1  lane <-> item: merge the sweep's partials, decide "certified" vs "ambiguous"
 //   phase 2  lane <-> item: re-evaluate the located candidates exactly (16-byte loads, batched)
 //   phase 3  the (rare) ambiguous items, one at a time, whole block: exact scan of every tile within the window
-__global__ void __launch_bounds__(kFinThreads) chamfer_filter_finalize_kernel(FiltFinalizeParams p) {
+#ifndef F3D_FIN_MINB
+#define F3D_FIN_MINB 5
+#endif
+__global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_finalize_kernel(FiltFinalizeParams p) {
     __shared__ double s_red[kFinThreads / 32];
     __shared__ bool s_last;
+    constexpr int kMaxSel = 32;  // phase 3: tiles within an ambiguous item's window that are scanned as one candidate range
+    __shared__ int s_sel[kMaxSel], s_nsel;
     __shared__ unsigned s_amb[kFinThreads / 32], s_wd[kFinThreads / 32];  // phase 3: ambiguous-item queue, block argmin
     __shared__ int s_wj[kFinThreads / 32], s_ib[kFinThreads], s_iq[kFinThreads];
     __shared__ float s_ilim[kFinThreads];
@@ -943,7 +948,55 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_filter_finalize_kernel(Fi
                 const float* P = gP + (size_t)bb * R * 3;
                 float d = INFINITY;
                 int j = 0x7fffffff;
-                if (rows) {
+                // (a) which tiles lie within the window: one thread per tile, so ONE round trip instead of one per tile
+                const int ntile = rows ? p.CS : p.RB, tw = rows ? p.BN : kTileRows;
+                if (tid == 0) s_nsel = 0;
+                __syncthreads();
+                for (int t0 = 0; t0 < ntile; t0 += kFinThreads) {
+                    const int t = t0 + tid;
+                    if (t < ntile) {
+                        const float e1 = rows ? __ldcg(&p.rowpart[((size_t)bb * p.CS + t) * p.Npad + qq].x)
+                                              : __uint_as_float(__ldcg(&p.colpart[((size_t)bb * p.RB + t) * p.Mpad + qq].x));
+                        if (!(fmaxf(e1, 0.0f) > lim)) {
+                            const int pos = atomicAdd(&s_nsel, 1);
+                            if (pos < kMaxSel) s_sel[pos] = t;
+                        }
+                    }
+                }
+                __syncthreads();
+                const int nsel = s_nsel;
+                if (nsel <= kMaxSel) {
+                    // (b) the selected tiles as ONE candidate range: thread t takes candidates 4t .. 4t+3 (+ 1024 per trip), so
+                    // the loads of all tiles are in flight together.  The order of s_sel is arbitrary: full (d, j) comparison.
+                    const int total = nsel * tw;
+                    for (int idx = 4 * tid; idx < total; idx += 4 * kFinThreads) {
+                        const int sidx = idx / tw, jb = s_sel[sidx] * tw + (idx - sidx * tw);  // tw is a multiple of 4
+                        if (jb >= R) continue;
+                        const float* pp = P + 3 * (size_t)jb;
+                        float c[12];
+                        if (jb + 4 <= R && (reinterpret_cast<uintptr_t>(pp) & 15u) == 0) {
+                            const float4 v0 = __ldg(reinterpret_cast<const float4*>(pp));
+                            const float4 v1 = __ldg(reinterpret_cast<const float4*>(pp) + 1);
+                            const float4 v2 = __ldg(reinterpret_cast<const float4*>(pp) + 2);
+                            c[0] = v0.x; c[1] = v0.y; c[2] = v0.z; c[3] = v0.w; c[4] = v1.x; c[5] = v1.y;
+                            c[6] = v1.z; c[7] = v1.w; c[8] = v2.x; c[9] = v2.y; c[10] = v2.z; c[11] = v2.w;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int jj = min(jb + k, R - 1);  // clamped duplicates are harmless (same value, same index)
+                                c[3 * k] = __ldg(P + 3 * (size_t)jj); c[3 * k + 1] = __ldg(P + 3 * (size_t)jj + 1); c[3 * k + 2] = __ldg(P + 3 * (size_t)jj + 2);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // operand order of the reference: (a - b) with a from the first cloud
+                            const float dd = rows ? sqdist3<false>(qx, qy, qz, c[3 * k], c[3 * k + 1], c[3 * k + 2])
+                                                  : sqdist3<false>(c[3 * k], c[3 * k + 1], c[3 * k + 2], qx, qy, qz);
+                            const int jj = min(jb + k, R - 1);
+                            if (dd < d || (dd == d && jj < j)) { d = dd; j = jj; }
+                        }
+                    }
+                } else if (rows) {  // tie-heavy input: more tiles within the window than the list holds — scan them in order
                     for (int cs = 0; cs < p.CS; ++cs) {
                         const float e1 = fmaxf(__ldcg(&p.rowpart[((size_t)bb * p.CS + cs) * p.Npad + qq].x), 0.0f);
                         if (!(e1 > lim)) block_exact_scan<true>(P, cs * p.BN, min((cs + 1) * p.BN, R), qx, qy, qz, tid, d, j);
