@@ -72,6 +72,35 @@ Zygote.@adjoint function Flux3D._chamfer_distance(A::CuArray{Float32,3}, B::CuAr
     return CUDA.@allowscalar(res[1]), back
 end
 
+# ---- chamfer_distance on host Arrays (src/metrics/pcloud.jl:28-37 called with `Array`s) -----------------------
+# One C call: the sweep grid pulls the (page-locked) arrays over PCIe itself and stores the loss into mapped host memory.
+const _pipe = Ref{Ptr{Cvoid}}(C_NULL)
+function pipe_handle()
+    if _pipe[] == C_NULL
+        check(ccall((:f3d_chamfer_pipe_create, LIB), Int32, (Int32, Ptr{Ptr{Cvoid}}), 0, _pipe))
+    end
+    return _pipe[]
+end
+
+function Flux3D.chamfer_distance(A::Array{Float32,3}, B::Array{Float32,3}; w1::Number = 1.0, w2::Number = 1.0)
+    (_, N, Bn) = size(A); M = size(B, 2)
+    size(B, 3) == Bn || error("batch sizes differ: $Bn vs $(size(B, 3))")
+    # page-lock once per array (no-op if already pinned): lets the device read the arrays in place.  Pageable arrays also
+    # work — the library then copies them with cudaMemcpyAsync first.
+    CUDA.pin(A); CUDA.pin(B)
+    nbytes = ccall((:f3d_chamfer_pipe_workspace_bytes, LIB), Csize_t, (Int32, Int32, Int32), Bn, N, M)
+    ws = workspace((:chamfer_pipe, Bn, N, M), nbytes)
+    out = Ref{Float32}(0f0)
+    GC.@preserve A B begin
+        check(ccall((:f3d_chamfer_pipe_run, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int32, Int32, Int32, Float32, Float32, Int32, Ptr{Float32}, Ptr{Float32},
+             Ptr{Cvoid}, Csize_t, Int32, Ptr{Cvoid}),
+            pipe_handle(), pointer(A), pointer(B), Bn, N, M, Float32(w1), Float32(w2), 0, C_NULL, out,
+            devptr(ws), length(ws), 0, cur_stream()))
+    end
+    return out[]   # a host Float32, like the reference on Arrays
+end
+
 # _nearest_neighbors(::CuArray, ::CuArray) — src/metrics/pcloud.jl:72-86: CartesianIndex matrices (N,B),(M,B)
 function Flux3D._nearest_neighbors(x::CuArray{Float32,3}, y::CuArray{Float32,3})
     _, nnx, nny = chamfer_fwd(x, y, 1f0, 1f0)

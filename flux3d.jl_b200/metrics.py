@@ -54,6 +54,15 @@ def _is_host(x) -> bool:
     return not (isinstance(x, torch.Tensor) and x.is_cuda)
 
 
+def _host_f32(x) -> torch.Tensor:
+    if isinstance(x, torch.Tensor) and x.dtype == torch.float32 and not x.is_cuda and x.is_contiguous():
+        return x  # the common case: no conversion, no copy
+    return as_f32_tensor(x)
+
+
+_host_plans: dict = {}  # (device index, stream, uploaders, B, N, M) -> (pipe handle, workspace, its address, its size)
+
+
 def chamfer_forward_host(A, B, w1: float = 1.0, w2: float = 1.0, *, batch_total: int = 0, uploaders: int = 0,
                          flags: int = FLAG_NONE, device="cuda", to_host: bool = False) -> torch.Tensor:
     """One call of f3d_chamfer_pipe_run: HOST arrays A (B,N,3), B (B,M,3) → the loss.  With page-locked inputs the grid
@@ -62,8 +71,8 @@ def chamfer_forward_host(A, B, w1: float = 1.0, w2: float = 1.0, *, batch_total:
     ``to_host=True``: a 0-dim CPU tensor — the grid stores the loss into mapped host memory and the call returns when
     it has landed (no D2H copy)."""
     L = _lib.lib()
-    A = as_f32_tensor(A)
-    B = as_f32_tensor(B)
+    A = _host_f32(A)
+    B = _host_f32(B)
     if A.is_cuda or B.is_cuda:
         raise ValueError("chamfer_forward_host takes host arrays; use chamfer_forward_raw for device tensors")
     if A.dim() != 3 or B.dim() != 3 or A.shape[2] != 3 or B.shape[2] != 3:
@@ -71,33 +80,43 @@ def chamfer_forward_host(A, B, w1: float = 1.0, w2: float = 1.0, *, batch_total:
     if A.shape[0] != B.shape[0]:
         raise ValueError(f"batch sizes differ: {A.shape[0]} vs {B.shape[0]}")
     Bn, N, M = A.shape[0], A.shape[1], B.shape[1]
-    dev = torch.device(device)
-    if dev.index is None:
-        dev = torch.device("cuda", torch.cuda.current_device())
+    dev = device if isinstance(device, torch.device) else torch.device(device)
+    cur = torch.cuda.current_device()
+    idx = cur if dev.index is None else dev.index
     uploaders = max(0, min(int(uploaders), 1024))
-    with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev)
-        key = (dev.index, uploaders)
-        h = _pipes.get(key)
-        if h is None:
-            h = _lib.C.c_void_p()
-            _lib.check(L.f3d_chamfer_pipe_create(uploaders, _lib.C.byref(h)))
-            _pipes[key] = h
-        ws = _workspace(("chamfer_pipe", Bn, N, M), L.f3d_chamfer_pipe_workspace_bytes(Bn, N, M), dev)
+    guard = torch.cuda.device(idx) if idx != cur else None  # the library works on the current device
+    if guard is not None:
+        guard.__enter__()
+    try:
+        stream = torch.cuda.current_stream(idx)
+        sptr = stream.cuda_stream
+        key = (idx, sptr, uploaders, Bn, N, M)
+        plan = _host_plans.get(key)
+        if plan is None:
+            h = _pipes.get((idx, uploaders))
+            if h is None:
+                h = _lib.C.c_void_p()
+                _lib.check(L.f3d_chamfer_pipe_create(uploaders, _lib.C.byref(h)))
+                _pipes[(idx, uploaders)] = h
+            ws = _workspace(("chamfer_pipe", Bn, N, M), L.f3d_chamfer_pipe_workspace_bytes(Bn, N, M), torch.device("cuda", idx))
+            plan = _host_plans[key] = (h, ws, ws.data_ptr(), ws.numel())
+        h, ws, wptr, wsize = plan
         if to_host:
             out = _lib.C.c_float()
-            _lib.check(L.f3d_chamfer_pipe_run(h, _lib.ptr(A), _lib.ptr(B), Bn, N, M, w1, w2, batch_total, None,
-                                              _lib.C.byref(out), _lib.ptr(ws), ws.numel(), flags,
-                                              _lib.C.c_void_p(stream.cuda_stream)))
+            _lib.check(L.f3d_chamfer_pipe_run(h, A.data_ptr(), B.data_ptr(), Bn, N, M, w1, w2, batch_total, None,
+                                              _lib.C.byref(out), wptr, wsize, flags, sptr))
             return torch.tensor(out.value, dtype=torch.float32)  # the call returned after the loss landed
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
-        _lib.check(L.f3d_chamfer_pipe_run(h, _lib.ptr(A), _lib.ptr(B), Bn, N, M, w1, w2, batch_total, _lib.ptr(loss),
-                                          None, _lib.ptr(ws), ws.numel(), flags, _lib.C.c_void_p(stream.cuda_stream)))
-        # the uploads read A and B asynchronously: keep them alive until the stream has consumed them
+        loss = torch.empty(1, dtype=torch.float32, device=torch.device("cuda", idx))
+        _lib.check(L.f3d_chamfer_pipe_run(h, A.data_ptr(), B.data_ptr(), Bn, N, M, w1, w2, batch_total, loss.data_ptr(),
+                                          None, wptr, wsize, flags, sptr))
+        # the grid reads A and B asynchronously: keep them alive until the stream has consumed them
         ev = torch.cuda.Event()
         ev.record(stream)
         _inflight[:] = [e for e in _inflight if not e[0].query()]
         _inflight.append((ev, A, B))
+    finally:
+        if guard is not None:
+            guard.__exit__(None, None, None)
     return loss
 
 
