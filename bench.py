@@ -60,44 +60,60 @@ def make_inputs(wl, rank):
     return A, B
 
 
+SAMPLER_SRC = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    print(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+          nv.nvmlDeviceGetCurrentClocksEventReasons(h), flush=True)
+    time.sleep(0.002)
+"""
+
+
 class ClockSampler:
-    """SM clock / power / throttle reasons sampled DURING the timed region (every ~5 ms, NVML in a thread —
-    the same counters as B200_PROFILING.md's nvidia-smi clocks line, fast enough for a millisecond-scale region)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (every ~2 ms, NVML — the same counters as
+    B200_PROFILING.md's nvidia-smi clocks line, fast enough for a millisecond-scale region).  The sampler is a separate
+    PROCESS: a thread in this interpreter takes the GIL at every wake-up and shows up in the wall-clock e2e number."""
 
     def __init__(self, gpu_index):
-        self.idx, self.samples, self._stop, self._thr, self.err = gpu_index, [], False, None, None
+        self.idx, self.proc, self.err = gpu_index, None, None
 
-    def _loop(self):
-        import pynvml as nv
+    def start(self):
         try:
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            while not self._stop:
-                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
-                                     nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
-                time.sleep(0.005)
+            self.proc = subprocess.Popen([sys.executable, "-c", SAMPLER_SRC, str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.PIPE, text=True)
+            self.first = self.proc.stdout.readline()  # "max <MHz>": the sampler is up before the timed region starts
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
 
-    def start(self):
-        import threading
-        self._thr = threading.Thread(target=self._loop, daemon=True)
-        self._thr.start()
-
     def stop(self):
-        self._stop = True
-        if self._thr is not None:
-            self._thr.join(timeout=5)
-        if not self.samples:
+        samples, max_mhz = [], None
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, errtxt = self.proc.communicate(timeout=5)
+            except Exception as e:  # pragma: no cover
+                out, errtxt = "", repr(e)
+            for line in [self.first] + out.splitlines():
+                f = line.split()
+                if len(f) == 2 and f[0] == "max":
+                    max_mhz = float(f[1])
+                elif len(f) == 3:
+                    samples.append((float(f[0]), float(f[1]), int(f[2])))
+            if not samples:
+                self.err = (errtxt or "").strip()[-200:]
+        if not samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"no samples ({self.err})"]}
         import pynvml as nv
         bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
-        reasons = sorted(n for n, b in bits.items() if any(r & b for _, _, r in self.samples))
-        sm = sorted(c for c, _, _ in self.samples)
-        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_min_mhz": float(sm[0]), "sm_max_mhz": float(self.max_mhz),
-                "power_w_max": max(p for _, p, _ in self.samples), "samples": len(sm), "reasons": reasons}
+        reasons = sorted(n for n, b in bits.items() if any(r & b for _, _, r in samples))
+        sm = sorted(c for c, _, _ in samples)
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_min_mhz": float(sm[0]), "sm_max_mhz": max_mhz,
+                "power_w_max": max(p for _, p, _ in samples), "samples": len(sm), "reasons": reasons}
 
 
 def kdtree_step(A, B, workers):

@@ -306,10 +306,13 @@ Plan make_plan(int B, int N, int M) {
     Plan pl;
     int cpw = (int)align_up((size_t)(M + kWarps - 1) / kWarps, kChunk);
     if (cpw > kMaxColsPerWarp) cpw = kMaxColsPerWarp;
+    pl.RB = (N + kTileRows - 1) / kTileRows;
+    // small problems: narrower column tiles until the grid fills the machine once (4 CTAs x 148 SMs) — wide tiles are
+    // ≈ 5 % faster per pair, but not if most SMs have nothing to do (B=2 N=M=1024: 27.7 → 20.8 µs at 64 columns per warp; 32 is too narrow: 26.8 µs)
+    while (cpw > 2 * kChunk && cpw % (2 * kChunk) == 0 && (long)((M + kWarps * cpw - 1) / (kWarps * cpw)) * pl.RB * B < 592) cpw /= 2;
     pl.cols_per_warp = cpw;
     pl.BN = kWarps * cpw;
     pl.CS = (M + pl.BN - 1) / pl.BN;
-    pl.RB = (N + kTileRows - 1) / kTileRows;
     pl.Npad = pl.RB * kTileRows;
     pl.Mpad = pl.CS * pl.BN;
     pl.nbA = (int)(((long)B * N + kFinThreads - 1) / kFinThreads);
@@ -378,6 +381,10 @@ struct FiltParams {
     int cols_per_warp, CS, RB, Npad, Mpad;
     float4* rowpart;   // [B][CS][Npad] {b1, b2, c1 (int bits), -}
     uint2* colpart;    // [B][RB][Mpad] {m (float bits, may be slightly negative), lane ballot}
+    // prepared operands (chamfer_prepare_kernel; null in upload mode, where every tile stages its own operands):
+    const float4* Ap;   // [B][Npad]    {a'x, a'y, a'z, |a'|²}, pads {0, 0, 0, kPadF}
+    const float4* Bxy;  // [B][Mpad/2]  column pairs {-2b'x0, -2b'x1, -2b'y0, -2b'y1}: a tile is one contiguous bulk copy
+    const float4* Bzn;  // [B][Mpad/2]  {-2b'z0, -2b'z1, |b'0|², |b'1|²}, pads {0, 0, kPadF, kPadF}
     float* maxna;      // [B][RB]  max |a'|² over the valid rows of the block
     float* maxnb;      // [B][CS]  max |b'|² over the valid columns of the tile
     float* centre;     // [B][4]   the centre used for this batch element (finalize recomputes |a'|², |b'|² with it)
@@ -450,6 +457,91 @@ __device__ void upload_clouds(const FiltParams& p, const int u, const int tid) {
     }
 }
 
+// ---- TMA bulk copy (cp.async.bulk, completion on an mbarrier) -----------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// ---- prepare: centre every cloud, pre-scale, take the norms — ONCE per call instead of once per tile ----------------
+// Without it each of the B*CS*RB tiles re-derives its 1024 columns and 256 rows from the raw points (54 scalar loads per
+// thread, a shuffle reduction for the centre, the transform, two barriers): ≈ 25 % of a tile's life at cfg2, repeated RB = 16
+// times per column tile.  Here one thread per point writes the operands in exactly the layout the sweep keeps in shared
+// memory / registers, so a tile's prologue is two TMA bulk copies (8 KB each) and eight 16-byte loads per lane.
+// grid (blocks of 256 points, B, 2): z = 0 rows of A, z = 1 columns of B.  Same arithmetic, bit for bit, as the in-tile
+// staging of upload mode and as the finalize's recomputation of |q'|².
+constexpr int kPrepThreads = 256;
+#ifndef F3D_PREP_MIN_RB
+#define F3D_PREP_MIN_RB 32
+#endif
+constexpr int kPrepMinRowBlocks = F3D_PREP_MIN_RB;  // use the prepare grid from this many 256-row blocks per cloud on
+__global__ void __launch_bounds__(kPrepThreads) chamfer_prepare_kernel(FiltParams p, float4* __restrict__ Ap, float4* __restrict__ Bxy,
+                                                                       float4* __restrict__ Bzn) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the sweep's launch overlaps this grid; it waits before reading
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.y;
+    const bool isA = blockIdx.z == 0;
+    const int BN = kWarps * p.cols_per_warp;
+    if (isA ? (int)blockIdx.x * kPrepThreads >= p.Npad : (int)blockIdx.x * kPrepThreads >= p.Mpad) return;
+    const float* gA = p.A + (size_t)b * p.N * 3;
+    const float* gB = p.Bp + (size_t)b * p.M * 3;
+    // the centre of the batch element: the mean of 32 + 32 strided sample points (any point works: the certificate
+    // uses the norms actually obtained); every warp computes it with the same operations => same bits everywhere
+    const int ia = (int)(((long)lane * p.N) >> 5), ib = (int)(((long)lane * p.M) >> 5);
+    float cx = __ldg(gA + 3 * ia) + __ldg(gB + 3 * ib);
+    float cy = __ldg(gA + 3 * ia + 1) + __ldg(gB + 3 * ib + 1);
+    float cz = __ldg(gA + 3 * ia + 2) + __ldg(gB + 3 * ib + 2);
+    const int i = blockIdx.x * kPrepThreads + tid;  // point index (row of A / column of B)
+    const int n = isA ? p.N : p.M;
+    const float* src = (isA ? gA : gB) + 3 * (size_t)min(i, n - 1);
+    const float rx = __ldg(src), ry = __ldg(src + 1), rz = __ldg(src + 2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cx += __shfl_xor_sync(0xffffffffu, cx, o);
+        cy += __shfl_xor_sync(0xffffffffu, cy, o);
+        cz += __shfl_xor_sync(0xffffffffu, cz, o);
+    }
+    cx *= (1.0f / 64.0f); cy *= (1.0f / 64.0f); cz *= (1.0f / 64.0f);
+    if (isA && blockIdx.x == 0 && tid == 0) { p.centre[4 * b] = cx; p.centre[4 * b + 1] = cy; p.centre[4 * b + 2] = cz; }
+    float x = 0.f, y = 0.f, z = 0.f, nrm = kPadF, mx = 0.f;
+    if (i < n) {
+        x = rx - cx; y = ry - cy; z = rz - cz;
+        nrm = fmaf(z, z, fmaf(y, y, x * x));
+        mx = nrm;
+    }
+    mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));  // norms are >= 0
+    if (isA) {
+        if (i < p.Npad) Ap[(size_t)b * p.Npad + i] = make_float4(x, y, z, nrm);
+        // 32 consecutive rows lie in one 256-row block
+        if (lane == 0 && i < p.N) atomicMax(reinterpret_cast<unsigned*>(p.maxna) + (size_t)b * p.RB + i / kTileRows, __float_as_uint(mx));
+    } else {
+        // columns travel in pairs: the even lane writes {-2x0, -2x1, -2y0, -2y1}, the odd lane {-2z0, -2z1, n0, n1}
+        const float ox = __shfl_xor_sync(0xffffffffu, x, 1), oy = __shfl_xor_sync(0xffffffffu, y, 1);
+        const float oz = __shfl_xor_sync(0xffffffffu, z, 1), on = __shfl_xor_sync(0xffffffffu, nrm, 1);
+        if (i < p.Mpad) {
+            const size_t pp = ((size_t)b * p.Mpad + i) >> 1;
+            if ((lane & 1) == 0) Bxy[pp] = make_float4(-2.0f * x, -2.0f * ox, -2.0f * y, -2.0f * oy);
+            else Bzn[pp] = make_float4(-2.0f * oz, -2.0f * z, on, nrm);
+        }
+        // 32 consecutive columns lie in one column tile (BN is a multiple of 128)
+        if (lane == 0 && i < p.M) atomicMax(reinterpret_cast<unsigned*>(p.maxnb) + (size_t)b * p.CS + i / BN, __float_as_uint(mx));
+    }
+}
+
 #ifndef F3D_FILT_MINB
 #define F3D_FILT_MINB 4
 #endif
@@ -507,89 +599,115 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
     const float* gA = p.A + (size_t)b * p.N * 3;
     const float* gB = p.Bp + (size_t)b * p.M * 3;
 
-    // ---- prologue: issue EVERY global load first (centre samples, this thread's column pairs, this lane's rows),
-    // so the CTA pays one memory latency instead of one per dependent step -------------------------------------
-    constexpr int kMaxPairsPerThread = kMaxColsPerWarp * kWarps / 2 / kThreads;  // 4
-    const int ia = (int)(((long)lane * p.N) >> 5), ib = (int)(((long)lane * p.M) >> 5);
-    const float sx = __ldg(gA + 3 * ia) + __ldg(gB + 3 * ib);
-    const float sy = __ldg(gA + 3 * ia + 1) + __ldg(gB + 3 * ib + 1);
-    const float sz = __ldg(gA + 3 * ia + 2) + __ldg(gB + 3 * ib + 2);
-    float rawc[kMaxPairsPerThread][6];
-#pragma unroll
-    for (int k = 0; k < kMaxPairsPerThread; ++k) {
-        const int pp = tid + k * kThreads;
-        const int j = col0 + 2 * pp;
-#pragma unroll
-        for (int e = 0; e < 6; ++e) rawc[k][e] = (pp < BN / 2 && j + e / 3 < p.M) ? __ldg(gB + 3 * (size_t)j + e) : 0.0f;
-    }
     float ax[kRowsPerLane], ay[kRowsPerLane], az[kRowsPerLane], na[kRowsPerLane];
+    float maxna, maxnb;
+    if (p.Ap) {
+        // ---- prologue, prepared operands: the column tile arrives by TMA (two bulk copies onto one mbarrier), this
+        // lane's 8 rows by eight 16-byte loads — one memory latency, no arithmetic, no barrier besides the mbarrier ----
+        __shared__ __align__(8) unsigned long long s_bar;
+        const unsigned bar = smem_u32(&s_bar);
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // the prepare grid has completed and its writes are visible
+        if (tid == 0) {
+            const unsigned bytes = (unsigned)(BN / 2) * (unsigned)sizeof(float4);
+            mbar_expect_tx(bar, 2 * bytes);
+            tma_bulk_g2s(smem_u32(s_xy), p.Bxy + (((size_t)b * p.Mpad + col0) >> 1), bytes, bar);
+            tma_bulk_g2s(smem_u32(s_zn), p.Bzn + (((size_t)b * p.Mpad + col0) >> 1), bytes, bar);
+        }
+        const float4* gAp = p.Ap + (size_t)b * p.Npad + row0 + lane * kRowsPerLane;
 #pragma unroll
-    for (int r = 0; r < kRowsPerLane; ++r) {
-        const int i = row0 + lane * kRowsPerLane + r;
-        const bool ok = i < p.N;
-        ax[r] = ok ? __ldg(gA + 3 * (size_t)i) : 0.0f;
-        ay[r] = ok ? __ldg(gA + 3 * (size_t)i + 1) : 0.0f;
-        az[r] = ok ? __ldg(gA + 3 * (size_t)i + 2) : 0.0f;
-    }
-    // the centre of the batch element: every warp computes it redundantly (same operations => same bits)
-    float cx = sx, cy = sy, cz = sz;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        cx += __shfl_xor_sync(0xffffffffu, cx, o);
-        cy += __shfl_xor_sync(0xffffffffu, cy, o);
-        cz += __shfl_xor_sync(0xffffffffu, cz, o);
-    }
-    cx *= (1.0f / 64.0f); cy *= (1.0f / 64.0f); cz *= (1.0f / 64.0f);
-    // every tile publishes the (identical) centre and its norm maxima: a finalize block may only rely on the tiles
-    // of ITS row block / column split having finished
-    if (tid == 0) { p.centre[4 * b] = cx; p.centre[4 * b + 1] = cy; p.centre[4 * b + 2] = cz; }
-    __syncthreads();  // s_maxnb = 0 visible
-
-    // ---- stage the column tile: centred, pre-scaled by -2, with |b'|² -----------------------------------
-    {
-        float mynb = 0.0f;
+        for (int r = 0; r < kRowsPerLane; ++r) {
+            const float4 v = __ldg(gAp + r);
+            ax[r] = v.x; ay[r] = v.y; az[r] = v.z; na[r] = v.w;
+        }
+        maxna = __ldg(p.maxna + (size_t)b * p.RB + rb);
+        maxnb = __ldg(p.maxnb + (size_t)b * p.CS + cs);
+        while (!mbar_try_wait(bar, 0)) {}
+    } else {
+        // ---- prologue: issue EVERY global load first (centre samples, this thread's column pairs, this lane's rows),
+        // so the CTA pays one memory latency instead of one per dependent step -------------------------------------
+        constexpr int kMaxPairsPerThread = kMaxColsPerWarp * kWarps / 2 / kThreads;  // 4
+        const int ia = (int)(((long)lane * p.N) >> 5), ib = (int)(((long)lane * p.M) >> 5);
+        const float sx = __ldg(gA + 3 * ia) + __ldg(gB + 3 * ib);
+        const float sy = __ldg(gA + 3 * ia + 1) + __ldg(gB + 3 * ib + 1);
+        const float sz = __ldg(gA + 3 * ia + 2) + __ldg(gB + 3 * ib + 2);
+        float rawc[kMaxPairsPerThread][6];
 #pragma unroll
         for (int k = 0; k < kMaxPairsPerThread; ++k) {
             const int pp = tid + k * kThreads;
-            if (pp < BN / 2) {
-                const int j = col0 + 2 * pp;
-                float x0 = 0.f, y0 = 0.f, z0 = 0.f, n0 = kPadF, x1 = 0.f, y1 = 0.f, z1 = 0.f, n1 = kPadF;
-                if (j < p.M) {
-                    x0 = rawc[k][0] - cx; y0 = rawc[k][1] - cy; z0 = rawc[k][2] - cz;
-                    n0 = fmaf(z0, z0, fmaf(y0, y0, x0 * x0));
-                    mynb = fmaxf(mynb, n0);
+            const int j = col0 + 2 * pp;
+#pragma unroll
+            for (int e = 0; e < 6; ++e) rawc[k][e] = (pp < BN / 2 && j + e / 3 < p.M) ? __ldg(gB + 3 * (size_t)j + e) : 0.0f;
+        }
+#pragma unroll
+        for (int r = 0; r < kRowsPerLane; ++r) {
+            const int i = row0 + lane * kRowsPerLane + r;
+            const bool ok = i < p.N;
+            ax[r] = ok ? __ldg(gA + 3 * (size_t)i) : 0.0f;
+            ay[r] = ok ? __ldg(gA + 3 * (size_t)i + 1) : 0.0f;
+            az[r] = ok ? __ldg(gA + 3 * (size_t)i + 2) : 0.0f;
+        }
+        // the centre of the batch element: every warp computes it redundantly (same operations => same bits)
+        float cx = sx, cy = sy, cz = sz;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cx += __shfl_xor_sync(0xffffffffu, cx, o);
+            cy += __shfl_xor_sync(0xffffffffu, cy, o);
+            cz += __shfl_xor_sync(0xffffffffu, cz, o);
+        }
+        cx *= (1.0f / 64.0f); cy *= (1.0f / 64.0f); cz *= (1.0f / 64.0f);
+        // every tile publishes the (identical) centre and its norm maxima: a finalize block may only rely on the tiles
+        // of ITS row block / column split having finished
+        if (tid == 0) { p.centre[4 * b] = cx; p.centre[4 * b + 1] = cy; p.centre[4 * b + 2] = cz; }
+        __syncthreads();  // s_maxnb = 0 visible
+
+        // ---- stage the column tile: centred, pre-scaled by -2, with |b'|² -----------------------------------
+        {
+            float mynb = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kMaxPairsPerThread; ++k) {
+                const int pp = tid + k * kThreads;
+                if (pp < BN / 2) {
+                    const int j = col0 + 2 * pp;
+                    float x0 = 0.f, y0 = 0.f, z0 = 0.f, n0 = kPadF, x1 = 0.f, y1 = 0.f, z1 = 0.f, n1 = kPadF;
+                    if (j < p.M) {
+                        x0 = rawc[k][0] - cx; y0 = rawc[k][1] - cy; z0 = rawc[k][2] - cz;
+                        n0 = fmaf(z0, z0, fmaf(y0, y0, x0 * x0));
+                        mynb = fmaxf(mynb, n0);
+                    }
+                    if (j + 1 < p.M) {
+                        x1 = rawc[k][3] - cx; y1 = rawc[k][4] - cy; z1 = rawc[k][5] - cz;
+                        n1 = fmaf(z1, z1, fmaf(y1, y1, x1 * x1));
+                        mynb = fmaxf(mynb, n1);
+                    }
+                    s_xy[pp] = make_float4(-2.0f * x0, -2.0f * x1, -2.0f * y0, -2.0f * y1);
+                    s_zn[pp] = make_float4(-2.0f * z0, -2.0f * z1, n0, n1);
                 }
-                if (j + 1 < p.M) {
-                    x1 = rawc[k][3] - cx; y1 = rawc[k][4] - cy; z1 = rawc[k][5] - cz;
-                    n1 = fmaf(z1, z1, fmaf(y1, y1, x1 * x1));
-                    mynb = fmaxf(mynb, n1);
-                }
-                s_xy[pp] = make_float4(-2.0f * x0, -2.0f * x1, -2.0f * y0, -2.0f * y1);
-                s_zn[pp] = make_float4(-2.0f * z0, -2.0f * z1, n0, n1);
+            }
+            mynb = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mynb)));  // norms are >= 0
+            if (lane == 0) atomicMax(&s_maxnb, __float_as_uint(mynb));
+        }
+        // ---- this lane's 8 rows: centred coordinates and |a'|² ------------------------------------------------
+        float myna = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kRowsPerLane; ++r) {
+            const int i = row0 + lane * kRowsPerLane + r;
+            if (i < p.N) {
+                ax[r] -= cx; ay[r] -= cy; az[r] -= cz;
+                na[r] = fmaf(az[r], az[r], fmaf(ay[r], ay[r], ax[r] * ax[r]));
+                myna = fmaxf(myna, na[r]);
+            } else {
+                ax[r] = 0.f; ay[r] = 0.f; az[r] = 0.f; na[r] = kPadF;
             }
         }
-        mynb = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mynb)));  // norms are >= 0
-        if (lane == 0) atomicMax(&s_maxnb, __float_as_uint(mynb));
-    }
-    // ---- this lane's 8 rows: centred coordinates and |a'|² ------------------------------------------------
-    float myna = 0.0f;
-#pragma unroll
-    for (int r = 0; r < kRowsPerLane; ++r) {
-        const int i = row0 + lane * kRowsPerLane + r;
-        if (i < p.N) {
-            ax[r] -= cx; ay[r] -= cy; az[r] -= cz;
-            na[r] = fmaf(az[r], az[r], fmaf(ay[r], ay[r], ax[r] * ax[r]));
-            myna = fmaxf(myna, na[r]);
-        } else {
-            ax[r] = 0.f; ay[r] = 0.f; az[r] = 0.f; na[r] = kPadF;
+        maxna = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(myna)));
+        __syncthreads();
+        maxnb = __uint_as_float(s_maxnb);
+        if (tid == 0) {
+            p.maxnb[(size_t)b * p.CS + cs] = maxnb;
+            p.maxna[(size_t)b * p.RB + rb] = maxna;
         }
-    }
-    const float maxna = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(myna)));
-    __syncthreads();
-    const float maxnb = __uint_as_float(s_maxnb);
-    if (tid == 0) {
-        p.maxnb[(size_t)b * p.CS + cs] = maxnb;
-        p.maxna[(size_t)b * p.RB + rb] = maxna;
     }
     const float wt = kBallotAbs * (maxna + maxnb);
 
@@ -1067,7 +1185,8 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
 
 struct FiltPlan {
     int cols_per_warp, BN, CS, RB, Npad, Mpad, nbA, nbB;
-    size_t off_rowpart, off_colpart, off_maxna, off_maxnb, off_centre, off_partial, off_counter, counter_bytes, total;
+    size_t off_rowpart, off_colpart, off_Ap, off_Bxy, off_Bzn, off_maxna, off_maxnb, off_centre, off_partial, off_counter, counter_bytes,
+        zero_from, zero_bytes, total;
 };
 
 FiltPlan make_filt_plan(int B, int N, int M) {
@@ -1085,6 +1204,10 @@ FiltPlan make_filt_plan(int B, int N, int M) {
     size_t o = 0;
     pl.off_rowpart = o; o = align_up(o + sizeof(float4) * (size_t)B * pl.CS * pl.Npad, 256);
     pl.off_colpart = o; o = align_up(o + sizeof(uint2) * (size_t)B * pl.RB * pl.Mpad, 256);
+    pl.off_Ap = o;      o = align_up(o + sizeof(float4) * (size_t)B * pl.Npad, 256);
+    pl.off_Bxy = o;     o = align_up(o + sizeof(float4) * (size_t)B * (pl.Mpad / 2), 256);
+    pl.off_Bzn = o;     o = align_up(o + sizeof(float4) * (size_t)B * (pl.Mpad / 2), 256);
+    pl.zero_from = o;   // everything from here on is zeroed by ONE memset per call: norm maxima (atomicMax), counters, flags
     pl.off_maxna = o;   o = align_up(o + sizeof(float) * (size_t)B * pl.RB, 256);
     pl.off_maxnb = o;   o = align_up(o + sizeof(float) * (size_t)B * pl.CS, 256);
     pl.off_centre = o;  o = align_up(o + sizeof(float) * 4 * (size_t)B, 256);
@@ -1093,6 +1216,7 @@ FiltPlan make_filt_plan(int B, int N, int M) {
     // rowdone [B][RB] | coldone [B][CS] | arrived [B] (upload mode)  — one memset zeroes all of it per call
     pl.counter_bytes = sizeof(int) * kHdrInts + sizeof(int) * ((size_t)B * pl.RB + (size_t)B * pl.CS + (size_t)B);
     pl.off_counter = o; o = align_up(o + pl.counter_bytes, 256);
+    pl.zero_bytes = o - pl.zero_from;
     pl.total = o;
     return pl;
 }
@@ -1155,7 +1279,8 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
         sp.counter = reinterpret_cast<unsigned*>(w + fl.off_counter);
         sp.rowdone = reinterpret_cast<int*>(w + fl.off_counter) + kHdrInts;
         sp.coldone = sp.rowdone + (size_t)B * fl.RB;
-        F3D_CUDA(cudaMemsetAsync(w + fl.off_counter, 0, fl.counter_bytes, stream));
+        F3D_CUDA(cudaMemsetAsync(w + fl.zero_from, 0, fl.zero_bytes, stream));
+        sp.Ap = nullptr; sp.Bxy = nullptr; sp.Bzn = nullptr;
         sp.up.hA = nullptr; sp.up.hB = nullptr; sp.up.dA = nullptr; sp.up.dB = nullptr; sp.up.U = 0;
         sp.up.arrived = reinterpret_cast<unsigned*>(sp.coldone + (size_t)B * fl.CS);
         sp.up.timeout = sp.counter + kHdrTimeout;
@@ -1178,8 +1303,34 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
             }
         }
         sp.B = B;
-        if (sp.up.U) chamfer_filter_sweep_kernel<<<dim3((unsigned)fl.CS * fl.RB * B + sp.up.U), kThreads, smem, stream>>>(sp);
-        else chamfer_filter_sweep_kernel<<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
+        if (sp.up.U) {
+            // upload mode: the operands do not exist yet — every tile stages its own once its batch element has landed
+            chamfer_filter_sweep_kernel<<<dim3((unsigned)fl.CS * fl.RB * B + sp.up.U), kThreads, smem, stream>>>(sp);
+        } else if (fl.RB < kPrepMinRowBlocks) {
+            // few row blocks: re-deriving a column tile RB times costs less than one more grid in front of the sweep
+            // (cfg2, RB = 16: 158.7 µs against 161.1 µs with the prepare grid — profiles/r01g)
+            chamfer_filter_sweep_kernel<<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
+        } else {
+#ifndef F3D_EXP_NOPREP
+            // many row blocks: prepare the operands once, then the sweep — launched programmatically, it waits
+            // (griddepcontrol.wait) only where it first reads them (B=16 N=M=10000: 430 → 419 µs)
+            float4* Ap = reinterpret_cast<float4*>(w + fl.off_Ap);
+            float4* Bxy = reinterpret_cast<float4*>(w + fl.off_Bxy);
+            float4* Bzn = reinterpret_cast<float4*>(w + fl.off_Bzn);
+            chamfer_prepare_kernel<<<dim3((std::max(fl.Npad, fl.Mpad) + kPrepThreads - 1) / kPrepThreads, B, 2), kPrepThreads, 0, stream>>>(sp, Ap, Bxy, Bzn);
+            F3D_CHECK_LAUNCH("chamfer_prepare_kernel");
+            sp.Ap = Ap; sp.Bxy = Bxy; sp.Bzn = Bzn;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(fl.CS, fl.RB, B); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_filter_sweep_kernel, sp));
+#else
+            chamfer_filter_sweep_kernel<<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
+#endif
+        }
         F3D_CHECK_LAUNCH("chamfer_filter_sweep_kernel");
         if (flags & F3D_FLAG_SWEEP_ONLY) return F3D_OK;
         FiltFinalizeParams fp;

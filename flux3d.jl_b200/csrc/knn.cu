@@ -29,7 +29,13 @@ namespace {
 
 constexpr int kWarpsK = 8;
 constexpr int kThreadsK = 32 * kWarpsK;
-constexpr int kQW = 2;                    // queries per warp
+#ifndef F3D_KNN_QW
+#define F3D_KNN_QW 2
+#endif
+#ifndef F3D_KNN_MINB
+#define F3D_KNN_MINB 2
+#endif
+constexpr int kQW = F3D_KNN_QW;           // queries per warp
 constexpr int kQPC = kWarpsK * kQW;       // queries per CTA (16)
 constexpr int kCPL = 4;                   // candidates per lane per tile
 constexpr int kTileC = 32 * kCPL;         // candidates per staged tile (128)
@@ -124,7 +130,7 @@ __device__ __forceinline__ void bitonic_sort64(T& v0, T& v1, int lane) {
 }
 
 template <int kSlots>
-__global__ void __launch_bounds__(kThreadsK, 2) knn_graph_kernel(KnnParams p) {
+__global__ void __launch_bounds__(kThreadsK, F3D_KNN_MINB) knn_graph_kernel(KnnParams p) {
     extern __shared__ __align__(16) float smem_k[];
     const int stride = p.Fp + 4;           // floats per staged row
     float* s_q = smem_k;                   // [kQPC][stride]

@@ -51,6 +51,18 @@ def test_parity_random(f3d, oracle, B, N, M, seed):
     _check(f3d, oracle, A, Bc)
 
 
+def test_many_row_blocks_prepared_operands(f3d, oracle):
+    """Clouds with >= 32 row blocks take the prepare grid + TMA bulk-copy prologue (chamfer_prepare_kernel): same bits as
+    the oracle, ragged N and M (pads inside the last row block / column tile), N != M."""
+    rng = np.random.default_rng(91)
+    A = rng.random((1, 9001, 3), dtype=np.float32)
+    B = rng.random((1, 8203, 3), dtype=np.float32)
+    _check(f3d, oracle, A, B)
+    A2 = (rng.standard_normal((2, 8192, 3)) * 3.0).astype(np.float32)
+    B2 = (rng.standard_normal((2, 1500, 3)) * 3.0 + 1.0).astype(np.float32)
+    _check(f3d, oracle, A2, B2, w1=0.3, w2=2.0)
+
+
 def test_cfg1_known_value(f3d, oracle):
     """cfg1 golden: loss 0.0074543296 (seeds 101/102) — oracle and kernel both."""
     A = np.random.default_rng(101).random((2, 1024, 3), dtype=np.float32)
