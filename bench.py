@@ -179,10 +179,28 @@ def run_b200(args):
     out = (torch.empty(3, dtype=torch.float32, device=dev), None, None)
     stream = torch.cuda.current_stream(dev)
 
+    # N > 1: the single exchange of the path (the sum of the shard losses) is fused into the finalize kernel — peer
+    # mailboxes mapped over NVLink (f3d_comm_enable_p2p); if peer mapping is not possible, one NCCL all-reduce instead
+    comm, exchange = None, "none"
+    if multi:
+        exchange = "nccl_allreduce"
+        try:
+            if os.environ.get("F3D_BENCH_EXCHANGE", "fused") == "nccl":  # A/B aid
+                raise RuntimeError("F3D_BENCH_EXCHANGE=nccl")
+            comm = f3d.Communicator(rank, world, dev).enable_p2p()
+            exchange = "fused_peer_mailboxes"
+        except Exception as e:  # pragma: no cover
+            comm = None
+            print(f"[rank {rank}] peer mailboxes unavailable ({e}); using NCCL all-reduce", file=sys.stderr)
+        ok = torch.tensor([1.0 if comm is not None else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks take the same path
+        if ok.item() == 0.0:
+            comm, exchange = None, "nccl_allreduce"
+
     def step(flags=0):
-        loss, _, _, _ = f3d.chamfer_forward_raw(dA, dB, 1.0, 1.0, batch_total=B_total, want_indices=False, flags=flags, out=out)
         if multi and not flags:
-            dist.all_reduce(loss)  # the single exchange of the path: 4 bytes over NCCL/NVLink
+            return f3d.chamfer_distance_sharded(dA, dB, B_total, comm=comm).reshape(1)
+        loss, _, _, _ = f3d.chamfer_forward_raw(dA, dB, 1.0, 1.0, batch_total=B_total, want_indices=False, flags=flags, out=out)
         return loss
 
     def barrier():
@@ -223,7 +241,7 @@ def run_b200(args):
         with torch.no_grad():
             # host arrays in: f3d_chamfer_pipe_run uploads chunk k+1 while chunk k is swept (one C call per step)
             if multi:
-                return float(f3d.chamfer_distance_sharded(pA, pB, B_total).item())
+                return float(f3d.chamfer_distance_sharded(pA, pB, B_total, comm=comm, to_host=comm is not None).item())
             return float(f3d.chamfer_distance(pA, pB).item())
     for _ in range(3):
         e2e_step()
@@ -256,7 +274,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"chamfer_distance B={Bn}/GPU (global {B_total}) N={N} M={M} Float32 ({args.workload}), "
-                                   "U[0,1)^3, forward incl. loss reduction" + (" + 1 NCCL all-reduce" if multi else ""),
+                                   "U[0,1)^3, forward incl. loss reduction" + (f" + cross-rank loss sum ({exchange})" if multi else ""),
                        "parallelism": f"batch-sharded x{world}", "l2": "flushed between steps (256 MiB memset outside the event pairs)",
                        "arithmetic": "results bit-identical to the direct form ((dx*dx)+(dy*dy))+(dz*dz) without FMA contraction "
                                      "(expanded-form FP32 filter, every reported distance/index re-evaluated exactly)"},
@@ -300,6 +318,8 @@ def run_b200(args):
                                                                      "cores": O.num_threads()}}
         print(json.dumps(line))
     if multi:
+        if comm is not None:
+            comm.close()
         dist.destroy_process_group()
 
 

@@ -23,7 +23,7 @@ SIGNATURES = {
     "f3d_chamfer_pipe_create": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
     "f3d_chamfer_pipe_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "f3d_chamfer_pipe_run": (C.c_int32, [_vp, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
-                                         C.c_int32, _f32p, _f32p, _vp, C.c_size_t, C.c_int32, _vp]),
+                                         C.c_int32, _f32p, _f32p, _vp, C.c_size_t, C.c_int32, _vp, _vp]),
     "f3d_chamfer_pipe_destroy": (C.c_int32, [_vp]),
     "f3d_chamfer_bwd": (C.c_int32, [_f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
                                     C.c_int32, _i32p, _i32p, _f32p, _f32p, _f32p, _vp]),
@@ -49,6 +49,9 @@ SIGNATURES = {
     "f3d_comm_unique_id_host": (C.c_int32, [_vp]),
     "f3d_comm_init": (C.c_int32, [C.c_int32, C.c_int32, _vp, C.POINTER(C.c_void_p)]),
     "f3d_allreduce_sum_f32": (C.c_int32, [_vp, _f32p, C.c_int32, _vp]),
+    "f3d_comm_enable_p2p": (C.c_int32, [_vp, _vp]),
+    "f3d_chamfer_fwd_allreduce": (C.c_int32, [_vp, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                                              C.c_int32, _f32p, _i32p, _i32p, _vp, C.c_size_t, C.c_int32, _vp]),
     "f3d_comm_destroy": (C.c_int32, [_vp]),
 }
 

@@ -835,6 +835,7 @@ struct FiltFinalizeParams {
     float* loss;
     float* terms;
     const unsigned* upload_timeout;  // null unless the sweep ran in upload mode
+    ChamferPeerSum peer;             // nranks > 1: sum the loss over the ranks through peer memory (NVLink), see below
 };
 
 
@@ -1179,7 +1180,45 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
         if (p.terms) { p.terms[0] = dAB; p.terms[1] = dBA; }
         float l = __fadd_rn(__fmul_rn(p.w1, dAB), __fmul_rn(p.w2, dBA));          // pcloud.jl:50
         if (p.upload_timeout && __ldcg(p.upload_timeout) != 0u) l = __int_as_float(0x7fc00000);  // an upload never landed
-        p.loss[0] = l;
+        if (p.peer.nranks <= 1) p.loss[0] = l;
+        s_a[0] = (double)l;
+    }
+    if (p.peer.nranks <= 1) return;
+
+    // ---- the one exchange of the sharded path, fused into this kernel: every rank stores its shard's loss (already
+    // divided by the GLOBAL N*B_total / M*B_total) into a mailbox slot on EVERY peer over NVLink — one 8-byte word
+    // {step number, float bits}, so value and flag arrive together — then waits for the R words in its own mailbox and
+    // adds them in rank order: the same bits on every rank, no NCCL kernel, no launch, no second pass over the data.
+    // Slots are double-buffered by the parity of the step number: a rank can only be two steps ahead of a peer after
+    // that peer has sent its word for the step in between, i.e. after it finished reading the older one.
+    __shared__ float s_v[kMaxPeerRanks];
+    __syncthreads();
+    if (tid < p.peer.nranks) {
+        const float mine_l = (float)s_a[0];
+        const unsigned long long word = ((unsigned long long)p.peer.seq << 32) | (unsigned long long)__float_as_uint(mine_l);
+        const int base = (int)(p.peer.seq & 1u) * p.peer.nranks;
+        unsigned long long* dst = p.peer.mailboxes[tid] + base + p.peer.rank;  // my slot in rank tid's mailbox
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+        const unsigned long long* src = p.peer.mailboxes[p.peer.rank] + base + tid;  // rank tid's slot in my mailbox
+        unsigned long long got = 0, t0 = 0;
+        float v = __int_as_float(0x7fc00000);
+        for (unsigned spins = 0;; ++spins) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
+            if ((unsigned)(got >> 32) == p.peer.seq) { v = __uint_as_float((unsigned)got); break; }
+            if ((spins & 4095u) == 4095u) {  // a peer that never sends (crashed rank) must not hang this device: NaN after 2 s
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 2000000000ull) break;
+            }
+        }
+        s_v[tid] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float sum = 0.0f;
+        for (int r = 0; r < p.peer.nranks; ++r) sum = __fadd_rn(sum, s_v[r]);
+        p.loss[0] = sum;
     }
 }
 
@@ -1244,12 +1283,13 @@ extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, i
                                    float* terms_dev, int32_t* nnA_dev, int32_t* nnB_dev, void* ws,
                                    size_t ws_bytes, int32_t flags, f3d_stream_t stream_) {
     return f3d::chamfer_fwd_launch(A, Bp, B, N, M, w1, w2, B_total, loss_dev, terms_dev, nnA_dev, nnB_dev, ws, ws_bytes, flags,
-                                   static_cast<cudaStream_t>(stream_), nullptr);
+                                   static_cast<cudaStream_t>(stream_), nullptr, nullptr);
 }
 
 int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M, float w1, float w2,
                                 int32_t B_total, float* loss_dev, float* terms_dev, int32_t* nnA_dev, int32_t* nnB_dev,
-                                void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream, const ChamferUpload* upload) {
+                                void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream, const ChamferUpload* upload,
+                                const ChamferPeerSum* peer) {
     using namespace f3d;
     if (!A || !Bp || !loss_dev) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: null A/B/loss pointer");
     if (B <= 0 || N <= 0 || M <= 0) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: B, N, M must be positive (got %d, %d, %d)", B, N, M);
@@ -1261,8 +1301,10 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
     if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0) return fail(F3D_ERR_MISALIGNED, "f3d_chamfer_fwd: workspace must be 256-byte aligned");
     unsigned char* w = static_cast<unsigned char*>(ws);
     const bool fma = (flags & F3D_FLAG_FMA) != 0;
-    if (upload && (fma || (flags & (F3D_FLAG_EXACT_SWEEP | F3D_FLAG_SWEEP_ONLY))))
-        return fail(F3D_ERR_INVALID, "chamfer_fwd_launch: the in-grid upload exists only for the default (filtered) sweep");
+    if ((upload || peer) && (fma || (flags & (F3D_FLAG_EXACT_SWEEP | F3D_FLAG_SWEEP_ONLY))))
+        return fail(F3D_ERR_INVALID, "chamfer_fwd_launch: the in-grid upload / peer sum exist only for the default (filtered) sweep");
+    if (peer && (peer->nranks < 1 || peer->nranks > kMaxPeerRanks || peer->rank < 0 || peer->rank >= peer->nranks))
+        return fail(F3D_ERR_INVALID, "chamfer_fwd_launch: bad peer rank %d of %d", peer->rank, peer->nranks);
 
     if (!fma && !(flags & F3D_FLAG_EXACT_SWEEP)) {
         // ---- default: filtered sweep + certified exact finalize (bit-identical results, ~half the FP32 work) ----
@@ -1346,6 +1388,8 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
         fp.denomB = (double)M * (double)B_total;
         fp.loss = loss_dev; fp.terms = terms_dev;
         fp.upload_timeout = upload ? sp.up.timeout : nullptr;
+        if (peer) fp.peer = *peer;
+        else { fp.peer.mailboxes = nullptr; fp.peer.nranks = 0; fp.peer.rank = 0; fp.peer.seq = 0; }
         {
             // programmatic dependent launch: blocks may start while the sweep's last wave is still running
             cudaLaunchConfig_t cfg = {};

@@ -87,7 +87,7 @@ extern "C" size_t f3d_chamfer_pipe_workspace_bytes(int32_t B, int32_t N, int32_t
 
 extern "C" int32_t f3d_chamfer_pipe_run(void* pipe, const float* A_host, const float* B_host, int32_t B, int32_t N, int32_t M,
                                         float w1, float w2, int32_t B_total, float* loss_dev, float* loss_host, void* ws,
-                                        size_t ws_bytes, int32_t flags, f3d_stream_t stream_) {
+                                        size_t ws_bytes, int32_t flags, void* comm, f3d_stream_t stream_) {
     if (!pipe) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: null pipe handle");
     if (!A_host || !B_host) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: null host array");
     if (!loss_dev && !loss_host) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: give loss_dev, loss_host or both");
@@ -121,8 +121,15 @@ extern "C" int32_t f3d_chamfer_pipe_run(void* pipe, const float* A_host, const f
         F3D_CUDA(cudaMemcpyAsync(dA, A_host, sizeof(float) * 3 * (size_t)B * N, cudaMemcpyHostToDevice, stream));
         F3D_CUDA(cudaMemcpyAsync(dB, B_host, sizeof(float) * 3 * (size_t)B * M, cudaMemcpyHostToDevice, stream));
     }
+    // sharded batch: the loss is summed over the ranks inside the finalize kernel (peer mailboxes over NVLink)
+    ChamferPeerSum peer;
+    const bool fused_sum = comm != nullptr;
+    if (fused_sum) {
+        if (flags & (F3D_FLAG_FMA | F3D_FLAG_EXACT_SWEEP)) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: the fused cross-rank sum exists only for the default sweep");
+        if (!comm_next_peer_sum(comm, &peer)) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: communicator has no peer mailboxes (call f3d_comm_enable_p2p)");
+    }
     const int32_t rc = chamfer_fwd_launch(dA, dB, B, N, M, w1, w2, B_total, target, nullptr, nullptr, nullptr, w + pl.off_ws, pl.ws_chamfer,
-                                          flags, stream, in_grid ? &up : nullptr);
+                                          flags, stream, in_grid ? &up : nullptr, fused_sum ? &peer : nullptr);
     if (rc != F3D_OK) return rc;
     if (!loss_host) return F3D_OK;
 

@@ -17,6 +17,7 @@ struct NcclId { char internal[128]; };
 typedef int (*fn_get_unique_id)(NcclId*);
 typedef int (*fn_comm_init_rank)(void**, int, NcclId, int);
 typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_all_gather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*fn_comm_destroy)(void*);
 typedef const char* (*fn_get_error_string)(int);
 
@@ -25,11 +26,13 @@ struct NcclApi {
     fn_get_unique_id get_unique_id = nullptr;
     fn_comm_init_rank comm_init_rank = nullptr;
     fn_all_reduce all_reduce = nullptr;
+    fn_all_gather all_gather = nullptr;
     fn_comm_destroy comm_destroy = nullptr;
     fn_get_error_string get_error_string = nullptr;
 };
 
 constexpr int kNcclFloat32 = 7;  // ncclFloat32
+constexpr int kNcclChar = 0;     // ncclInt8 / ncclChar
 constexpr int kNcclSum = 0;      // ncclSum
 
 NcclApi* nccl() {
@@ -48,6 +51,7 @@ NcclApi* nccl() {
             api.get_unique_id = (fn_get_unique_id)dlsym(api.handle, "ncclGetUniqueId");
             api.comm_init_rank = (fn_comm_init_rank)dlsym(api.handle, "ncclCommInitRank");
             api.all_reduce = (fn_all_reduce)dlsym(api.handle, "ncclAllReduce");
+            api.all_gather = (fn_all_gather)dlsym(api.handle, "ncclAllGather");
             api.comm_destroy = (fn_comm_destroy)dlsym(api.handle, "ncclCommDestroy");
             api.get_error_string = (fn_get_error_string)dlsym(api.handle, "ncclGetErrorString");
         }
@@ -63,6 +67,11 @@ int32_t nccl_fail(NcclApi* api, int rc, const char* what) {
 struct Comm {
     void* nccl_comm;
     int nranks, rank;
+    // peer mailboxes (f3d_comm_enable_p2p): the fused cross-rank sum of the chamfer finalize writes straight into them
+    unsigned long long* mailbox = nullptr;        // this rank's: [2][nranks] words {step number << 32 | float bits}
+    unsigned long long** mailboxes_dev = nullptr; // device array [nranks]: every rank's mailbox as this device addresses it
+    void* opened[kMaxPeerRanks] = {};             // cudaIpcOpenMemHandle mappings to close
+    unsigned seq = 0;                             // steps issued so far (the same on every rank: collective calls only)
 };
 
 }  // namespace
@@ -91,7 +100,8 @@ extern "C" int32_t f3d_comm_init(int32_t nranks, int32_t rank, const void* id128
     void* c = nullptr;
     int rc = api->comm_init_rank(&c, nranks, id, rank);
     if (rc != 0) return nccl_fail(api, rc, "ncclCommInitRank");
-    Comm* h = new Comm{c, nranks, rank};
+    Comm* h = new Comm();
+    h->nccl_comm = c; h->nranks = nranks; h->rank = rank;
     *comm = h;
     return F3D_OK;
 }
@@ -106,10 +116,83 @@ extern "C" int32_t f3d_allreduce_sum_f32(void* comm, float* dev_buf, int32_t cou
     return F3D_OK;
 }
 
+bool f3d::comm_next_peer_sum(void* comm, ChamferPeerSum* out) {
+    Comm* h = static_cast<Comm*>(comm);
+    if (!h || !h->mailboxes_dev) return false;
+    out->mailboxes = h->mailboxes_dev;
+    out->nranks = h->nranks;
+    out->rank = h->rank;
+    out->seq = ++h->seq;  // 1, 2, ...: never 0, the value the mailboxes start with
+    return true;
+}
+
+// Peer mailboxes: every rank allocates 2 x nranks 8-byte words, exports them with CUDA IPC, gathers everybody's handle
+// over the existing NCCL communicator and maps the peers' mailboxes (NVLink peer access).  Collective; off the hot path.
+extern "C" int32_t f3d_comm_enable_p2p(void* comm, f3d_stream_t stream_) {
+    if (!comm) return fail(F3D_ERR_INVALID, "f3d_comm_enable_p2p: null communicator");
+    NcclApi* api = nccl();
+    if (!api || !api->all_gather) return fail(F3D_ERR_NCCL, "f3d_comm_enable_p2p: ncclAllGather not available");
+    Comm* h = static_cast<Comm*>(comm);
+    if (h->mailboxes_dev) return F3D_OK;
+    if (h->nranks > kMaxPeerRanks) return fail(F3D_ERR_INVALID, "f3d_comm_enable_p2p: at most %d ranks", kMaxPeerRanks);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t words = 2 * (size_t)h->nranks;
+    F3D_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->mailbox), words * sizeof(unsigned long long)));
+    F3D_CUDA(cudaMemset(h->mailbox, 0, words * sizeof(unsigned long long)));
+    cudaIpcMemHandle_t mine;
+    F3D_CUDA(cudaIpcGetMemHandle(&mine, h->mailbox));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    unsigned char* gather = nullptr;  // [nranks][64]
+    F3D_CUDA(cudaMalloc(reinterpret_cast<void**>(&gather), 64 * (size_t)h->nranks));
+    F3D_CUDA(cudaMemcpyAsync(gather + 64 * (size_t)h->rank, &mine, 64, cudaMemcpyHostToDevice, stream));
+    int rc = api->all_gather(gather + 64 * (size_t)h->rank, gather, 64, kNcclChar, h->nccl_comm, stream);
+    if (rc != 0) { cudaFree(gather); return nccl_fail(api, rc, "ncclAllGather"); }
+    cudaIpcMemHandle_t all[kMaxPeerRanks];
+    F3D_CUDA(cudaMemcpyAsync(all, gather, 64 * (size_t)h->nranks, cudaMemcpyDeviceToHost, stream));
+    F3D_CUDA(cudaStreamSynchronize(stream));
+    F3D_CUDA(cudaFree(gather));
+    unsigned long long* ptrs[kMaxPeerRanks];
+    for (int r = 0; r < h->nranks; ++r) {
+        if (r == h->rank) { ptrs[r] = h->mailbox; continue; }
+        void* mapped = nullptr;
+        F3D_CUDA(cudaIpcOpenMemHandle(&mapped, all[r], cudaIpcMemLazyEnablePeerAccess));
+        h->opened[r] = mapped;
+        ptrs[r] = static_cast<unsigned long long*>(mapped);
+    }
+    F3D_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->mailboxes_dev), sizeof(unsigned long long*) * (size_t)h->nranks));
+    F3D_CUDA(cudaMemcpy(h->mailboxes_dev, ptrs, sizeof(unsigned long long*) * (size_t)h->nranks, cudaMemcpyHostToDevice));
+    // nobody may write into a mailbox before its owner has zeroed it: one more collective as a barrier
+    float* token = nullptr;
+    F3D_CUDA(cudaMalloc(reinterpret_cast<void**>(&token), sizeof(float)));
+    F3D_CUDA(cudaMemsetAsync(token, 0, sizeof(float), stream));
+    rc = api->all_reduce(token, token, 1, kNcclFloat32, kNcclSum, h->nccl_comm, stream);
+    if (rc != 0) { cudaFree(token); return nccl_fail(api, rc, "ncclAllReduce (barrier)"); }
+    F3D_CUDA(cudaStreamSynchronize(stream));
+    F3D_CUDA(cudaFree(token));
+    return F3D_OK;
+}
+
+// f3d_chamfer_fwd on one shard of a batch split across the ranks of `comm`, with the sum of the shard losses fused into
+// the finalize kernel (peer mailboxes over NVLink): loss_dev receives the loss of the WHOLE batch on every rank.
+extern "C" int32_t f3d_chamfer_fwd_allreduce(void* comm, const float* A, const float* Bp, int32_t B, int32_t N, int32_t M, float w1,
+                                             float w2, int32_t B_total, float* loss_dev, int32_t* nnA_dev, int32_t* nnB_dev,
+                                             void* ws, size_t ws_bytes, int32_t flags, f3d_stream_t stream_) {
+    if (!comm) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd_allreduce: null communicator");
+    if (flags != F3D_FLAG_NONE) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd_allreduce: only the default sweep has the fused cross-rank sum");
+    ChamferPeerSum peer;
+    if (!comm_next_peer_sum(comm, &peer)) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd_allreduce: communicator has no peer mailboxes (call f3d_comm_enable_p2p)");
+    return chamfer_fwd_launch(A, Bp, B, N, M, w1, w2, B_total, loss_dev, nullptr, nnA_dev, nnB_dev, ws, ws_bytes, flags,
+                              static_cast<cudaStream_t>(stream_), nullptr, &peer);
+}
+
 extern "C" int32_t f3d_comm_destroy(void* comm) {
     if (!comm) return F3D_OK;
     NcclApi* api = nccl();
     Comm* h = static_cast<Comm*>(comm);
+    for (int r = 0; r < kMaxPeerRanks; ++r)
+        if (h->opened[r]) cudaIpcCloseMemHandle(h->opened[r]);
+    if (h->mailboxes_dev) cudaFree(h->mailboxes_dev);
+    if (h->mailbox) cudaFree(h->mailbox);
     int rc = api ? api->comm_destroy(h->nccl_comm) : 0;
     delete h;
     if (rc != 0) return nccl_fail(api, rc, "ncclCommDestroy");

@@ -34,9 +34,21 @@ struct ChamferUpload {
     const float* B_host_dev;
     int uploaders;
 };
+// ... and with the optional cross-rank sum of the loss through peer memory (comm.cu: f3d_comm_enable_p2p): mailboxes[r]
+// is rank r's mailbox (2 x nranks 8-byte words) as THIS device addresses it; seq is the step number (same on every rank).
+constexpr int kMaxPeerRanks = 64;
+struct ChamferPeerSum {
+    unsigned long long* const* mailboxes;  // device array [nranks]
+    int nranks, rank;
+    unsigned seq;
+};
 int32_t chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M, float w1, float w2,
                            int32_t B_total, float* loss_dev, float* terms_dev, int32_t* nnA_dev, int32_t* nnB_dev,
-                           void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream, const ChamferUpload* upload);
+                           void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream, const ChamferUpload* upload,
+                           const ChamferPeerSum* peer);
+// comm.cu: the peer-sum descriptor of a communicator for its next step (advances the step number); false if the
+// communicator has no peer mailboxes (f3d_comm_enable_p2p not called)
+bool comm_next_peer_sum(void* comm, ChamferPeerSum* out);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -43,6 +43,15 @@ class Communicator:
         with torch.cuda.device(self.device):
             _lib.check(L.f3d_comm_init(world, rank, idbuf, ctypes.byref(h)))
         self._h = h
+        self.p2p = False
+
+    def enable_p2p(self):
+        """Collective: map every rank's mailbox over NVLink (CUDA IPC) so that chamfer_distance_sharded can sum the
+        shard losses INSIDE the finalize kernel instead of calling NCCL after it (f3d_comm_enable_p2p)."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().f3d_comm_enable_p2p(self._h, _lib.stream_ptr(self.device)))
+        self.p2p = True
+        return self
 
     def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
         if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
@@ -57,6 +66,16 @@ class Communicator:
             self._h = None
 
 
+class _NcclOnly:
+    """View of a Communicator that hides its peer mailboxes (measurement aid: forces the NCCL all-reduce path)."""
+
+    def __init__(self, comm):
+        self._c, self.p2p = comm, False
+
+    def allreduce_sum_(self, t):
+        return self._c.allreduce_sum_(t)
+
+
 def allreduce_loss_(loss: torch.Tensor, comm=None) -> torch.Tensor:
     """In-place sum of the per-shard loss over all ranks: ``comm`` a Communicator, or None to use the default
     torch.distributed group."""
@@ -68,12 +87,29 @@ def allreduce_loss_(loss: torch.Tensor, comm=None) -> torch.Tensor:
 
 
 def chamfer_distance_sharded(A_shard, B_shard, batch_total: int, *, w1: float = 1.0, w2: float = 1.0, comm=None,
-                             flags: int = 0) -> torch.Tensor:
+                             flags: int = 0, to_host: bool = False) -> torch.Tensor:
     """chamfer_distance over a batch split across ranks: every rank passes its shard (b_local, N, 3) /
     (b_local, M, 3) and the GLOBAL batch size; the per-shard partial losses (already divided by the global
     N*B_total / M*B_total) are summed with one all-reduce, so every rank returns the reference's value for
     the whole batch.  A rank with an empty shard contributes 0."""
     from .metrics import chamfer_forward_host, chamfer_forward_raw
+    if comm is not None and getattr(comm, "p2p", False) and not flags:
+        # fused exchange: the finalize kernel's last block trades the shard losses with its peers through mailboxes
+        # mapped over NVLink — no NCCL call, no extra launch.  Every rank must take part, so shards may not be empty.
+        if len(A_shard) == 0:
+            raise ValueError("the fused cross-rank sum needs a non-empty shard on every rank (batch_total >= world size)")
+        if not (isinstance(A_shard, torch.Tensor) and A_shard.is_cuda):
+            return chamfer_forward_host(A_shard, B_shard, w1, w2, batch_total=batch_total, comm=comm._h,
+                                        to_host=to_host, device=comm.device).reshape(())
+        L = _lib.lib()
+        Bn, N, M = A_shard.shape[0], A_shard.shape[1], B_shard.shape[1]
+        dev = A_shard.device
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(("chamfer", Bn, N, M), L.f3d_chamfer_workspace_bytes(Bn, N, M), dev)
+            loss = torch.empty(1, dtype=torch.float32, device=dev)
+            _lib.check(L.f3d_chamfer_fwd_allreduce(comm._h, _lib.ptr(A_shard), _lib.ptr(B_shard), Bn, N, M, w1, w2, batch_total,
+                                                   _lib.ptr(loss), None, None, _lib.ptr(ws), ws.numel(), 0, _lib.stream_ptr(dev)))
+        return loss.reshape(())
     if not (isinstance(A_shard, torch.Tensor) and A_shard.is_cuda) and len(A_shard) > 0:
         # host shards: upload pipelined against the sweep (f3d_chamfer_pipe_run), then the same one all-reduce
         loss = chamfer_forward_host(A_shard, B_shard, w1, w2, batch_total=batch_total, flags=flags)

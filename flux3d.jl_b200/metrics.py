@@ -64,12 +64,13 @@ _host_plans: dict = {}  # (device index, stream, uploaders, B, N, M) -> (pipe ha
 
 
 def chamfer_forward_host(A, B, w1: float = 1.0, w2: float = 1.0, *, batch_total: int = 0, uploaders: int = 0,
-                         flags: int = FLAG_NONE, device="cuda", to_host: bool = False) -> torch.Tensor:
+                         flags: int = FLAG_NONE, device="cuda", to_host: bool = False, comm=None) -> torch.Tensor:
     """One call of f3d_chamfer_pipe_run: HOST arrays A (B,N,3), B (B,M,3) → the loss.  With page-locked inputs the grid
     pulls the batch over PCIe itself (its first ``uploaders`` CTAs; 0 = default) while the other CTAs sweep what has
     landed; pageable inputs are copied first.  ``to_host=False``: loss[1] on ``device``, no host synchronisation.
     ``to_host=True``: a 0-dim CPU tensor — the grid stores the loss into mapped host memory and the call returns when
-    it has landed (no D2H copy)."""
+    it has landed (no D2H copy).  ``comm``: the handle of a Communicator with peer mailboxes — A and B are then this
+    rank's shard of a ``batch_total`` batch and the loss is the whole batch's, summed inside the finalize kernel."""
     L = _lib.lib()
     A = _host_f32(A)
     B = _host_f32(B)
@@ -104,11 +105,11 @@ def chamfer_forward_host(A, B, w1: float = 1.0, w2: float = 1.0, *, batch_total:
         if to_host:
             out = _lib.C.c_float()
             _lib.check(L.f3d_chamfer_pipe_run(h, A.data_ptr(), B.data_ptr(), Bn, N, M, w1, w2, batch_total, None,
-                                              _lib.C.byref(out), wptr, wsize, flags, sptr))
+                                              _lib.C.byref(out), wptr, wsize, flags, comm, sptr))
             return torch.tensor(out.value, dtype=torch.float32)  # the call returned after the loss landed
         loss = torch.empty(1, dtype=torch.float32, device=torch.device("cuda", idx))
         _lib.check(L.f3d_chamfer_pipe_run(h, A.data_ptr(), B.data_ptr(), Bn, N, M, w1, w2, batch_total, loss.data_ptr(),
-                                          None, wptr, wsize, flags, sptr))
+                                          None, wptr, wsize, flags, comm, sptr))
         # the grid reads A and B asynchronously: keep them alive until the stream has consumed them
         ev = torch.cuda.Event()
         ev.record(stream)

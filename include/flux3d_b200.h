@@ -107,12 +107,14 @@ F3D_API int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, int3
  *   loss_host (optional): when given, the grid stores the loss into mapped host memory and the call returns once it
  *     has landed (no D2H copy) — the one entry point of this ABI that blocks, because a host scalar was asked for.
  *   ws: f3d_chamfer_pipe_workspace_bytes(B, N, M) device bytes (staging copies of both clouds + the sweep workspace),
- *     256-byte aligned, owned by the caller. */
+ *     256-byte aligned, owned by the caller.
+ *   comm (optional): a communicator with peer mailboxes (f3d_comm_enable_p2p) — the call then handles this rank's shard
+ *     of a B_total batch and the loss it delivers is the whole batch's (see f3d_chamfer_fwd_allreduce). */
 F3D_API int32_t f3d_chamfer_pipe_create(int32_t uploaders, void** pipe);
 F3D_API size_t f3d_chamfer_pipe_workspace_bytes(int32_t B, int32_t N, int32_t M);
 F3D_API int32_t f3d_chamfer_pipe_run(void* pipe, const float* A_host, const float* B_host, int32_t B, int32_t N,
                              int32_t M, float w1, float w2, int32_t B_total, float* loss_dev,
-                             float* loss_host, void* ws, size_t ws_bytes, int32_t flags,
+                             float* loss_host, void* ws, size_t ws_bytes, int32_t flags, void* comm,
                              f3d_stream_t stream);
 F3D_API int32_t f3d_chamfer_pipe_destroy(void* pipe);
 
@@ -235,6 +237,20 @@ F3D_API int32_t f3d_sample_points_bwd(const float* gsamples, const int32_t* face
 F3D_API int32_t f3d_comm_unique_id_host(void* id128_host);
 F3D_API int32_t f3d_comm_init(int32_t nranks, int32_t rank, const void* id128_host, void** comm);
 F3D_API int32_t f3d_allreduce_sum_f32(void* comm, float* dev_buf, int32_t count, f3d_stream_t stream);
+/* The same exchange FUSED into the chamfer kernels (no NCCL call, no extra launch on the hot path):
+ *   f3d_comm_enable_p2p: collective, once per communicator — every rank allocates a mailbox (2 x nranks 8-byte words),
+ *     exports it with CUDA IPC, gathers the handles over NCCL and maps its peers' mailboxes (NVLink peer access).
+ *   f3d_chamfer_fwd_allreduce: f3d_chamfer_fwd on this rank's shard (B batch elements of a B_total batch); the finalize
+ *     kernel's last block stores the shard loss — already divided by N*B_total / M*B_total — into its slot of every
+ *     peer's mailbox as one word {step number, float bits}, waits for the nranks words in its own mailbox and adds them
+ *     in rank order, so loss_dev[0] holds the WHOLE batch's loss, the same bits on every rank.  Collective: every rank
+ *     must call it the same number of times.  A peer that never arrives turns the loss into NaN after 2 s.
+ *   f3d_chamfer_pipe_run takes the same communicator (or NULL) as `comm`. */
+F3D_API int32_t f3d_comm_enable_p2p(void* comm, f3d_stream_t stream);
+F3D_API int32_t f3d_chamfer_fwd_allreduce(void* comm, const float* A, const float* Bp, int32_t B, int32_t N, int32_t M,
+                                  float w1, float w2, int32_t B_total, float* loss_dev, int32_t* nnA_dev,
+                                  int32_t* nnB_dev, void* ws, size_t ws_bytes, int32_t flags,
+                                  f3d_stream_t stream);
 F3D_API int32_t f3d_comm_destroy(void* comm);
 
 #ifdef __cplusplus

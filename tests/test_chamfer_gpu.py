@@ -278,11 +278,11 @@ def test_host_pipeline_errors(f3d):
     loss = torch.empty(1, device="cuda")
     s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     P = f3d._lib.ptr
-    assert L.f3d_chamfer_pipe_run(None, P(A), P(A), 2, 8, 8, 1.0, 1.0, 0, P(loss), None, P(ws), ws.numel(), 0, s) == 1
-    assert L.f3d_chamfer_pipe_run(h, None, P(A), 2, 8, 8, 1.0, 1.0, 0, P(loss), None, P(ws), ws.numel(), 0, s) == 1
-    assert L.f3d_chamfer_pipe_run(h, P(A), P(A), 2, 8, 8, 1.0, 1.0, 0, P(loss), None, P(ws), 16, 0, s) == 3
+    assert L.f3d_chamfer_pipe_run(None, P(A), P(A), 2, 8, 8, 1.0, 1.0, 0, P(loss), None, P(ws), ws.numel(), 0, None, s) == 1
+    assert L.f3d_chamfer_pipe_run(h, None, P(A), 2, 8, 8, 1.0, 1.0, 0, P(loss), None, P(ws), ws.numel(), 0, None, s) == 1
+    assert L.f3d_chamfer_pipe_run(h, P(A), P(A), 2, 8, 8, 1.0, 1.0, 0, P(loss), None, P(ws), 16, 0, None, s) == 3
     assert "workspace" in f3d._lib.last_error()
     host = (C.c_float * 1)(-1.0)
-    assert L.f3d_chamfer_pipe_run(h, P(A), P(A), 2, 8, 8, 1.0, 1.0, 0, None, host, P(ws), ws.numel(), 0, s) == 0
+    assert L.f3d_chamfer_pipe_run(h, P(A), P(A), 2, 8, 8, 1.0, 1.0, 0, None, host, P(ws), ws.numel(), 0, None, s) == 0
     assert host[0] == 0.0  # loss_host given: copied back and synchronised inside the call
     assert L.f3d_chamfer_pipe_destroy(h) == 0

@@ -31,6 +31,12 @@ def test_comm_world1(f3d):
         parts = [f3d.chamfer_forward_raw(A[a:b].contiguous(), B[a:b].contiguous(), 1.0, 1.0, batch_total=3)[0].clone()
                  for a, b in ((0, 2), (2, 3))]
         assert abs((parts[0] + parts[1]).item() - full.item()) <= 1e-6 * full.item()
+        # the fused cross-rank sum (peer mailboxes): with one rank it must set everything up (CUDA IPC export, handle
+        # gather over NCCL) and reproduce the plain call bit for bit, for device and for host shards
+        comm.enable_p2p()
+        fused = f3d.chamfer_distance_sharded(A, B, 3, comm=comm)
+        fused_host = f3d.chamfer_distance_sharded(A.cpu().pin_memory(), B.cpu().pin_memory(), 3, comm=comm, to_host=True)
+        assert torch.equal(full, fused) and fused_host.item() == full.item()
         comm.close()
     finally:
         if own:
