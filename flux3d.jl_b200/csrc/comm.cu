@@ -136,39 +136,61 @@ extern "C" int32_t f3d_comm_enable_p2p(void* comm, f3d_stream_t stream_) {
     if (h->mailboxes_dev) return F3D_OK;
     if (h->nranks > kMaxPeerRanks) return fail(F3D_ERR_INVALID, "f3d_comm_enable_p2p: at most %d ranks", kMaxPeerRanks);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const size_t words = 2 * (size_t)h->nranks;
-    F3D_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->mailbox), words * sizeof(unsigned long long)));
-    F3D_CUDA(cudaMemset(h->mailbox, 0, words * sizeof(unsigned long long)));
-    cudaIpcMemHandle_t mine;
-    F3D_CUDA(cudaIpcGetMemHandle(&mine, h->mailbox));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
-    unsigned char* gather = nullptr;  // [nranks][64]
-    F3D_CUDA(cudaMalloc(reinterpret_cast<void**>(&gather), 64 * (size_t)h->nranks));
-    F3D_CUDA(cudaMemcpyAsync(gather + 64 * (size_t)h->rank, &mine, 64, cudaMemcpyHostToDevice, stream));
-    int rc = api->all_gather(gather + 64 * (size_t)h->rank, gather, 64, kNcclChar, h->nccl_comm, stream);
-    if (rc != 0) { cudaFree(gather); return nccl_fail(api, rc, "ncclAllGather"); }
+    // A rank whose LOCAL step fails must still take part in both collectives (with an all-zero handle / a zero vote):
+    // otherwise its peers would wait in NCCL for ever.  Every rank then returns the same verdict.
+    const size_t words = 2 * (size_t)h->nranks;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->mailbox), words * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(h->mailbox, 0, words * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mine, h->mailbox);
+    if (e != cudaSuccess) { memset(&mine, 0, sizeof(mine)); cudaGetLastError(); }
+    cudaError_t first_err = e;
+    unsigned char* scratch = nullptr;  // [nranks][64] handles, then one float vote
+    F3D_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch), 64 * (size_t)h->nranks + 64));
+    F3D_CUDA(cudaMemcpyAsync(scratch + 64 * (size_t)h->rank, &mine, 64, cudaMemcpyHostToDevice, stream));
+    int rc = api->all_gather(scratch + 64 * (size_t)h->rank, scratch, 64, kNcclChar, h->nccl_comm, stream);
+    if (rc != 0) { cudaFree(scratch); return nccl_fail(api, rc, "ncclAllGather"); }
     cudaIpcMemHandle_t all[kMaxPeerRanks];
-    F3D_CUDA(cudaMemcpyAsync(all, gather, 64 * (size_t)h->nranks, cudaMemcpyDeviceToHost, stream));
+    F3D_CUDA(cudaMemcpyAsync(all, scratch, 64 * (size_t)h->nranks, cudaMemcpyDeviceToHost, stream));
     F3D_CUDA(cudaStreamSynchronize(stream));
-    F3D_CUDA(cudaFree(gather));
-    unsigned long long* ptrs[kMaxPeerRanks];
-    for (int r = 0; r < h->nranks; ++r) {
+    bool ok = first_err == cudaSuccess;
+    unsigned long long* ptrs[kMaxPeerRanks] = {};
+    static const cudaIpcMemHandle_t zero = {};
+    for (int r = 0; r < h->nranks && ok; ++r) {
+        if (memcmp(&all[r], &zero, sizeof(zero)) == 0) { ok = false; break; }  // that rank could not export a mailbox
         if (r == h->rank) { ptrs[r] = h->mailbox; continue; }
         void* mapped = nullptr;
-        F3D_CUDA(cudaIpcOpenMemHandle(&mapped, all[r], cudaIpcMemLazyEnablePeerAccess));
+        e = cudaIpcOpenMemHandle(&mapped, all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { if (first_err == cudaSuccess) first_err = e; cudaGetLastError(); ok = false; break; }
         h->opened[r] = mapped;
         ptrs[r] = static_cast<unsigned long long*>(mapped);
     }
-    F3D_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->mailboxes_dev), sizeof(unsigned long long*) * (size_t)h->nranks));
-    F3D_CUDA(cudaMemcpy(h->mailboxes_dev, ptrs, sizeof(unsigned long long*) * (size_t)h->nranks, cudaMemcpyHostToDevice));
-    // nobody may write into a mailbox before its owner has zeroed it: one more collective as a barrier
-    float* token = nullptr;
-    F3D_CUDA(cudaMalloc(reinterpret_cast<void**>(&token), sizeof(float)));
-    F3D_CUDA(cudaMemsetAsync(token, 0, sizeof(float), stream));
-    rc = api->all_reduce(token, token, 1, kNcclFloat32, kNcclSum, h->nccl_comm, stream);
-    if (rc != 0) { cudaFree(token); return nccl_fail(api, rc, "ncclAllReduce (barrier)"); }
+    if (ok) {
+        e = cudaMalloc(reinterpret_cast<void**>(&h->mailboxes_dev), sizeof(unsigned long long*) * (size_t)h->nranks);
+        if (e == cudaSuccess) e = cudaMemcpy(h->mailboxes_dev, ptrs, sizeof(unsigned long long*) * (size_t)h->nranks, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { if (first_err == cudaSuccess) first_err = e; cudaGetLastError(); ok = false; }
+    }
+    // the vote doubles as the barrier "nobody writes into a mailbox before its owner has zeroed it"
+    float* vote = reinterpret_cast<float*>(scratch + 64 * (size_t)h->nranks);
+    const float myvote = ok ? 1.0f : 0.0f;
+    F3D_CUDA(cudaMemcpyAsync(vote, &myvote, sizeof(float), cudaMemcpyHostToDevice, stream));
+    rc = api->all_reduce(vote, vote, 1, kNcclFloat32, kNcclSum, h->nccl_comm, stream);
+    if (rc != 0) { cudaFree(scratch); return nccl_fail(api, rc, "ncclAllReduce (vote)"); }
+    float votes = 0.0f;
+    F3D_CUDA(cudaMemcpyAsync(&votes, vote, sizeof(float), cudaMemcpyDeviceToHost, stream));
     F3D_CUDA(cudaStreamSynchronize(stream));
-    F3D_CUDA(cudaFree(token));
+    F3D_CUDA(cudaFree(scratch));
+    if ((int)(votes + 0.5f) != h->nranks) {
+        // somebody failed: everybody gives the mailboxes up and reports it (the NCCL all-reduce path still works)
+        for (int r = 0; r < kMaxPeerRanks; ++r)
+            if (h->opened[r]) { cudaIpcCloseMemHandle(h->opened[r]); h->opened[r] = nullptr; }
+        if (h->mailboxes_dev) { cudaFree(h->mailboxes_dev); h->mailboxes_dev = nullptr; }
+        if (h->mailbox) { cudaFree(h->mailbox); h->mailbox = nullptr; }
+        if (first_err != cudaSuccess) return cuda_fail(first_err, "f3d_comm_enable_p2p (this rank)");
+        return fail(F3D_ERR_CUDA, "f3d_comm_enable_p2p: %d of %d ranks could not map the peer mailboxes", h->nranks - (int)(votes + 0.5f), h->nranks);
+    }
     return F3D_OK;
 }
 
