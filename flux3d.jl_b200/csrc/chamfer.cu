@@ -23,6 +23,7 @@
 // column pairs {x0,x1,y0,y1},{z0,z1} so that one broadcast LDS.128 + LDS.64 feeds 16 pair distances
 // per lane.
 #include <algorithm>
+#include <cstdlib>
 
 #include "f3d_common.cuh"
 
@@ -484,6 +485,10 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
 // memory / registers, so a tile's prologue is two TMA bulk copies (8 KB each) and eight 16-byte loads per lane.
 // grid (blocks of 256 points, B, 2): z = 0 rows of A, z = 1 columns of B.  Same arithmetic, bit for bit, as the in-tile
 // staging of upload mode and as the finalize's recomputation of |q'|².
+#ifndef F3D_SWEEP_CTAS_PER_SM
+#define F3D_SWEEP_CTAS_PER_SM 0
+#endif
+constexpr int kSweepCtasPerSm = F3D_SWEEP_CTAS_PER_SM;  // > 0: persistent sweep grid of this many CTAs per SM (experiment); 0: one tile per CTA
 constexpr int kPrepThreads = 256;
 #ifndef F3D_PREP_MIN_RB
 #define F3D_PREP_MIN_RB 32
@@ -548,6 +553,9 @@ __global__ void __launch_bounds__(kPrepThreads) chamfer_prepare_kernel(FiltParam
 #ifndef F3D_FILT_UNROLL
 #define F3D_FILT_UNROLL 2
 #endif
+// kLoop = false: one tile per CTA on a (CS, RB, B) grid — the default for resident inputs; kLoop = true: 1-D grid, tile loop
+// c, c + G, ... with roles by start ticket (upload mode; persistent-grid experiments)
+template <bool kLoop>
 __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_kernel(FiltParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int BN = kWarps * p.cols_per_warp;
@@ -558,17 +566,20 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
     __shared__ int s_ticket;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int cs = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
 
     DBG_T(0);
-    // Programmatic dependent launch: let the finalize grid become resident as soon as every CTA of this grid has been
-    // dispatched; its blocks wait on rowdone/coldone, so they soak up the SM slots the last partial wave leaves idle.
+    // Programmatic dependent launch: let the finalize grid become resident as soon as every CTA of this grid has
+    // started; its blocks wait on rowdone/coldone, so they soak up the SM slots the last partial wave leaves idle.
+    // A CTA sweeps tiles c, c + G, c + 2G, ... (G = grid size).  By default G = number of tiles — one tile per CTA and
+    // the hardware block scheduler keeps every SM slot busy; a persistent grid (G = 3 or 4 CTAs per SM, the finalize
+    // resident beside it from the start) measured 13–40 % slower (profiles/r01g §4): its CTAs march through prologue,
+    // loop and epilogue in step, and nothing fills the FMA pipe meanwhile.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (tid == 0) s_maxnb = 0u;
-    if (p.up.U) {
-        // Upload mode (1-D grid of U + tiles CTAs).  Roles go by START order, not by blockIdx: the first U CTAs to start
-        // are the uploaders, so every CTA that waits for data below started after the CTAs that deliver it — forward
-        // progress needs no assumption about the dispatch order.  The others take tiles in batch order.
+    int first = blockIdx.x, stride = gridDim.x;
+    if (kLoop && p.up.U) {
+        // Upload mode (U extra CTAs).  Roles go by START order, not by blockIdx: the first U CTAs to start are the
+        // uploaders, so every CTA that waits for data below started after the CTAs that deliver it — forward progress
+        // needs no assumption about the dispatch order.
         if (tid == 0) s_ticket = (int)atomicAdd(p.counter + kHdrStarted, 1u);
         __syncthreads();
         const int ticket = s_ticket;
@@ -576,8 +587,24 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
             upload_clouds(p, ticket, tid);
             return;
         }
-        const int tile = ticket - p.up.U;
-        cs = tile % p.CS; rb = (tile / p.CS) % p.RB; b = tile / (p.CS * p.RB);
+        first = ticket - p.up.U;
+        stride = gridDim.x - p.up.U;
+    }
+    const int ntiles = p.CS * p.RB * p.B;
+    __shared__ __align__(8) unsigned long long s_bar;
+    const unsigned bar = smem_u32(&s_bar);
+    if (p.Ap) {
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // the prepare grid has completed and its writes are visible
+    }
+    unsigned bar_phase = 0;
+    int arrived_b = -1;  // upload mode: batch elements up to this one have landed
+  for (int tile = first; kLoop ? tile < ntiles : tile == first; tile += kLoop ? stride : 1) {
+    const int cs = kLoop ? tile % p.CS : (int)blockIdx.x, rb = kLoop ? (tile / p.CS) % p.RB : (int)blockIdx.y,
+              b = kLoop ? tile / (p.CS * p.RB) : (int)blockIdx.z;
+    if (tid == 0) s_maxnb = 0u;
+    if (kLoop && p.up.U && b > arrived_b) {
         // wait until this batch element has landed; the bounded wait (2 s) turns a lost upload into a reported error
         // instead of a hung device
         if (tid == 0) {
@@ -594,6 +621,7 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
             }
         }
         __syncthreads();
+        arrived_b = b;
     }
     const int col0 = cs * BN, row0 = rb * kTileRows;
     const float* gA = p.A + (size_t)b * p.N * 3;
@@ -604,11 +632,6 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
     if (p.Ap) {
         // ---- prologue, prepared operands: the column tile arrives by TMA (two bulk copies onto one mbarrier), this
         // lane's 8 rows by eight 16-byte loads — one memory latency, no arithmetic, no barrier besides the mbarrier ----
-        __shared__ __align__(8) unsigned long long s_bar;
-        const unsigned bar = smem_u32(&s_bar);
-        if (tid == 0) mbar_init(bar, 1);
-        __syncthreads();
-        asm volatile("griddepcontrol.wait;" ::: "memory");  // the prepare grid has completed and its writes are visible
         if (tid == 0) {
             const unsigned bytes = (unsigned)(BN / 2) * (unsigned)sizeof(float4);
             mbar_expect_tx(bar, 2 * bytes);
@@ -623,7 +646,8 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
         }
         maxna = __ldg(p.maxna + (size_t)b * p.RB + rb);
         maxnb = __ldg(p.maxnb + (size_t)b * p.CS + cs);
-        while (!mbar_try_wait(bar, 0)) {}
+        while (!mbar_try_wait(bar, bar_phase)) {}
+        bar_phase ^= 1u;
     } else {
         // ---- prologue: issue EVERY global load first (centre samples, this thread's column pairs, this lane's rows),
         // so the CTA pays one memory latency instead of one per dependent step -------------------------------------
@@ -811,6 +835,8 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
         atomicAdd(p.coldone + (size_t)b * p.CS + cs, 1);
     }
     DBG_T(3);
+    // (the barrier above also separates this tile's last use of the shared tile / s_row from the next tile's staging)
+  }
 }
 
 // ---- finalize for the filtered sweep: certify, rescan exactly, reduce the loss ------------------------------
@@ -888,9 +914,19 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
     __shared__ int s_wj[kFinThreads / 32], s_ib[kFinThreads], s_iq[kFinThreads];
     __shared__ float s_ilim[kFinThreads];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool rows = (int)blockIdx.x < p.nbA;
-    const long t = ((long)(rows ? blockIdx.x : blockIdx.x - p.nbA) * (kFinThreads / 32) + warp) * 32 + lane;
+    // Blocks are numbered in the order the persistent sweep completes their inputs: batch element by batch element,
+    // its row blocks (fbA = ceil(N/256) of them), then its column blocks (fbB = ceil(M/256)).
+    const int fbA = (p.N + kFinThreads - 1) / kFinThreads, fbB = (p.M + kFinThreads - 1) / kFinThreads;
+#ifdef F3D_EXP_FIN_ROWS_FIRST
+    // (experiment) all row blocks of the batch first, then all column blocks
+    const int fe = (int)blockIdx.x < p.B * fbA ? (int)blockIdx.x / fbA : ((int)blockIdx.x - p.B * fbA) / fbB;
+    const int fj = (int)blockIdx.x < p.B * fbA ? (int)blockIdx.x - fe * fbA : fbA + ((int)blockIdx.x - p.B * fbA) - fe * fbB;
+#else
+    const int fe = (int)blockIdx.x / (fbA + fbB), fj = (int)blockIdx.x - fe * (fbA + fbB);
+#endif
+    const bool rows = fj < fbA;
     const int Q = rows ? p.N : p.M;        // items per batch element (queries)
+    const long t = (long)fe * Q + (long)(rows ? fj : fj - fbA) * kFinThreads + tid;  // flat item index b*Q + q
     const int R = rows ? p.M : p.N;        // points searched per query
     const float* gQ = rows ? p.A : p.Bp;   // queries
     const float* gP = rows ? p.Bp : p.A;   // searched cloud
@@ -898,7 +934,7 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
     if (blockIdx.x + threadIdx.x == 0) p.loss[0] = 0.f;
     return;
 #endif
-    const bool valid = t < (long)p.B * Q;
+    const bool valid = (rows ? fj : fj - fbA) * kFinThreads + tid < Q;
     double mine = 0.0;
     DBG_F(0);
 
@@ -1166,8 +1202,14 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
     if (!s_last) return;
     __threadfence();
     double sa = 0.0, sb = 0.0;
-    for (int k = tid; k < p.nbA; k += kFinThreads) sa += __ldcg(p.partial + k);
-    for (int k = tid; k < p.nbB; k += kFinThreads) sb += __ldcg(p.partial + p.nbA + k);
+    for (int k = tid; k < p.nbA + p.nbB; k += kFinThreads) {
+        const double v = __ldcg(p.partial + k);
+#ifdef F3D_EXP_FIN_ROWS_FIRST
+        if (k < p.B * fbA) sa += v; else sb += v;
+#else
+        if (k % (fbA + fbB) < fbA) sa += v; else sb += v;
+#endif
+    }
     sa = warp_sum(sa);
     sb = warp_sum(sb);
     __shared__ double s_a[kFinThreads / 32], s_b[kFinThreads / 32];
@@ -1238,8 +1280,8 @@ FiltPlan make_filt_plan(int B, int N, int M) {
     pl.RB = (N + kTileRows - 1) / kTileRows;
     pl.Npad = pl.RB * kTileRows;
     pl.Mpad = pl.CS * pl.BN;
-    pl.nbA = (int)(((long)B * N + kFinThreads - 1) / kFinThreads);
-    pl.nbB = (int)(((long)B * M + kFinThreads - 1) / kFinThreads);
+    pl.nbA = B * ((N + kFinThreads - 1) / kFinThreads);  // finalize blocks: 256 rows of ONE batch element ...
+    pl.nbB = B * ((M + kFinThreads - 1) / kFinThreads);  // ... or 256 of its columns
     size_t o = 0;
     pl.off_rowpart = o; o = align_up(o + sizeof(float4) * (size_t)B * pl.CS * pl.Npad, 256);
     pl.off_colpart = o; o = align_up(o + sizeof(uint2) * (size_t)B * pl.RB * pl.Mpad, 256);
@@ -1333,25 +1375,43 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
             sp.up.U = upload->uploaders;
         }
         const size_t smem = filt_smem_bytes(fl.BN);
+        int dev_id = 0;
         {
             // opt in to the largest tile's shared memory once per device (idempotent; racing threads at worst set it twice)
             static unsigned char attr_done[256];
             int dev = 0;
             F3D_CUDA(cudaGetDevice(&dev));
+            dev_id = dev;
             if (dev < 0 || dev >= 256 || !attr_done[dev]) {
-                F3D_CUDA(cudaFuncSetAttribute(chamfer_filter_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                F3D_CUDA(cudaFuncSetAttribute(chamfer_filter_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)filt_smem_bytes(kWarps * kMaxColsPerWarp)));
+                F3D_CUDA(cudaFuncSetAttribute(chamfer_filter_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)filt_smem_bytes(kWarps * kMaxColsPerWarp)));
                 if (dev >= 0 && dev < 256) attr_done[dev] = 1;
             }
         }
         sp.B = B;
+        // grid: one CTA per tile (kSweepCtasPerSm > 0: a persistent grid instead, each CTA sweeping tiles c, c + G, ...)
+        static int sm_count[256];
+        if (kSweepCtasPerSm > 0 && dev_id >= 0 && dev_id < 256 && sm_count[dev_id] == 0)
+            F3D_CUDA(cudaDeviceGetAttribute(&sm_count[dev_id], cudaDevAttrMultiProcessorCount, dev_id));
+        const int sms = (dev_id >= 0 && dev_id < 256 && sm_count[dev_id] > 0) ? sm_count[dev_id] : 148;
+        const long long ntiles = (long long)fl.CS * fl.RB * B;
+        if (ntiles > 0x7fffffffLL - 2048) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: too many tiles (%lld)", ntiles);
+        unsigned G = (unsigned)(kSweepCtasPerSm > 0 ? std::min<long long>(ntiles, (long long)kSweepCtasPerSm * sms) : ntiles);
+#ifdef F3D_EXP_GRID_ENV
+        if (const char* g = getenv("F3D_SWEEP_G")) G = (unsigned)std::min<long long>(ntiles, atoll(g));  // development aid
+#endif
+        const bool loop = G != (unsigned)ntiles;  // a persistent grid (experiments); else one tile per CTA, 3-D grid
+        if (fl.RB > 65535 && !loop && !sp.up.U) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: N too large");
         if (sp.up.U) {
             // upload mode: the operands do not exist yet — every tile stages its own once its batch element has landed
-            chamfer_filter_sweep_kernel<<<dim3((unsigned)fl.CS * fl.RB * B + sp.up.U), kThreads, smem, stream>>>(sp);
+            chamfer_filter_sweep_kernel<true><<<dim3(G + sp.up.U), kThreads, smem, stream>>>(sp);
         } else if (fl.RB < kPrepMinRowBlocks) {
             // few row blocks: re-deriving a column tile RB times costs less than one more grid in front of the sweep
             // (cfg2, RB = 16: 158.7 µs against 161.1 µs with the prepare grid — profiles/r01g)
-            chamfer_filter_sweep_kernel<<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
+            if (loop) chamfer_filter_sweep_kernel<true><<<dim3(G), kThreads, smem, stream>>>(sp);
+            else chamfer_filter_sweep_kernel<false><<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
         } else {
 #ifndef F3D_EXP_NOPREP
             // many row blocks: prepare the operands once, then the sweep — launched programmatically, it waits
@@ -1363,14 +1423,15 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
             F3D_CHECK_LAUNCH("chamfer_prepare_kernel");
             sp.Ap = Ap; sp.Bxy = Bxy; sp.Bzn = Bzn;
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(fl.CS, fl.RB, B); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+            cfg.gridDim = loop ? dim3(G) : dim3(fl.CS, fl.RB, B); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
-            F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_filter_sweep_kernel, sp));
+            if (loop) F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_filter_sweep_kernel<true>, sp));
+            else F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_filter_sweep_kernel<false>, sp));
 #else
-            chamfer_filter_sweep_kernel<<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
+            chamfer_filter_sweep_kernel<true><<<dim3(G), kThreads, smem, stream>>>(sp);
 #endif
         }
         F3D_CHECK_LAUNCH("chamfer_filter_sweep_kernel");
