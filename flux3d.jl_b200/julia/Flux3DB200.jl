@@ -94,11 +94,34 @@ function Flux3D.chamfer_distance(A::Array{Float32,3}, B::Array{Float32,3}; w1::N
     GC.@preserve A B begin
         check(ccall((:f3d_chamfer_pipe_run, LIB), Int32,
             (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int32, Int32, Int32, Float32, Float32, Int32, Ptr{Float32}, Ptr{Float32},
-             Ptr{Cvoid}, Csize_t, Int32, Ptr{Cvoid}),
+             Ptr{Cvoid}, Csize_t, Int32, Ptr{Cvoid}, Ptr{Cvoid}),
             pipe_handle(), pointer(A), pointer(B), Bn, N, M, Float32(w1), Float32(w2), 0, C_NULL, out,
-            devptr(ws), length(ws), 0, cur_stream()))
+            devptr(ws), length(ws), 0, #=comm=# C_NULL, cur_stream()))
     end
     return out[]   # a host Float32, like the reference on Arrays
+end
+
+# ---- batch sharded over GPUs (one Julia process per GPU): the shard losses are summed INSIDE the finalize kernel ----
+# comm = comm_init(nranks, rank, id) once (id: the 128 bytes of f3d_comm_unique_id_host from rank 0, broadcast e.g. with MPI)
+function comm_init(nranks::Integer, rank::Integer, id::Vector{UInt8})
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:f3d_comm_init, LIB), Int32, (Int32, Int32, Ptr{UInt8}, Ptr{Ptr{Cvoid}}), nranks, rank, id, h))
+    check(ccall((:f3d_comm_enable_p2p, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), h[], cur_stream()))   # peer mailboxes over NVLink
+    return h[]
+end
+
+# this rank's shard (3,N,b_local) / (3,M,b_local) of a batch of batch_total elements -> the loss of the WHOLE batch
+function chamfer_distance_sharded(comm::Ptr{Cvoid}, A::CuArray{Float32,3}, B::CuArray{Float32,3}, batch_total::Integer;
+                                  w1::Float32 = 1f0, w2::Float32 = 1f0)
+    (_, N, Bn) = size(A); M = size(B, 2)
+    nbytes = ccall((:f3d_chamfer_workspace_bytes, LIB), Csize_t, (Int32, Int32, Int32), Bn, N, M)
+    ws = workspace((:chamfer, Bn, N, M), nbytes)
+    loss = CUDA.zeros(Float32, 1)
+    check(ccall((:f3d_chamfer_fwd_allreduce, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int32, Int32, Int32, Float32, Float32, Int32, Ptr{Float32}, Ptr{Int32}, Ptr{Int32},
+         Ptr{Cvoid}, Csize_t, Int32, Ptr{Cvoid}),
+        comm, devptr(A), devptr(B), Bn, N, M, w1, w2, batch_total, devptr(loss), C_NULL, C_NULL, devptr(ws), length(ws), 0, cur_stream()))
+    return CUDA.@allowscalar loss[1]
 end
 
 # _nearest_neighbors(::CuArray, ::CuArray) — src/metrics/pcloud.jl:72-86: CartesianIndex matrices (N,B),(M,B)
