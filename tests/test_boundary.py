@@ -133,3 +133,19 @@ def test_shard_range(f3d):
             assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
     with pytest.raises(ValueError):
         f3d.shard_range(4, 4, 4)
+
+
+def test_workspace_size_queries_are_host_only(f3d):
+    """The *_workspace_bytes queries are pure host arithmetic (callable without a GPU): positive, 256-byte granular,
+    monotone in the batch size, and 0 for invalid shapes — the caller sizes its device buffers from them."""
+    L = f3d._lib.lib()
+    w = L.f3d_chamfer_workspace_bytes(32, 4096, 4096)
+    assert w > 0 and w % 256 == 0
+    assert L.f3d_chamfer_workspace_bytes(64, 4096, 4096) > w
+    assert L.f3d_chamfer_workspace_bytes(0, 4096, 4096) == 0 and L.f3d_chamfer_workspace_bytes(1, -5, 3) == 0
+    wp = L.f3d_chamfer_pipe_workspace_bytes(32, 4096, 4096)
+    # the host-array entry point adds the staging copies of both clouds to the sweep workspace
+    assert wp >= w + 2 * 32 * 4096 * 12 and wp % 256 == 0
+    assert L.f3d_chamfer_pipe_workspace_bytes(32, 0, 4096) == 0
+    # ragged shapes: pads inside the last row block / column tile are accounted for
+    assert L.f3d_chamfer_workspace_bytes(3, 257, 1025) >= L.f3d_chamfer_workspace_bytes(3, 256, 1024)
