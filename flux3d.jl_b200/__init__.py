@@ -12,7 +12,8 @@ from .metrics import (FLAG_EXACT_SWEEP, FLAG_FMA, FLAG_NONE, FLAG_SWEEP_ONLY, ch
                       nearest_neighbors)
 from .mesh import (NORMALS_ACCUMULATE, NORMALS_REFERENCE_CPU, TriMesh, compute_faces_areas_packed,
                    compute_faces_normals_packed, compute_verts_normals_packed, edge_loss, get_edges_packed,
-                   get_laplacian_packed, get_verts_packed, laplacian_loss, load_trimesh, offset)
+                   get_laplacian_packed, get_verts_packed, laplacian_loss, load_trimesh, offset, packed_to_padded,
+                   padded_to_packed)
 from .sampling import sample_points
 from .dgcnn import create_single_knn_graph, edgeconv_features, knn_graph
 from .distributed import Communicator, allreduce_loss_, chamfer_distance_sharded, shard_range
@@ -20,7 +21,8 @@ from .distributed import Communicator, allreduce_loss_, chamfer_distance_sharded
 __all__ = ["PointCloud", "TriMesh", "chamfer_distance", "chamfer_forward_raw", "chamfer_forward_host", "nearest_neighbors", "laplacian_loss",
            "edge_loss", "sample_points", "knn_graph", "create_single_knn_graph", "edgeconv_features",
            "compute_verts_normals_packed", "compute_faces_normals_packed", "compute_faces_areas_packed",
-           "get_verts_packed", "get_edges_packed", "get_laplacian_packed", "load_trimesh", "offset",
+           "get_verts_packed", "get_edges_packed", "get_laplacian_packed", "load_trimesh", "offset", "packed_to_padded",
+           "padded_to_packed",
            "shard_range", "chamfer_distance_sharded", "allreduce_loss_", "Communicator",
            "NORMALS_REFERENCE_CPU", "NORMALS_ACCUMULATE", "FLAG_FMA", "FLAG_NONE", "FLAG_EXACT_SWEEP", "FLAG_SWEEP_ONLY", "Flux3DB200Error", "LIB_PATH"]
 __version__ = "0.1.0"

@@ -33,6 +33,8 @@ SIGNATURES = {
     "f3d_faces_areas_normals": (C.c_int32, [_f32p, _i32p, C.c_int32, C.c_int32, _f32p, _f32p, _vp]),
     "f3d_mesh_topology_build_host": (C.c_int32, [_i32p, C.c_int32, C.c_int32, _i32p, C.POINTER(C.c_int32), _i32p,
                                                  _i32p, _i32p, _f32p, _i32p, _i32p]),
+    "f3d_packed_to_padded": (C.c_int32, [_vp, _i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, _vp, _vp]),
+    "f3d_padded_to_packed": (C.c_int32, [_vp, _i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
     "f3d_verts_normals": (C.c_int32, [_f32p, _i32p, _i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, _f32p, _vp]),
     "f3d_laplacian_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "f3d_laplacian_loss": (C.c_int32, [_f32p, _i32p, _i32p, _f32p, C.c_int32, C.c_int32, _f32p, _vp, C.c_size_t, _vp]),

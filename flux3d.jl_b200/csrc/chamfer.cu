@@ -389,7 +389,7 @@ struct FiltParams {
     float* maxna;      // [B][RB]  max |a'|² over the valid rows of the block
     float* maxnb;      // [B][CS]  max |b'|² over the valid columns of the tile
     float* centre;     // [B][4]   the centre used for this batch element (finalize recomputes |a'|², |b'|² with it)
-    unsigned* counter;  // [0] finalize's block counter; zeroed by a memset node before every sweep, with:
+    unsigned* counter;  // header of the zeroed region (kHdr*: finalize blocks done, CTAs started, upload timeout); one memset per call zeroes it with:
     int* rowdone;       // [B][RB]  tiles of the row block that have published their partials (target CS)
     int* coldone;       // [B][CS]  tiles of the column split that have published their partials (target RB)
     // host-array pipeline (chamfer_pipe.cu): the first up.U CTAs of the grid (by start ticket) do not sweep — they pull the

@@ -243,6 +243,41 @@ __global__ void __launch_bounds__(kMT) edge_loss_bwd_kernel(const float* __restr
     gverts[3 * (size_t)i] = s * gx; gverts[3 * (size_t)i + 1] = s * gy; gverts[3 * (size_t)i + 2] = s * gz;
 }
 
+// ---- packed <-> padded (src/rep/utils.jl:131-185): 4-byte elements, so Float32 verts and Int32 faces share the code ----
+// packed [ΣL][D], item i = rows offsets[i] .. offsets[i+1]-1;  padded [N][W][D], rows past an item's length hold `fill`.
+// delta (optional, [N]): added to every real element on the way to packed, subtracted on the way to padded — the
+// global <-> local vertex ids of packed / padded faces (src/rep/mesh.jl:884-896).
+__global__ void __launch_bounds__(kMT) packed_to_padded_kernel(const unsigned* __restrict__ packed, const int* __restrict__ offsets,
+                                                               const int* __restrict__ delta, int N, int W, int D, unsigned fill,
+                                                               unsigned* __restrict__ padded) {
+    const size_t e = (size_t)blockIdx.x * kMT + threadIdx.x;  // flat index into padded
+    if (e >= (size_t)N * W * D) return;
+    const int d = (int)(e % D), w = (int)((e / D) % W), n = (int)(e / ((size_t)D * W));
+    const int o0 = __ldg(offsets + n), len = __ldg(offsets + n + 1) - o0;
+    unsigned v = fill;
+    if (w < len) {
+        v = __ldg(packed + (size_t)(o0 + w) * D + d);
+        if (delta) v = (unsigned)((int)v - __ldg(delta + n));
+    }
+    padded[e] = v;
+}
+
+__global__ void __launch_bounds__(kMT) padded_to_packed_kernel(const unsigned* __restrict__ padded, const int* __restrict__ offsets,
+                                                               const int* __restrict__ delta, int N, int W, int D, int total_rows,
+                                                               unsigned* __restrict__ packed) {
+    const size_t e = (size_t)blockIdx.x * kMT + threadIdx.x;  // flat index into packed
+    if (e >= (size_t)total_rows * D) return;
+    const int d = (int)(e % D), r = (int)(e / D);
+    int lo = 0, hi = N;  // the item that owns packed row r: largest n with offsets[n] <= r (empty items are skipped)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid) <= r) lo = mid; else hi = mid;
+    }
+    unsigned v = __ldg(padded + ((size_t)lo * W + (r - __ldg(offsets + lo))) * D + d);
+    if (delta) v = (unsigned)((int)v + __ldg(delta + lo));
+    packed[e] = v;
+}
+
 size_t reduce_ws_bytes(int n) {
     const int blocks = (n + kMT - 1) / kMT;
     return align_up(sizeof(double) * (size_t)blocks, 256) + 256;
@@ -425,5 +460,30 @@ extern "C" int32_t f3d_mesh_topology_build_host(const int32_t* faces, int32_t nV
         for (int k = 0; k < 3; ++k)          // slot-major, faces ascending inside a slot
             for (int f = 0; f < nF; ++f) v2c[fill[faces[3 * (size_t)f + k]]++] = 3 * f + k;
     }
+    return F3D_OK;
+}
+
+extern "C" int32_t f3d_packed_to_padded(const void* packed, const int32_t* offsets, const int32_t* delta, int32_t N, int32_t W,
+                                        int32_t D, uint32_t fill_bits, void* padded, f3d_stream_t stream) {
+    using namespace f3d;
+    if (!packed || !offsets || !padded) return fail(F3D_ERR_INVALID, "f3d_packed_to_padded: null pointer");
+    if (N <= 0 || W <= 0 || D <= 0) return fail(F3D_ERR_INVALID, "f3d_packed_to_padded: N, W, D must be positive (got %d, %d, %d)", N, W, D);
+    const size_t total = (size_t)N * W * D;
+    packed_to_padded_kernel<<<(unsigned)((total + kMT - 1) / kMT), kMT, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const unsigned*>(packed), offsets, delta, N, W, D, fill_bits, static_cast<unsigned*>(padded));
+    F3D_CHECK_LAUNCH("packed_to_padded_kernel");
+    return F3D_OK;
+}
+
+extern "C" int32_t f3d_padded_to_packed(const void* padded, const int32_t* offsets, const int32_t* delta, int32_t N, int32_t W,
+                                        int32_t D, int32_t total_rows, void* packed, f3d_stream_t stream) {
+    using namespace f3d;
+    if (!padded || !offsets || !packed) return fail(F3D_ERR_INVALID, "f3d_padded_to_packed: null pointer");
+    if (N <= 0 || W <= 0 || D <= 0 || total_rows < 0) return fail(F3D_ERR_INVALID, "f3d_padded_to_packed: bad sizes (N %d, W %d, D %d, rows %d)", N, W, D, total_rows);
+    if (total_rows == 0) return F3D_OK;
+    const size_t total = (size_t)total_rows * D;
+    padded_to_packed_kernel<<<(unsigned)((total + kMT - 1) / kMT), kMT, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const unsigned*>(padded), offsets, delta, N, W, D, total_rows, static_cast<unsigned*>(packed));
+    F3D_CHECK_LAUNCH("padded_to_packed_kernel");
     return F3D_OK;
 }

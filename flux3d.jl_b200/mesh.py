@@ -25,6 +25,77 @@ NORMALS_REFERENCE_CPU = 0  # last face per corner slot wins: what rep/mesh.jl:60
 NORMALS_ACCUMULATE = 1     # sum over all incident corners: what its docstring says
 
 
+def _packed_to_padded_raw(packed: torch.Tensor, offsets: torch.Tensor, N: int, W: int, fill_bits: int = 0, delta=None) -> torch.Tensor:
+    """f3d_packed_to_padded on a contiguous 4-byte-element tensor (rows, D...) -> (N, W, D...)."""
+    L = _lib.lib()
+    packed = packed.contiguous()
+    D = int(np.prod(packed.shape[1:])) if packed.dim() > 1 else 1
+    out = torch.empty((N, W) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+    with torch.cuda.device(packed.device):
+        _lib.check(L.f3d_packed_to_padded(_lib.ptr(packed), _lib.ptr(offsets), _lib.ptr(delta), N, W, D, fill_bits,
+                                          _lib.ptr(out), _lib.stream_ptr(packed.device)))
+    return out
+
+
+def _padded_to_packed_raw(padded: torch.Tensor, offsets: torch.Tensor, total_rows: int, delta=None) -> torch.Tensor:
+    """f3d_padded_to_packed on a contiguous 4-byte-element tensor (N, W, D...) -> (total_rows, D...)."""
+    L = _lib.lib()
+    padded = padded.contiguous()
+    N, W = padded.shape[0], padded.shape[1]
+    D = int(np.prod(padded.shape[2:])) if padded.dim() > 2 else 1
+    out = torch.empty((total_rows,) + tuple(padded.shape[2:]), dtype=padded.dtype, device=padded.device)
+    with torch.cuda.device(padded.device):
+        _lib.check(L.f3d_padded_to_packed(_lib.ptr(padded), _lib.ptr(offsets), _lib.ptr(delta), N, W, D, total_rows,
+                                          _lib.ptr(out), _lib.stream_ptr(padded.device)))
+    return out
+
+
+class _PackedToPadded(torch.autograd.Function):
+    """_packed_to_padded (src/rep/utils.jl:131-152) with zero fill; the pullback is _padded_to_packed of the gradient."""
+
+    @staticmethod
+    def forward(ctx, packed, offsets, N, W):
+        ctx.offsets, ctx.rows = offsets, packed.shape[0]
+        return _packed_to_padded_raw(packed, offsets, N, W, 0)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _padded_to_packed_raw(g, ctx.offsets, ctx.rows), None, None, None
+
+
+class _PaddedToPacked(torch.autograd.Function):
+    """_padded_to_packed (src/rep/utils.jl:168-185); the pullback scatters the gradient back, pads get zero."""
+
+    @staticmethod
+    def forward(ctx, padded, offsets, total_rows):
+        ctx.offsets, ctx.N, ctx.W = offsets, padded.shape[0], padded.shape[1]
+        return _padded_to_packed_raw(padded, offsets, total_rows)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _packed_to_padded_raw(g, ctx.offsets, ctx.N, ctx.W, 0), None, None
+
+
+def packed_to_padded(packed: torch.Tensor, items_len, pad_value: float = 0.0) -> torch.Tensor:
+    """_packed_to_padded(packed, items_len, pad_value) — src/rep/utils.jl:131-152 — on the device: packed (ΣL, D) float32
+    CUDA tensor (== Julia (D, ΣL)), items_len a list of lengths -> (N, max len, D) (== Julia (D, max len, N))."""
+    lens = [int(x) for x in items_len]
+    offs = torch.tensor(np.concatenate([[0], np.cumsum(lens)]).astype(np.int32), device=packed.device)
+    if pad_value == 0.0:
+        return _PackedToPadded.apply(packed, offs, len(lens), max(lens))
+    bits = int(np.float32(pad_value).view(np.uint32))
+    return _packed_to_padded_raw(packed, offs, len(lens), max(lens), bits)
+
+
+def padded_to_packed(padded: torch.Tensor, items_len) -> torch.Tensor:
+    """_padded_to_packed(padded, items_len) — src/rep/utils.jl:168-185 — on the device: (N, W, D) -> (ΣL, D)."""
+    lens = [int(x) for x in items_len]
+    if len(lens) != padded.shape[0]:
+        raise ValueError("items_len length should match the first dimension of the padded array")  # utils.jl:177-178
+    offs = torch.tensor(np.concatenate([[0], np.cumsum(lens)]).astype(np.int32), device=padded.device)
+    return _PaddedToPacked.apply(padded, offs, int(sum(lens)))
+
+
 def _as_faces(f) -> np.ndarray:
     if isinstance(f, torch.Tensor):
         f = f.detach().cpu().numpy()
@@ -108,17 +179,23 @@ class TriMesh:
         if self._verts_padded is None:
             if self.equalised:
                 self._verts_padded = self._verts_packed.reshape(self.N, self.V, 3)
+            elif self._verts_packed.is_cuda:
+                # _packed_to_padded (rep/utils.jl:131-152) as one kernel; differentiable (pullback: _padded_to_packed)
+                self._verts_padded = _PackedToPadded.apply(self._verts_packed.contiguous(), self.vert_offsets_device(), self.N, self.V)
             else:
-                idx = self._device_tensor("padded_gather", self._padded_gather_index)
-                pad = torch.cat([self._verts_packed, self._verts_packed.new_zeros(1, 3)], dim=0)
-                self._verts_padded = pad[idx].reshape(self.N, self.V, 3)
+                # a host-resident container (only the layout getters work there — every kernel needs CUDA storage):
+                # plain indexing, the way the reference fills its padded Array (rep/utils.jl:144-149)
+                pad = self._verts_packed.new_zeros((self.N, self.V, 3))
+                for i in range(self.N):
+                    pad[i, :self._verts_len[i]] = self._verts_packed[self._vert_offsets[i]:self._vert_offsets[i + 1]]
+                self._verts_padded = pad
         return self._verts_padded
 
-    def _padded_gather_index(self):
-        idx = np.full((self.N, self.V), int(self._vert_offsets[-1]), np.int64)  # → the appended zero row
-        for i in range(self.N):
-            idx[i, :self._verts_len[i]] = np.arange(self._vert_offsets[i], self._vert_offsets[i + 1])
-        return idx.reshape(-1)
+    def vert_offsets_device(self):
+        return self._device_tensor("vert_offsets", lambda: np.asarray(self._vert_offsets, np.int32))
+
+    def face_offsets_device(self):
+        return self._device_tensor("face_offsets", lambda: np.asarray(self._face_offsets, np.int32))
 
     # ------------------------------------------------------------------ faces getters (rep/mesh.jl:382-450, 884-905)
     def get_faces_list(self):
@@ -151,7 +228,17 @@ class TriMesh:
         return self._device_tensor("faces_packed", self.get_faces_packed)
 
     def faces_padded_device(self):
-        return self._device_tensor("faces_padded", self.get_faces_padded)
+        """Padded faces with LOCAL vertex ids, pads -1, built ON the device from the packed faces (global ids): the
+        inverse of the packed-face offsets of rep/mesh.jl:884-896."""
+        t = self._dev.get("faces_padded")
+        if t is None:
+            if self.equalised and self.N == 1:
+                t = self.faces_packed_device().reshape(1, self.F, 3)
+            else:
+                delta = self._device_tensor("vert_base", lambda: np.asarray(self._vert_offsets[:-1], np.int32))
+                t = _packed_to_padded_raw(self.faces_packed_device(), self.face_offsets_device(), self.N, self.F, 0xFFFFFFFF, delta)
+            self._dev["faces_padded"] = t
+        return t
 
     def verts_len_device(self):
         return self._device_tensor("verts_len", lambda: np.asarray(self._verts_len, np.int32))
@@ -205,10 +292,9 @@ class TriMesh:
         return [packed[offsets[i]:offsets[i + 1]] for i in range(self.N)]
 
     def _pad(self, packed, offsets, width):
-        out = packed.new_zeros((self.N, width) + tuple(packed.shape[1:]))
-        for i in range(self.N):
-            out[i, :offsets[i + 1] - offsets[i]] = packed[offsets[i]:offsets[i + 1]]
-        return out
+        """packed (ΣL, ...) -> zero-padded (N, width, ...): one f3d_packed_to_padded launch instead of a host loop."""
+        offs = self.vert_offsets_device() if offsets is self._vert_offsets else self.face_offsets_device()
+        return _packed_to_padded_raw(packed, offs, self.N, width, 0)
 
     def compute_verts_normals_packed(self, mode: int = NORMALS_REFERENCE_CPU) -> torch.Tensor:
         """(ΣV, 3) — rep/mesh.jl:589-618.  mode: NORMALS_REFERENCE_CPU (bit-matches the reference's CPU result)

@@ -168,6 +168,17 @@ F3D_API int32_t f3d_mesh_topology_build_host(const int32_t* faces_host, int32_t 
                                      float* lap_vals_host, int32_t* v2c_rowptr_host,
                                      int32_t* v2c_host);
 
+/* _packed_to_padded / _padded_to_packed (src/rep/utils.jl:131-185) on the device, for 4-byte elements (Float32 verts and
+ * normals, Int32 faces): packed [ΣL][D] with item i = rows offsets[i] .. offsets[i+1]-1 (offsets [N+1], device)  <->
+ * padded [N][W][D]; rows past an item's length are filled with the bit pattern fill_bits (e.g. 0 for 0.0f, 0xffffffff
+ * for the -1 of padded faces).  delta (optional, [N], device) is subtracted from every real element on the way to
+ * padded and added on the way to packed: the global <-> local vertex ids of packed / padded faces
+ * (src/rep/mesh.jl:884-896).  total_rows = offsets[N]. */
+F3D_API int32_t f3d_packed_to_padded(const void* packed, const int32_t* offsets, const int32_t* delta, int32_t N,
+                             int32_t W, int32_t D, uint32_t fill_bits, void* padded, f3d_stream_t stream);
+F3D_API int32_t f3d_padded_to_packed(const void* padded, const int32_t* offsets, const int32_t* delta, int32_t N,
+                             int32_t W, int32_t D, int32_t total_rows, void* packed, f3d_stream_t stream);
+
 /* compute_verts_normals_packed (src/rep/mesh.jl:589-618).  mode: F3D_NORMALS_*.  out [nV][3]. */
 F3D_API int32_t f3d_verts_normals(const float* verts, const int32_t* faces, const int32_t* v2c_rowptr,
                           const int32_t* v2c, int32_t nV, int32_t nF, int32_t mode, float* out,

@@ -388,3 +388,28 @@ def kdtree_chamfer(A, Bc, w1=1.0, w2=1.0, workers=1):
     sA = sum(p[0] for p in parts)
     sB = sum(p[1] for p in parts)
     return np.float32(w1 * sA / (B * A.shape[1]) + w2 * sB / (B * Bc.shape[1]))
+
+
+# ---- packed / padded / list converters (src/rep/utils.jl:51-206), numpy restatement --------------------------------
+def np_packed_to_padded(packed, items_len, pad_value=0):
+    """_packed_to_padded — src/rep/utils.jl:131-152.  packed (ΣL, D) (== Julia (D, ΣL)) -> (N, max len, D)."""
+    packed = np.asarray(packed)
+    n, m = len(items_len), int(max(items_len))
+    padded = np.full((n, m) + packed.shape[1:], pad_value, packed.dtype)
+    cur = 0
+    for i, ln in enumerate(items_len):
+        padded[i, :ln] = packed[cur:cur + ln]
+        cur += ln
+    return padded
+
+
+def np_padded_to_packed(padded, items_len):
+    """_padded_to_packed — src/rep/utils.jl:168-185.  (N, W, D) -> (ΣL, D): the first items_len[i] rows of every item."""
+    padded = np.asarray(padded)
+    assert len(items_len) == padded.shape[0]  # utils.jl:177-178
+    return np.concatenate([padded[i, :ln] for i, ln in enumerate(items_len)], axis=0)
+
+
+def np_list_to_padded(lst, pad_value=0):
+    """_list_to_padded — src/rep/utils.jl:51-93."""
+    return np_packed_to_padded(np.concatenate(lst, axis=0), [len(x) for x in lst], pad_value)

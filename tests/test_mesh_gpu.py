@@ -132,3 +132,47 @@ def test_fit_mesh_step(f3d, oracle, golden_dir):
         opt.step()
         losses.append(float(loss.item()))
     assert losses[-1] < 0.8 * losses[0], losses
+
+
+def test_packed_padded_converters(f3d, oracle):
+    """_packed_to_padded / _padded_to_packed on the device (src/rep/utils.jl:131-185) against the reference's own golden
+    (test/rep.jl:403-490: values and the gradient identities) and against the numpy restatement on ragged random items
+    (an empty item included)."""
+    packed = np.arange(1, 28, dtype=np.float32).reshape(9, 3)
+    items_len = [4, 2, 3]
+    tp = torch.from_numpy(packed).cuda().requires_grad_(True)
+    padded = f3d.packed_to_padded(tp, items_len, 0)
+    want = oracle.np_packed_to_padded(packed, items_len, 0)
+    assert np.array_equal(padded.detach().cpu().numpy(), want)
+    (0.5 * (padded ** 2).sum()).backward()                      # rep.jl:455-458: the gradient is the packed array itself
+    assert np.array_equal(tp.grad.cpu().numpy(), packed)
+    tq = torch.from_numpy(want).cuda().requires_grad_(True)
+    back = f3d.padded_to_packed(tq, items_len)
+    assert np.array_equal(back.detach().cpu().numpy(), packed)   # rep.jl:482
+    (0.5 * (back ** 2).sum()).backward()                        # rep.jl:484-488: the gradient is the padded array (pads 0)
+    assert np.array_equal(tq.grad.cpu().numpy(), want)
+    assert np.array_equal(f3d.packed_to_padded(tp.detach(), items_len, -7.5).cpu().numpy(), oracle.np_packed_to_padded(packed, items_len, -7.5))
+    rng = np.random.default_rng(5)
+    lens = [0, 1, 37, 256, 5, 1000]
+    big = rng.standard_normal((sum(lens), 3)).astype(np.float32)
+    got = f3d.packed_to_padded(torch.from_numpy(big).cuda(), lens, 0)
+    assert np.array_equal(got.cpu().numpy(), oracle.np_packed_to_padded(big, lens, 0))
+    assert np.array_equal(f3d.padded_to_packed(got, lens).cpu().numpy(), big)
+
+
+def test_trimesh_padded_views_on_device(f3d, oracle, golden_dir):
+    """TriMesh's padded views come from the device converters: padded verts / normals / areas and padded faces (local ids,
+    pads -1) equal the host restatement for a heterogeneous batch."""
+    import os
+    v1, f1 = oracle.load_obj(os.path.join(golden_dir, "teapot.obj"))
+    v2, f2 = oracle.load_obj(os.path.join(golden_dir, "sphere.obj"))
+    m = f3d.TriMesh([v1, v2, v1[:200]], [f1, f2, f1[(f1 < 200).all(1)]])
+    lens_v = [len(v1), len(v2), 200]
+    vp = m.get_verts_padded().cpu().numpy()
+    assert np.array_equal(vp, oracle.np_packed_to_padded(m.get_verts_packed().cpu().numpy(), lens_v, 0))
+    assert np.array_equal(m.faces_padded_device().cpu().numpy(), m.get_faces_padded())
+    fa = m.compute_faces_areas_padded().cpu().numpy()
+    lens_f = [len(f) for f in m.get_faces_list()]
+    assert np.array_equal(fa, oracle.np_packed_to_padded(m.compute_faces_areas_packed().cpu().numpy(), lens_f, 0))
+    vn = m.compute_verts_normals_padded().cpu().numpy()
+    assert np.array_equal(vn, oracle.np_packed_to_padded(m.compute_verts_normals_packed().cpu().numpy(), lens_v, 0))

@@ -216,3 +216,14 @@ def test_philox_known_answer(oracle):
     u, r1, r2 = oracle.philox_draws(0xffffffffffffffff, 0xffffffffffffffff, -1, -1)
     assert u == ((0x408f276d << 32) | 0x41c83b0e) >> 11
     assert r1 == np.float32((0xa20bc7c6 >> 8) / 16777216.0) and r2 == np.float32((0x6d5451fd >> 8) / 16777216.0)
+
+
+def test_packed_padded_converters_reference_golden(oracle):
+    """test/rep.jl:403-490: the 9 points 1..27 split 4 / 2 / 3 — _packed_to_padded, _list_to_padded, _padded_to_packed."""
+    packed = np.arange(1, 28, dtype=np.float32).reshape(9, 3)   # == the Julia (3, 9) matrix read column by column
+    items_len = [4, 2, 3]
+    padded = np.zeros((3, 4, 3), np.float32)
+    padded[0, :4], padded[1, :2], padded[2, :3] = packed[0:4], packed[4:6], packed[6:9]
+    assert np.array_equal(oracle.np_packed_to_padded(packed, items_len, 0), padded)
+    assert np.array_equal(oracle.np_list_to_padded([packed[0:4], packed[4:6], packed[6:9]], 0), padded)
+    assert np.array_equal(oracle.np_padded_to_packed(padded, items_len), packed)
