@@ -63,6 +63,21 @@ def test_many_row_blocks_prepared_operands(f3d, oracle):
     _check(f3d, oracle, A2, B2, w1=0.3, w2=2.0)
 
 
+def test_ties_across_more_tiles_than_the_rescan_list(f3d, oracle):
+    """Every pair at the same distance across > 32 row blocks / column tiles: the ambiguous-item rescan overflows its
+    tile list (kMaxSel) and must fall back to scanning the tiles in order — lowest index wins everywhere."""
+    P = np.full((1, 9000, 3), 0.25, np.float32)      # 36 row blocks
+    Q = np.full((1, 300, 3), 0.25, np.float32)
+    loss, _, nnA, nnB = _run(f3d, P, Q)
+    assert loss == 0.0 and not nnA.any() and not nnB.any()
+    _check(f3d, oracle, P, Q)
+    R = np.full((1, 40000, 3), -1.5, np.float32)     # 40 column tiles
+    R[0, 12345] = (0.25, 0.25, 0.25)                 # one exact hit far from index 0
+    loss, _, nnA, nnB = _run(f3d, Q, R)
+    assert np.all(nnA == 12345) and nnB[0, 12345] == 0
+    _check(f3d, oracle, Q, R, both=False)
+
+
 def test_cfg1_known_value(f3d, oracle):
     """cfg1 golden: loss 0.0074543296 (seeds 101/102) — oracle and kernel both."""
     A = np.random.default_rng(101).random((2, 1024, 3), dtype=np.float32)
