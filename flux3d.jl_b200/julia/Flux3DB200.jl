@@ -224,4 +224,33 @@ function Flux3D.sample_points(m::TriMesh{Float32,R,CuArray}, num_samples::Int = 
     return samples
 end
 
+# _packed_to_padded / _padded_to_packed — src/rep/utils.jl:131-185 — on the device (one launch each, no host loop).
+# Julia (D, ΣL) / (D, W, N) arrays are the C [ΣL][D] / [N][W][D] arrays the kernels read.
+item_offsets(items_len) = CuArray(Int32.(vcat(0, cumsum(collect(items_len)))))
+
+function Flux3D._packed_to_padded(packed::CuArray{Float32,2}, items_len::AbstractArray{<:Number,1}, pad_value::Number)
+    D = size(packed, 1); N = length(items_len); W = Int(maximum(items_len))
+    padded = similar(packed, D, W, N); offs = item_offsets(items_len)
+    check(ccall((:f3d_packed_to_padded, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Int32, Int32, Int32, UInt32, Ptr{Cvoid}, Ptr{Cvoid}),
+        devptr(packed), devptr(offs), C_NULL, N, W, D, reinterpret(UInt32, Float32(pad_value)), devptr(padded), cur_stream()))
+    return padded
+end
+
+function Flux3D._padded_to_packed(padded::CuArray{Float32,3}, items_len::AbstractArray{<:Number,1}, pad_value::Nothing = nothing)
+    (D, W, N) = size(padded)
+    N == length(items_len) || error("items_len length should match the last dimension of padded array")   # utils.jl:177-178
+    total = Int(sum(items_len)); packed = similar(padded, D, total); offs = item_offsets(items_len)
+    check(ccall((:f3d_padded_to_packed, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Int32, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}),
+        devptr(padded), devptr(offs), C_NULL, N, W, D, total, devptr(packed), cur_stream()))
+    return packed
+end
+
+# each is the other's pullback (pads receive / contribute zero), as in test/rep.jl:455-458, 484-488
+Zygote.@adjoint Flux3D._packed_to_padded(packed::CuArray{Float32,2}, items_len::AbstractArray{<:Number,1}, pad_value::Number) =
+    Flux3D._packed_to_padded(packed, items_len, pad_value), g -> (Flux3D._padded_to_packed(CuArray{Float32,3}(g), items_len), nothing, nothing)
+Zygote.@adjoint Flux3D._padded_to_packed(padded::CuArray{Float32,3}, items_len::AbstractArray{<:Number,1}, pad_value::Nothing) =
+    Flux3D._padded_to_packed(padded, items_len), g -> (Flux3D._packed_to_padded(CuArray{Float32,2}(g), items_len, 0), nothing, nothing)
+
 end # module
