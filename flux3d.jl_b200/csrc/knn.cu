@@ -51,6 +51,8 @@ struct KnnParams {
     float* dist;     // [B][N][K] or null
     float* gathered; // [B][N][K][F] or null
     float* edge;     // [B][N][K][2F] or null
+    int stage_block; // 1: narrow features — a whole 1024-candidate selection block is staged at once (one exposed load
+                     // latency and two barriers per block instead of eight of each); 0: one 128-candidate tile at a time
 };
 
 template <int kSlots>
@@ -159,32 +161,46 @@ __global__ void __launch_bounds__(kThreadsK, F3D_KNN_MINB) knn_graph_kernel(KnnP
     for (int q = 0; q < kQW; ++q) { top[q].init(); thr[q] = kKeyInf; }
     const float* qrow = s_q + (warp * kQW) * stride;
 
+    // stage rows [c0, c0 + nrows) of the cloud (zero-filled past N) as float4 quads; row = e / q4 by multiply-shift
+    // (exact for e < 2^16: nrows * q4 <= 1024 * 2 in block mode, 128 * 64 in tile mode)
+    auto stage = [&](int c0, int nrows) {
+        const int nc = min(nrows, p.N - c0);
+        for (int e = tid; e < nrows * q4; e += kThreadsK) {
+            const int r = (int)(((unsigned long long)(unsigned)e * q4_inv) >> 32), c4 = e - r * q4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nc) {
+                const float* src = Xb + (size_t)(c0 + r) * p.F + 4 * c4;
+                if (vec4) v = __ldg(reinterpret_cast<const float4*>(src));
+                else {
+                    const int d = 4 * c4;
+                    if (d < p.F) v.x = __ldg(src);
+                    if (d + 1 < p.F) v.y = __ldg(src + 1);
+                    if (d + 2 < p.F) v.z = __ldg(src + 2);
+                    if (d + 3 < p.F) v.w = __ldg(src + 3);
+                }
+            }
+            *reinterpret_cast<float4*>(s_c + r * stride + 4 * c4) = v;
+        }
+    };
+
     for (int blk0 = 0; blk0 < p.N; blk0 += kBlockC) {
         float dist[kQW][kSPL];
+        if (p.stage_block) {
+            __syncthreads();  // previous block fully consumed (and s_q visible on the first pass)
+            stage(blk0, kBlockC);
+            __syncthreads();
+        }
 #pragma unroll
         for (int t = 0; t < kTilesPerBlock; ++t) {
             const int c0 = blk0 + t * kTileC;
             if (c0 < p.N) {  // CTA-uniform
-                __syncthreads();  // previous tile fully consumed (and s_q visible on the first pass)
-                const int nc = min(kTileC, p.N - c0);
-                // stage 128 candidate rows as float4 quads; row = e / q4 by multiply-shift (exact for e < 2^16)
-                for (int e = tid; e < kTileC * q4; e += kThreadsK) {
-                    const int r = (int)(((unsigned long long)(unsigned)e * q4_inv) >> 32), c4 = e - r * q4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < nc) {
-                        const float* src = Xb + (size_t)(c0 + r) * p.F + 4 * c4;
-                        if (vec4) v = __ldg(reinterpret_cast<const float4*>(src));
-                        else {
-                            const int d = 4 * c4;
-                            if (d < p.F) v.x = __ldg(src);
-                            if (d + 1 < p.F) v.y = __ldg(src + 1);
-                            if (d + 2 < p.F) v.z = __ldg(src + 2);
-                            if (d + 3 < p.F) v.w = __ldg(src + 3);
-                        }
-                    }
-                    *reinterpret_cast<float4*>(s_c + r * stride + 4 * c4) = v;
+                const float* s_ct = s_c;
+                if (p.stage_block) s_ct = s_c + t * kTileC * stride;
+                else {
+                    __syncthreads();  // previous tile fully consumed (and s_q visible on the first pass)
+                    stage(c0, kTileC);
+                    __syncthreads();
                 }
-                __syncthreads();
                 float acc[kQW][kCPL];
 #pragma unroll
                 for (int q = 0; q < kQW; ++q)
@@ -193,7 +209,7 @@ __global__ void __launch_bounds__(kThreadsK, F3D_KNN_MINB) knn_graph_kernel(KnnP
                 for (int d = 0; d < p.Fp; d += 4) {
                     float4 cv[kCPL], qv[kQW];
 #pragma unroll
-                    for (int c = 0; c < kCPL; ++c) cv[c] = *reinterpret_cast<const float4*>(s_c + (c * 32 + lane) * stride + d);
+                    for (int c = 0; c < kCPL; ++c) cv[c] = *reinterpret_cast<const float4*>(s_ct + (c * 32 + lane) * stride + d);
 #pragma unroll
                     for (int q = 0; q < kQW; ++q) qv[q] = *reinterpret_cast<const float4*>(qrow + q * stride + d);
 #pragma unroll
@@ -361,7 +377,7 @@ __global__ void __launch_bounds__(kThreadsK, F3D_KNN_MINB) knn_graph_kernel(KnnP
     }
 }
 
-size_t knn_smem_bytes(int Fp) { return sizeof(float) * (size_t)(kQPC + kTileC) * (Fp + 4); }
+size_t knn_smem_bytes(int Fp, bool stage_block) { return sizeof(float) * (size_t)(kQPC + (stage_block ? kBlockC : kTileC)) * (Fp + 4); }
 
 }  // namespace
 
@@ -391,7 +407,12 @@ extern "C" int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F
     KnnParams p;
     p.X = X; p.N = N; p.F = F; p.Fp = (F + 3) / 4 * 4; p.K = K;
     p.idx = idx; p.dist = dist; p.gathered = gathered; p.edge = edge_feat;
-    const size_t smem = knn_smem_bytes(p.Fp);
+    // narrow features (F <= 8: 16 + 1024 rows of <= 48 bytes = 49 KB): the whole selection block fits in shared memory
+    p.stage_block = p.Fp <= 8 ? 1 : 0;
+#ifdef F3D_EXP_KNN_TILE_STAGING
+    p.stage_block = 0;
+#endif
+    const size_t smem = knn_smem_bytes(p.Fp, p.stage_block != 0);
     dim3 grid((N + kQPC - 1) / kQPC, B);
     if (K + 1 <= 32) {
         F3D_CUDA(cudaFuncSetAttribute(knn_graph_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
