@@ -66,7 +66,8 @@ import pynvml as nv
 nv.nvmlInit()
 h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
 print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
-while True:
+t_end = time.time() + 600  # never outlive a bench that died without stopping us
+while time.time() < t_end:
     print(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
           nv.nvmlDeviceGetCurrentClocksEventReasons(h), flush=True)
     time.sleep(0.002)
