@@ -746,13 +746,15 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
     // (b1, c1, b2) after the sweep: keeping that state out of the loop's registers lets ptxas emit the FFMA2s
     // stage by stage with operand reuse (each FFMA2 then reads <= 2 registers per bank; the row-by-row order it
     // picks under register pressure costs 3 cycles per FFMA2 instead of 2 — profiles/r01b notes).
-    float* s_rm = reinterpret_cast<float*>(s_row) + (size_t)warp * nchunks * kTileRows;
+    // (the LAST chunk's minima never leave the registers — they are still live when the loop ends — so nchunks - 1 chunks
+    // are parked: 28 KB instead of 32 KB at 256 columns per warp, which is what lets a fifth CTA fit the SM's 228 KB)
+    float* s_rm = reinterpret_cast<float*>(s_row) + (size_t)warp * (nchunks - 1) * kTileRows;
     DBG_T(1);
 #ifdef F3D_EXP_REPEAT
     for (int rep = 0; rep < F3D_EXP_REPEAT; ++rep)
 #endif
+    float rm[kRowsPerLane];
     for (int ch = 0; ch < nchunks; ++ch) {
-        float rm[kRowsPerLane];
 #pragma unroll
         for (int r = 0; r < kRowsPerLane; ++r) rm[r] = INFINITY;
 #pragma unroll 2
@@ -787,8 +789,10 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
             if (lane == 0) gcol4[pp] = make_uint4((unsigned)m0, bal0, (unsigned)m1, bal1);
 #endif
         }
+        if (ch + 1 < nchunks) {
 #pragma unroll
-        for (int r = 0; r < kRowsPerLane; ++r) s_rm[(ch * kRowsPerLane + r) * 32 + lane] = rm[r];
+            for (int r = 0; r < kRowsPerLane; ++r) s_rm[(ch * kRowsPerLane + r) * 32 + lane] = rm[r];
+        }
     }
 
     // ---- (b1, c1, b2) per row over this warp's chunks: minimum, the EARLIEST chunk reaching it, and the minimum
@@ -800,7 +804,7 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
     for (int ch = 0; ch < nchunks; ++ch) {
 #pragma unroll
         for (int r = 0; r < kRowsPerLane; ++r) {
-            const float cm = s_rm[(ch * kRowsPerLane + r) * 32 + lane];
+            const float cm = ch + 1 < nchunks ? s_rm[(ch * kRowsPerLane + r) * 32 + lane] : rm[r];
             b2[r] = fminf(b2[r], fmaxf(b1[r], cm));
             if (cm < b1[r]) c1[r] = gchunk0 + ch;
             b1[r] = fminf(b1[r], cm);
@@ -1303,7 +1307,7 @@ FiltPlan make_filt_plan(int B, int N, int M) {
 }
 
 size_t filt_smem_bytes(int BN) {
-    const size_t rm_bytes = (size_t)(BN / kChunk) * kTileRows * sizeof(float);  // [kWarps][chunks per warp][8][32]
+    const size_t rm_bytes = (size_t)(BN / kChunk - kWarps) * kTileRows * sizeof(float);  // [kWarps][chunks per warp - 1][8][32]
     return (size_t)(BN / 2) * (2 * sizeof(float4)) + std::max(rm_bytes, (size_t)kWarps * kTileRows * sizeof(float4));
 }
 
