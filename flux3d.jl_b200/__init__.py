@@ -8,7 +8,7 @@ and torch.distributed plumbing."""
 from . import _lib
 from ._lib import Flux3DB200Error, LIB_PATH
 from .pcloud import PointCloud
-from .metrics import (FLAG_EXACT_SWEEP, FLAG_FMA, FLAG_NONE, FLAG_SWEEP_ONLY, chamfer_distance, chamfer_forward_host, chamfer_forward_raw,
+from .metrics import (FLAG_CUDA_CORES, FLAG_EXACT_SWEEP, FLAG_FMA, FLAG_NONE, FLAG_SWEEP_ONLY, FLAG_TENSOR, chamfer_distance, chamfer_forward_host, chamfer_forward_raw,
                       nearest_neighbors)
 from .mesh import (NORMALS_ACCUMULATE, NORMALS_REFERENCE_CPU, TriMesh, compute_faces_areas_packed,
                    compute_faces_normals_packed, compute_verts_normals_packed, edge_loss, get_edges_packed,
@@ -24,5 +24,5 @@ __all__ = ["PointCloud", "TriMesh", "chamfer_distance", "chamfer_forward_raw", "
            "get_verts_packed", "get_edges_packed", "get_laplacian_packed", "load_trimesh", "offset", "packed_to_padded",
            "padded_to_packed",
            "shard_range", "chamfer_distance_sharded", "allreduce_loss_", "Communicator",
-           "NORMALS_REFERENCE_CPU", "NORMALS_ACCUMULATE", "FLAG_FMA", "FLAG_NONE", "FLAG_EXACT_SWEEP", "FLAG_SWEEP_ONLY", "Flux3DB200Error", "LIB_PATH"]
+           "NORMALS_REFERENCE_CPU", "NORMALS_ACCUMULATE", "FLAG_FMA", "FLAG_NONE", "FLAG_EXACT_SWEEP", "FLAG_SWEEP_ONLY", "FLAG_TENSOR", "FLAG_CUDA_CORES", "Flux3DB200Error", "LIB_PATH"]
 __version__ = "0.1.0"

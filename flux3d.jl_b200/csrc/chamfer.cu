@@ -1231,35 +1231,10 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
     }
     if (p.peer.nranks <= 1) return;
 
-    // ---- the one exchange of the sharded path, fused into this kernel: every rank stores its shard's loss (already
-    // divided by the GLOBAL N*B_total / M*B_total) into a mailbox slot on EVERY peer over NVLink — one 8-byte word
-    // {step number, float bits}, so value and flag arrive together — then waits for the R words in its own mailbox and
-    // adds them in rank order: the same bits on every rank, no NCCL kernel, no launch, no second pass over the data.
-    // Slots are double-buffered by the parity of the step number: a rank can only be two steps ahead of a peer after
-    // that peer has sent its word for the step in between, i.e. after it finished reading the older one.
+    // ---- the one exchange of the sharded path, fused into this kernel (peer mailboxes over NVLink: f3d_common.cuh) ----
     __shared__ float s_v[kMaxPeerRanks];
     __syncthreads();
-    if (tid < p.peer.nranks) {
-        const float mine_l = (float)s_a[0];
-        const unsigned long long word = ((unsigned long long)p.peer.seq << 32) | (unsigned long long)__float_as_uint(mine_l);
-        const int base = (int)(p.peer.seq & 1u) * p.peer.nranks;
-        unsigned long long* dst = p.peer.mailboxes[tid] + base + p.peer.rank;  // my slot in rank tid's mailbox
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
-        const unsigned long long* src = p.peer.mailboxes[p.peer.rank] + base + tid;  // rank tid's slot in my mailbox
-        unsigned long long got = 0, t0 = 0;
-        float v = __int_as_float(0x7fc00000);
-        for (unsigned spins = 0;; ++spins) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
-            if ((unsigned)(got >> 32) == p.peer.seq) { v = __uint_as_float((unsigned)got); break; }
-            if ((spins & 4095u) == 4095u) {  // a peer that never sends (crashed rank) must not hang this device: NaN after 2 s
-                unsigned long long now;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > 2000000000ull) break;
-            }
-        }
-        s_v[tid] = v;
-    }
+    if (tid < p.peer.nranks) s_v[tid] = peer_exchange(p.peer, tid, (float)s_a[0]);
     __syncthreads();
     if (tid == 0) {
         float sum = 0.0f;
@@ -1321,7 +1296,7 @@ extern "C" __attribute__((visibility("default"))) int f3d_debug_read_fin(void* h
 
 extern "C" size_t f3d_chamfer_workspace_bytes(int32_t B, int32_t N, int32_t M) {
     if (B <= 0 || N <= 0 || M <= 0) return 0;
-    return std::max(f3d::make_plan(B, N, M).total, f3d::make_filt_plan(B, N, M).total);
+    return std::max(std::max(f3d::make_plan(B, N, M).total, f3d::make_filt_plan(B, N, M).total), f3d::chamfer_tc_workspace_bytes(B, N, M));
 }
 
 extern "C" int32_t f3d_chamfer_fwd(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M,
@@ -1352,8 +1327,13 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
     if (peer && (peer->nranks < 1 || peer->nranks > kMaxPeerRanks || peer->rank < 0 || peer->rank >= peer->nranks))
         return fail(F3D_ERR_INVALID, "chamfer_fwd_launch: bad peer rank %d of %d", peer->rank, peer->nranks);
 
+    // ---- default for problems that fill the machine: the filter sweep on the tensor cores (chamfer_tc.cu) --------------
+    // (F3D_FLAG_TENSOR forces it for any shape: tests drive small and ragged shapes through it that way)
+    if (!fma && !upload && !(flags & (F3D_FLAG_EXACT_SWEEP | F3D_FLAG_CUDA_CORES)) && ((flags & F3D_FLAG_TENSOR) || chamfer_tc_supported(B, N, M)))
+        return chamfer_tc_launch(A, Bp, B, N, M, w1, w2, B_total, loss_dev, terms_dev, nnA_dev, nnB_dev, ws, ws_bytes, flags, stream, peer);
+
     if (!fma && !(flags & F3D_FLAG_EXACT_SWEEP)) {
-        // ---- default: filtered sweep + certified exact finalize (bit-identical results, ~half the FP32 work) ----
+        // ---- CUDA-core filtered sweep + certified exact finalize (bit-identical results, ~half the FP32 work) ----
         FiltPlan fl = make_filt_plan(B, N, M);
         if (fl.RB > 65535) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: N too large");
         FiltParams sp;
@@ -1454,7 +1434,7 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
         fp.loss = loss_dev; fp.terms = terms_dev;
         fp.upload_timeout = upload ? sp.up.timeout : nullptr;
         if (peer) fp.peer = *peer;
-        else { fp.peer.mailboxes = nullptr; fp.peer.nranks = 0; fp.peer.rank = 0; fp.peer.seq = 0; }
+        else { fp.peer.mailboxes = nullptr; fp.peer.nranks = 0; fp.peer.rank = 0; fp.peer.seq = 0; fp.peer.timeout_ns = 0; fp.peer.fault = nullptr; }
         {
             // programmatic dependent launch: blocks may start while the sweep's last wave is still running
             cudaLaunchConfig_t cfg = {};

@@ -126,11 +126,12 @@ extern "C" int32_t f3d_chamfer_pipe_run(void* pipe, const float* A_host, const f
     const bool fused_sum = comm != nullptr;
     if (fused_sum) {
         if (flags & (F3D_FLAG_FMA | F3D_FLAG_EXACT_SWEEP)) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: the fused cross-rank sum exists only for the default sweep");
-        if (!comm_next_peer_sum(comm, &peer)) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: communicator has no peer mailboxes (call f3d_comm_enable_p2p)");
+        if (!comm_peek_peer_sum(comm, &peer)) return F3D_ERR_NCCL;  // the error string is set
     }
     const int32_t rc = chamfer_fwd_launch(dA, dB, B, N, M, w1, w2, B_total, target, nullptr, nullptr, nullptr, w + pl.off_ws, pl.ws_chamfer,
                                           flags, stream, in_grid ? &up : nullptr, fused_sum ? &peer : nullptr);
     if (rc != F3D_OK) return rc;
+    if (fused_sum) comm_commit_peer_sum(comm);  // only now: a rank-local failure above must not advance the step number
     if (!loss_host) return F3D_OK;
 
     if (loss_dev) F3D_CUDA(cudaMemcpyAsync(loss_dev, h->host_dev, sizeof(float), cudaMemcpyDefault, stream));

@@ -1,0 +1,904 @@
+// chamfer_tc.cu — the chamfer filter sweep on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Same contract and the same bits as chamfer.cu (src/metrics/pcloud.jl:39-52, :54-70 semantics): every reported index and
+// distance is evaluated in the reference arithmetic; the tensor cores only decide WHERE to look.
+//
+// The N x 3 . 3 x M contraction of the squared distance is the dense part of the path.  One direction of the search
+// ("for every query row, the nearest candidate column") is a K = 16 TF32 GEMM whose accumulator never leaves the SM:
+//     f_ij = |q_i|² + |c_j|² - 2 q_i.c_j = sum_k R[i][k] C[j][k]
+//     R[i] = {xh,xh,xl,xl, yh,yh,yl,yl | zh,zh,zl,zl, nh,nl,1,1}        (x = xh + xl: an FP32 value as two TF32 pieces)
+//     C[j] = {Xh,Xl,Xh,Xl, Yh,Yl,Yh,Yl | Zh,Zl,Zh,Zl, 1,1,Nh,Nl}        (X = -2x of the candidate; points are centred)
+// Both directions run the same kernel with the clouds swapped (the MMA is nearly free; what costs is reading the
+// accumulator: in TMEM a thread owns one query ROW, so a row minimum is an in-thread FMNMX3 tree, a column minimum would
+// need one warp reduction per column).  Measured error of f against the exact distance: <= 6.4 u (|q|² + |c|²), u = 2^-24
+// (tools/tc_probe.cu; 5.3 u of it is the tensor core's own accumulation) — tighter than the FP32 expanded form of
+// chamfer.cu; the certificate below assumes 35 u.
+//
+// Work item = 256 query rows of one batch element and direction (two 128-row UMMA tiles) against ALL candidates of the
+// other cloud, streamed as 128-candidate tiles.  One persistent CTA per SM, 14 warps with fixed roles:
+//     producer (1 thread)   TMA bulk copies (cp.async.bulk -> UBLKCP) of compact operands {x', y', z', |p'|²} (16 B / point,
+//                           written once by chamfer_tc_prepare_kernel) into a 4-slot ring
+//     converters (4 warps)  thread <-> point: split the four values into TF32 pieces and write the 64-byte K-major
+//                           SWIZZLE_64B operand row (the 64 B/point image is never in HBM or L2: at 256 rows per candidate
+//                           tile a pre-expanded image would need ~9 TB/s of L2 -> SM traffic at the rate the MMAs run)
+//     MMA issuer (1 thread) four tcgen05.mma.kind::tf32 (2 row tiles x 2 K-steps, M = 128, N = 128) per candidate tile into
+//                           double-buffered TMEM accumulators (4 x 128 columns = all 512)
+//     read-out (8 warps)    thread <-> query row (TMEM lane): tcgen05.ld 32 columns at a time, FMNMX3 tree, and the locator
+//                           triple of chamfer.cu — b1 = row minimum, c1 = the 32-candidate chunk where it was first reached,
+//                           b2 = the minimum over all other chunks — plus one minimum per 1024-candidate supertile.
+// chamfer_tc_finalize_kernel (launched programmatically, co-resident with the sweep: it runs on the FP32 pipe the sweep
+// leaves idle) certifies every row — b2 > b1 + window proves the exact argmin, lowest index on ties, lies in chunk c1 —
+// re-evaluates those 32 candidates in the reference arithmetic, and rescans the supertiles within the window for the rare
+// ambiguous rows.  The loss is reduced in a fixed order (bitwise repeatable); for a sharded batch the sum over ranks is
+// fused into its last block (peer mailboxes over NVLink, as in chamfer.cu).
+#include <algorithm>
+#include <cstdlib>
+
+#include "f3d_common.cuh"
+
+namespace f3d {
+namespace {
+
+constexpr int kTQ = 128;                    // UMMA M = TMEM lanes = query rows per row tile
+constexpr int kRT = 2;                      // row tiles per work item
+constexpr int kItemRows = kTQ * kRT;        // 256
+constexpr int kTNc = 256;                   // UMMA N = candidates per tile.  A tcgen05.mma costs ~245 cycles however small it is
+                                            // (tools/tc_probe3.cu: N = 32 ... 128 all take 245; N = 256 takes 293 = 87 % of the TF32 rate)
+constexpr int kTcChunk = 32;                // locator chunk (candidates re-evaluated per certified row)
+constexpr int kSuper = 2048;                // supertile: one stored minimum per row, column quarter and 2048 candidates
+constexpr int kTilesPerSuper = kSuper / kTNc;
+constexpr int kRowB = 64;                   // operand row: 16 TF32 = 64 bytes
+constexpr int kStages = 3;                  // operand ring (16 KB per stage)
+// Tunables (development: tools/build_variants.sh)
+#ifndef F3D_TC_CSTAGES
+#define F3D_TC_CSTAGES 4
+#endif
+#ifndef F3D_TC_EPI_REGS
+#define F3D_TC_EPI_REGS 88
+#endif
+constexpr int kCStages = F3D_TC_CSTAGES;    // compact ring (4 KB per slot)
+constexpr int kParts = 4;                   // a row's 256 accumulator columns are read by four warps, 64 columns each
+constexpr int kEpiWarps = 4 * kParts;       // read-out warps: warp w reads lane quadrant w & 3, column quarter w >> 2 of BOTH row tiles' accumulators
+constexpr int kConvWarps = 4;               // converters: thread <-> two points of a 256-point tile
+constexpr int kWarpProducer = kEpiWarps + kConvWarps, kWarpMma = kWarpProducer + 1, kWarpPublisher = kWarpMma + 1;
+constexpr int kTcThreads = (kEpiWarps + kConvWarps + 4) * 32;   // 768: six warpgroups (the last one: producer, MMA issuer, publisher, one idle warp)
+// Registers: the CTA is launched with kLaunchRegs per thread; the four read-out warpgroups then grow to kEpiRegs — both
+// tcgen05.ld of an accumulator quarter are in flight at once, 64 registers of data — and the other two shrink to kAuxRegs
+// (setmaxnreg).  768 x 72 = 512 x 88 + 256 x 40, and 10 240 registers stay free for a co-resident finalize block.
+constexpr int kLaunchRegs = 72, kEpiRegs = F3D_TC_EPI_REGS, kAuxRegs = 40;
+static_assert(kTcThreads * kLaunchRegs >= kEpiWarps * 32 * kEpiRegs + (kTcThreads - kEpiWarps * 32) * kAuxRegs, "register budget");
+static_assert(kItemRows == kTNc, "the query rows of an item travel as one 256-point compact tile");
+constexpr int kFinT = 128;                  // finalize block = one row tile
+constexpr float kPadN = 1.0e30f;            // |p'|² of padded points: never a minimum for in-contract inputs
+constexpr float kTcNormLimit = 1.0e29f, kTcNormFloor = 1.0e-30f;  // outside: certify nothing (overflow / underflow of the pieces)
+// Certificate: |f - d| <= kErrAbs (nq + nc) + 5.001 u d  (u = 2^-24; d = the reference-arithmetic distance).  35 u =
+// 12 u (two-piece TF32 representation of the coordinates and norms) + 7.02 u (FP32 norms, centring — as in chamfer.cu) +
+// 16 u allowed for the tensor core's accumulation (measured <= 5.3 u).  Hence "b2 > b1 + 70.1 u (nq + max nc) + 10.01 u b1"
+// proves that the exact argmin lies in chunk c1.  Every certified row is also CHECKED: the exact minimum found in the
+// chunk must lie within kErrAbs (nq + nc) + kErrRel d of b1, else the row is rescanned like an ambiguous one and counted
+// (header word kHdrViol; tests assert it stays 0).
+constexpr float kTcWinAbs = 4.2e-6f;        // >= 70.1 u = 4.178e-6
+constexpr float kTcWinRel = 6.2e-7f;        // >= 10.01 u
+constexpr float kTcErrAbs = 2.1e-6f, kTcErrRel = 3.1e-7f;
+// workspace header (ints); the first three words are diagnostics a caller may read after the call
+constexpr int kHdrDone = 0, kHdrAmb = 1, kHdrViol = 2, kHdrInts = 64;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(unsigned* slot_in_smem, int cols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned addr, int cols) {  // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {  // arrives on bar when all prior MMAs of this thread are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"l"((unsigned long long)__cvta_generic_to_shared(bar)) : "memory");
+}
+// issue only; the registers are valid after tmem_ld_wait(r), which carries them as in/out operands so that no consumer can
+// be scheduled ahead of the wait
+__device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, unsigned (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(unsigned (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                   "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]),
+                   "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),
+                   "+r"(r[31])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_issue(unsigned taddr, unsigned (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                   "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(unsigned (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                   "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ int ld_acquire_i32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ float min32(const unsigned (&r)[32]) {
+    float t[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) t[i] = min3(__uint_as_float(r[3 * i]), __uint_as_float(r[3 * i + 1]), __uint_as_float(r[3 * i + 2]));
+    t[10] = fminf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+    const float u0 = min3(t[0], t[1], t[2]), u1 = min3(t[3], t[4], t[5]), u2 = min3(t[6], t[7], t[8]), u3 = fminf(t[9], t[10]);
+    return fminf(min3(u0, u1, u2), u3);
+}
+__device__ __forceinline__ float min16(const unsigned (&r)[16]) {
+    float t[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) t[i] = min3(__uint_as_float(r[3 * i]), __uint_as_float(r[3 * i + 1]), __uint_as_float(r[3 * i + 2]));
+    return min3(min3(t[0], t[1], t[2]), fminf(t[3], t[4]), __uint_as_float(r[15]));
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// K-major SWIZZLE_64B operand descriptor (cute::UMMA::make_umma_desc<Major::K>, LayoutType::B64): rows of 64 B, the
+// 16-byte chunk c of row r at r*64 + ((c ^ ((r >> 1) & 3)) << 4), 8-row groups 512 B apart (SBO = 32), version 1
+__device__ __forceinline__ unsigned long long umma_desc64(unsigned smem_addr) {
+    return (unsigned long long)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+constexpr unsigned kIdescTc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kTNc >> 3) << 17) | ((unsigned)(kTQ >> 4) << 24);
+
+// x = h + l + e with h, l representable in TF32 (11 significant bits) and |e| <= 2^-22 |x|
+__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void split_tf32(float x, float& h, float& l) {
+    h = rn_tf32(x);
+    l = rn_tf32(__fsub_rn(x, h));
+}
+
+// ---- prepare: compact operands {x', y', z', |p'|²} of both clouds, once per call ---------------------------------------
+struct TcPrepParams {
+    const float* A;    // [B][N][3]
+    const float* Bp;   // [B][M][3]
+    int N, M, NpA, NpB;
+    float4* PA;        // [B][NpA]
+    float4* PB;        // [B][NpB]
+    unsigned* maxn;    // [2][B]  max |p'|² per cloud and batch element (float bits; zeroed before the launch)
+};
+constexpr int kPrepT = 256;
+__global__ void __launch_bounds__(kPrepT) chamfer_tc_prepare_kernel(TcPrepParams p) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the sweep's set-up overlaps this grid; it waits before it reads
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.y;
+    const bool isA = blockIdx.z == 0;
+    const int n = isA ? p.N : p.M, np = isA ? p.NpA : p.NpB;
+    if ((int)blockIdx.x * kPrepT >= np) return;
+    const float* gA = p.A + (size_t)b * p.N * 3;
+    const float* gB = p.Bp + (size_t)b * p.M * 3;
+    // the centre of the batch element: the mean of 32 + 32 strided sample points (any point works — the certificate uses the
+    // norms actually obtained); every warp computes it with the same operations => the same bits everywhere
+    const int ia = (int)(((long)lane * p.N) >> 5), ib = (int)(((long)lane * p.M) >> 5);
+    float cx = __ldg(gA + 3 * ia) + __ldg(gB + 3 * ib);
+    float cy = __ldg(gA + 3 * ia + 1) + __ldg(gB + 3 * ib + 1);
+    float cz = __ldg(gA + 3 * ia + 2) + __ldg(gB + 3 * ib + 2);
+    const int i = blockIdx.x * kPrepT + tid;
+    const float* src = (isA ? gA : gB) + 3 * (size_t)min(i, n - 1);
+    const float rx = __ldg(src), ry = __ldg(src + 1), rz = __ldg(src + 2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cx += __shfl_xor_sync(0xffffffffu, cx, o);
+        cy += __shfl_xor_sync(0xffffffffu, cy, o);
+        cz += __shfl_xor_sync(0xffffffffu, cz, o);
+    }
+    cx *= (1.0f / 64.0f); cy *= (1.0f / 64.0f); cz *= (1.0f / 64.0f);
+    float x = 0.f, y = 0.f, z = 0.f, nrm = kPadN, mx = 0.f;
+    if (i < n) {
+        x = rx - cx; y = ry - cy; z = rz - cz;
+        nrm = fmaf(z, z, fmaf(y, y, x * x));
+        mx = nrm;
+    }
+    if (i < np) (isA ? p.PA : p.PB)[(size_t)b * np + i] = make_float4(x, y, z, nrm);
+    mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));  // norms are >= 0 (NaN bits order above everything: caught by the limit test)
+    if (lane == 0) atomicMax(p.maxn + (size_t)(isA ? 0 : 1) * gridDim.y + b, __float_as_uint(mx));
+}
+
+// ---- sweep -------------------------------------------------------------------------------------------------------------
+#ifdef F3D_TC_PROF
+// development: cycles every role spends waiting / working, per CTA (read back with f3d_debug_read_tc)
+__device__ long long g_tcprof[148 * 16];
+#define PROF_DECL long long pf_[6] = {0, 0, 0, 0, 0, 0}; long long pt_ = clock64()
+#define PROF(k) do { const long long n_ = clock64(); pf_[k] += n_ - pt_; pt_ = n_; } while (0)
+#define PROF_OUT(base, n) do { if (blockIdx.x < 148) for (int i_ = 0; i_ < (n); ++i_) g_tcprof[blockIdx.x * 16 + (base) + i_] = pf_[i_]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(k)
+#define PROF_OUT(base, n)
+#endif
+struct TcSweepParams {
+    const float4* PA;
+    const float4* PB;
+    int B, NpA, NpB;       // padded cloud sizes (multiples of 256)
+    int rbA, rbB;          // 256-row blocks per batch element: NpA / 256, NpB / 256
+    float4* rowfin;        // [B][NpA + NpB]  {b1, b2, c1 (int bits), -}: rows of A (searching B), then rows of B (searching A)
+    float* tilemin;        // [B][ (nstB*NpA + nstA*NpB) * kParts ]  per supertile of the searched cloud, read-out group and row
+    int nstA, nstB;        // supertiles of cloud A / B
+    int* done;             // [B*(rbA+rbB)*kRT]  read-out warps that have published a row tile (target 4)
+    int wait_prepare;      // launched programmatically behind the prepare grid
+};
+
+__global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p) {
+    extern __shared__ unsigned char smem_raw_[];
+    unsigned char* smem = smem_raw_ + ((1024u - (smem_u32(smem_raw_) & 1023u)) & 1023u);
+    unsigned char* s_a = smem;                                            // [2][kRT][128][64 B]   query operand tiles, double-buffered per item
+    unsigned char* s_b = s_a + 2 * kRT * kTQ * kRowB;                     // [kStages][256][64 B]  candidate operand ring
+    float4* s_c = reinterpret_cast<float4*>(s_b + kStages * kTNc * kRowB);  // [kCStages][256]      compact ring
+    float4* s_pub = s_c + kCStages * kTNc;                                // [2][kParts][256]     locator triples per column quarter, per item parity
+    __shared__ unsigned long long cfull[kCStages], cempty[kCStages], full_b[kStages], empty_b[kStages], tfull[kRT], tempty[kRT], a_full[2], a_empty[2],
+        pub_full[2], pub_empty[2];
+    __shared__ unsigned s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the finalize grid may become resident beside this one right away: its blocks wait for `done`
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) {
+        for (int s = 0; s < kCStages; ++s) { mbar_init(&cfull[s], 1); mbar_init(&cempty[s], kConvWarps); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_b[s], kConvWarps); mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < kRT; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], kConvWarps); mbar_init(&a_empty[s], 1); mbar_init(&pub_full[s], kEpiWarps); mbar_init(&pub_empty[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&s_tmem, kRT * kTNc);  // all 512 columns: one 256-column accumulator per row tile
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = s_tmem;
+
+    const int ipe = p.rbA + p.rbB, nitems = p.B * ipe;   // items per batch element: row blocks of A, then of B
+    // every role walks the same item sequence; tile / slot counters run on across items so the pipelines never drain
+    if (warp >= kEpiWarps) {
+      // the two auxiliary warpgroups (converters; producer / MMA issuer / publisher / one idle warp) hand registers back
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAuxRegs));
+      if (warp == kWarpProducer) {
+        if (lane == 0) {
+            if (p.wait_prepare) asm volatile("griddepcontrol.wait;" ::: "memory");  // the compact operands are complete and visible
+            unsigned h = 0;  // compact tiles streamed so far
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int b = item / ipe, k = item - b * ipe;
+                const bool dir = k >= p.rbA;
+                const int rb = dir ? k - p.rbA : k;
+                const int npq = dir ? p.NpB : p.NpA, npc = dir ? p.NpA : p.NpB;
+                const float4* Pq = (dir ? p.PB : p.PA) + (size_t)b * npq + (size_t)rb * kItemRows;
+                const float4* Pc = (dir ? p.PA : p.PB) + (size_t)b * npc;
+                const int ntiles = npc / kTNc;
+                for (int t = -1; t < ntiles; ++t, ++h) {   // t = -1: the item's 256 query rows
+                    const unsigned s = h % kCStages, n = h / kCStages;
+                    mbar_wait(&cempty[s], (n & 1) ^ 1);
+                    mbar_expect_tx(&cfull[s], kTNc * 16);
+                    tma_bulk_g2s(s_c + s * kTNc, t < 0 ? Pq : Pc + (size_t)t * kTNc, kTNc * 16, &cfull[s]);
+                }
+            }
+        }
+      } else if (warp == kWarpMma) {
+        if (lane == 0) {
+            // The two row tiles' accumulators alternate: while the read-out warps of row tile r pull tile t out of TMEM, the
+            // MMAs of row tile 1-r run — each accumulator is single-buffered, the pair is the double buffer.
+            unsigned g = 0, it = 0;
+            const unsigned a0 = smem_u32(s_a), b0 = smem_u32(s_b);
+            PROF_DECL;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+                const int b = item / ipe, k = item - b * ipe;
+                const int ntiles = (k >= p.rbA ? p.NpA : p.NpB) / kTNc;
+                const unsigned ab = it & 1;
+                mbar_wait(&a_full[ab], (it >> 1) & 1);
+                PROF(0);
+                for (int t = 0; t < ntiles; ++t, ++g) {
+                    const unsigned s = g % kStages, n = g / kStages;
+                    mbar_wait(&full_b[s], n & 1);
+                    PROF(1);
+#pragma unroll
+                    for (int r = 0; r < kRT; ++r) {
+                        mbar_wait(&tempty[r], (g & 1) ^ 1);
+                        PROF(2 + r);
+                        tc_fence_after();
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+                            umma_tf32(tmem + (unsigned)(r * kTNc), umma_desc64(a0 + (ab * kRT + r) * kTQ * kRowB + ks * 32),
+                                      umma_desc64(b0 + s * kTNc * kRowB + ks * 32), kIdescTc, ks > 0);
+                        umma_commit(&tfull[r]);
+                    }
+                    umma_commit(&empty_b[s]);
+                    PROF(4);
+                }
+                umma_commit(&a_empty[ab]);  // the item's MMAs have read its query tiles
+            }
+            PROF_OUT(0, 5);
+        }
+      } else if (warp < kWarpProducer) {
+        // ---- converters: thread <-> points pt and pt + 128 of the 256-point tile; compact {x, y, z, n} -> 16 TF32 pieces in the
+        // operand row ----------------------------------------------------------------------------------------------------------
+        const int pt = (warp - kEpiWarps) * 32 + lane;
+        const unsigned sw = (unsigned)((pt >> 1) & 3);   // (pt + 128) has the same swizzle phase
+        unsigned h = 0, g = 0, it = 0;
+        PROF_DECL;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+            const int b = item / ipe, k = item - b * ipe;
+            const int ntiles = (k >= p.rbA ? p.NpA : p.NpB) / kTNc;
+            const unsigned ab = it & 1;
+            mbar_wait(&a_empty[ab], ((it >> 1) & 1) ^ 1);
+            for (int t = -1; t < ntiles; ++t, ++h) {
+                const unsigned cs = h % kCStages;
+                PROF(2);
+                mbar_wait(&cfull[cs], (h / kCStages) & 1);
+                PROF(0);
+                float4 v[2];
+                v[0] = s_c[cs * kTNc + pt];
+                v[1] = s_c[cs * kTNc + pt + 128];
+                // The compact slot is released only AFTER the stores below, which consume v: an mbarrier.arrive does not
+                // wait for an LDS in flight, and a 16-byte warp load executes in four quarter-warp passes — released right
+                // after the load, the slot was now and then refilled by the TMA before the last pass had read it (rows
+                // 24-31 of a tile then held the points of the tile one ring turn later).
+                unsigned char* dst;
+                unsigned s = 0;
+                if (t < 0) {
+                    // query role: rows 0..127 are row tile 0, rows 128..255 row tile 1 (contiguous 8 KB each)
+                    dst = s_a + ab * kRT * kTQ * kRowB + (unsigned)pt * kRowB;
+                } else {
+                    s = g % kStages;
+                    mbar_wait(&empty_b[s], ((g / kStages) & 1) ^ 1);
+                    PROF(1);
+                    dst = s_b + s * kTNc * kRowB + (unsigned)pt * kRowB;
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    float xh, xl, yh, yl, zh, zl, nh, nl;
+                    unsigned char* d = dst + u * 128 * kRowB;
+                    if (t < 0) {
+                        split_tf32(v[u].x, xh, xl); split_tf32(v[u].y, yh, yl); split_tf32(v[u].z, zh, zl); split_tf32(v[u].w, nh, nl);
+                        *reinterpret_cast<float4*>(d + ((0u ^ sw) << 4)) = make_float4(xh, xh, xl, xl);
+                        *reinterpret_cast<float4*>(d + ((1u ^ sw) << 4)) = make_float4(yh, yh, yl, yl);
+                        *reinterpret_cast<float4*>(d + ((2u ^ sw) << 4)) = make_float4(zh, zh, zl, zl);
+                        *reinterpret_cast<float4*>(d + ((3u ^ sw) << 4)) = make_float4(nh, nl, 1.0f, 1.0f);
+                    } else {
+                        split_tf32(-2.0f * v[u].x, xh, xl); split_tf32(-2.0f * v[u].y, yh, yl); split_tf32(-2.0f * v[u].z, zh, zl); split_tf32(v[u].w, nh, nl);
+                        *reinterpret_cast<float4*>(d + ((0u ^ sw) << 4)) = make_float4(xh, xl, xh, xl);
+                        *reinterpret_cast<float4*>(d + ((1u ^ sw) << 4)) = make_float4(yh, yl, yh, yl);
+                        *reinterpret_cast<float4*>(d + ((2u ^ sw) << 4)) = make_float4(zh, zl, zh, zl);
+                        *reinterpret_cast<float4*>(d + ((3u ^ sw) << 4)) = make_float4(1.0f, 1.0f, nh, nl);
+                    }
+                }
+                proxy_fence_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&cempty[cs]);
+                    mbar_arrive(t < 0 ? &a_full[ab] : &full_b[s]);
+                }
+                if (t >= 0) ++g;
+            }
+        }
+        if (warp == kEpiWarps && lane == 0) PROF_OUT(5, 3);
+      } else if (warp == kWarpPublisher) {
+        // ---- publisher: merges the four column quarters of every row, stores the row's locator triple, and raises the row
+        // tiles' completion flags — the device-wide fence and the atomics stay off the read-out warps' critical path --------
+        unsigned it = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+            const int b = item / ipe, k = item - b * ipe;
+            const bool dir = k >= p.rbA;
+            const int rb = dir ? k - p.rbA : k;
+            const unsigned pb = it & 1;
+            mbar_wait(&pub_full[pb], (it >> 1) & 1);
+            float4* out = p.rowfin + (size_t)b * (p.NpA + p.NpB) + (dir ? p.NpA : 0) + (size_t)rb * kItemRows;
+            const float4* src = s_pub + pb * kParts * kItemRows;
+#pragma unroll 2
+            for (int rin = lane; rin < kItemRows; rin += 32) {
+                float4 e = src[rin];
+#pragma unroll
+                for (int q = 1; q < kParts; ++q) {
+                    // disjoint chunk sets: b2 = minimum over every chunk other than the one holding the overall minimum (a tie
+                    // between quarters gives b2 == b1, i.e. an ambiguous row — which chunk c1 then names does not matter)
+                    const float4 o = src[q * kItemRows + rin];
+                    if (o.x < e.x) { e.y = fminf(e.x, o.y); e.x = o.x; e.z = o.z; }
+                    else e.y = fminf(e.y, o.x);
+                }
+                out[rin] = e;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&pub_empty[pb]);
+                // the read-out warps' supertile minima were stored before they arrived on pub_full (release / acquire at CTA
+                // scope); this fence is cumulative: they and this warp's rows are visible device-wide before the flags move
+                __threadfence();
+                atomicExch(p.done + (size_t)item * kRT, 4);
+                atomicExch(p.done + (size_t)item * kRT + 1, 4);
+            }
+            __syncwarp();
+        }
+      }
+    } else {
+        // the four read-out warpgroups take them: both tcgen05.ld of an accumulator quarter in flight = 64 registers of data
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
+        // ---- read-out: thread <-> (query row of BOTH row tiles, column quarter): TMEM lane quad*32 + lane, columns part*64 .. +63
+        // of whichever accumulator has been filled — all 16 warps pull a finished accumulator out together while the MMAs of
+        // the other row tile run ------------------------------------------------------------------------------------------------
+        const int quad = warp & 3, part = warp >> 2;
+        unsigned g = 0, it = 0;
+        PROF_DECL;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+            const int b = item / ipe, k = item - b * ipe;
+            const bool dir = k >= p.rbA;
+            const int rb = dir ? k - p.rbA : k;
+            const int npq = dir ? p.NpB : p.NpA, npc = dir ? p.NpA : p.NpB;
+            const int ntiles = npc / kTNc;
+            const int rin = quad * 32 + lane;               // row within its row tile
+            float* tm = p.tilemin + (size_t)kParts * ((size_t)b * ((size_t)p.nstB * p.NpA + (size_t)p.nstA * p.NpB) + (dir ? (size_t)p.nstB * p.NpA : 0)) +
+                        (size_t)rb * kItemRows + rin;
+            float b1[kRT], b2[kRT], stmin[kRT];
+            int c1[kRT];
+#pragma unroll
+            for (int r = 0; r < kRT; ++r) { b1[r] = INFINITY; b2[r] = INFINITY; stmin[r] = INFINITY; c1[r] = 0; }
+            for (int t = 0; t < ntiles; ++t, ++g) {
+#pragma unroll
+                for (int r = 0; r < kRT; ++r) {
+                    PROF(2);
+                    mbar_wait(&tfull[r], g & 1);
+                    PROF(0);
+                    tc_fence_after();
+                    const unsigned base = tmem + ((unsigned)(quad * 32) << 16) + (unsigned)(r * kTNc + part * (kTNc / kParts));
+                    // both 32-column loads of this quarter are issued before the (single) wait: one TMEM round trip per accumulator
+                    unsigned v[2][32];
+                    tmem_ld32_issue(base, v[0]);
+                    tmem_ld32_issue(base + 32, v[1]);
+                    tmem_ld_wait(v[0]);
+                    tmem_ld_wait(v[1]);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float m = min32(v[q]);
+                        const int chunk = t * (kTNc / kTcChunk) + part * (kTNc / kParts / kTcChunk) + q;
+                        b2[r] = fminf(b2[r], fmaxf(b1[r], m));
+                        c1[r] = m < b1[r] ? chunk : c1[r];        // strict: the EARLIEST chunk (of this quarter) that reaches the minimum
+                        b1[r] = fminf(b1[r], m);
+                        stmin[r] = fminf(stmin[r], m);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[r]);
+                    PROF(1);
+                }
+                if ((t & (kTilesPerSuper - 1)) == kTilesPerSuper - 1 || t == ntiles - 1) {
+#pragma unroll
+                    for (int r = 0; r < kRT; ++r) {
+                        tm[((size_t)(t / kTilesPerSuper) * kParts + part) * npq + r * kTQ] = stmin[r];
+                        stmin[r] = INFINITY;
+                    }
+                }
+            }
+            // hand the two rows' triples to the publisher (double-buffered by item parity)
+            const unsigned pb = it & 1;
+            mbar_wait(&pub_empty[pb], ((it >> 1) & 1) ^ 1);
+#pragma unroll
+            for (int r = 0; r < kRT; ++r)
+                s_pub[(pb * kParts + part) * kItemRows + r * kTQ + rin] = make_float4(b1[r], b2[r], __int_as_float(c1[r]), 0.f);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pub_full[pb]);
+        }
+        if ((warp == 0 || warp == 8) && lane == 0) PROF_OUT(8 + (warp >> 3) * 3, 3);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, kRT * kTNc); }
+}
+
+// ---- finalize: certify, re-evaluate exactly, reduce the loss -----------------------------------------------------------
+struct TcFinParams {
+    const float* A;
+    const float* Bp;
+    const float4* PA;
+    const float4* PB;
+    int B, N, M, NpA, NpB, rbA, rbB, nstA, nstB;
+    const float4* rowfin;
+    const float* tilemin;
+    const unsigned* maxn;   // [2][B]
+    const int* done;
+    int32_t* nnA;
+    int32_t* nnB;
+    double* partial;        // [nblocks]
+    int* hdr;               // kHdr*
+    float w1, w2;
+    double denomA, denomB;
+    float* loss;
+    float* terms;
+    ChamferPeerSum peer;
+};
+
+__global__ void __launch_bounds__(kFinT, 7) chamfer_tc_finalize_kernel(TcFinParams p) {
+    __shared__ double s_red[kFinT / 32];
+    __shared__ bool s_last;
+    constexpr int kMaxSel = 32;
+    __shared__ int s_sel[kMaxSel], s_nsel;
+    __shared__ unsigned s_amb[kFinT / 32], s_wd[kFinT / 32];
+    __shared__ int s_wj[kFinT / 32], s_iq[kFinT];
+    __shared__ float s_ilim[kFinT];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // block <-> row tile: (item, r) in the sweep's order, so that blocks become ready in the order they are resident
+    const int ipe = p.rbA + p.rbB;
+    const int item = (int)blockIdx.x / kRT, r = (int)blockIdx.x - item * kRT;
+    const int b = item / ipe, k = item - b * ipe;
+    const bool dir = k >= p.rbA;                       // false: rows of A search B; true: rows of B search A
+    const int rb = dir ? k - p.rbA : k;
+    const int Q = dir ? p.M : p.N, R = dir ? p.N : p.M;        // queries / searched points per element
+    const int npq = dir ? p.NpB : p.NpA;
+    const int nst = dir ? p.nstA : p.nstB;                      // supertiles of the searched cloud
+    const float* gQ = (dir ? p.Bp : p.A) + (size_t)b * Q * 3;
+    const float* gP = (dir ? p.A : p.Bp) + (size_t)b * R * 3;
+    const int q = rb * kItemRows + r * kTQ + tid;
+    const bool valid = q < Q;
+    double mine = 0.0;
+
+    if (tid == 0) {
+        const int* flag = p.done + (size_t)item * kRT + r;
+        while (ld_acquire_i32(flag) < 4) __nanosleep(200);
+    }
+    __syncthreads();
+
+    // ---- phase 1: certified or ambiguous --------------------------------------------------------------------------------
+    float qx = 0.f, qy = 0.f, qz = 0.f, best = 0.f, win = 0.f, errlim = 0.f;
+    int loc = 0;
+    bool amb = false;
+    if (valid) {
+        const float4 e = __ldcg(p.rowfin + (size_t)b * (p.NpA + p.NpB) + (dir ? p.NpA : 0) + q);
+        const float nq = __ldcg(&((dir ? p.PB : p.PA) + (size_t)b * npq + q)->w);
+        const float other = __uint_as_float(__ldcg(p.maxn + (size_t)(dir ? 0 : 1) * p.B + b));
+        qx = __ldg(gQ + 3 * (size_t)q); qy = __ldg(gQ + 3 * (size_t)q + 1); qz = __ldg(gQ + 3 * (size_t)q + 2);
+        best = fmaxf(e.x, 0.0f);
+        const float second = fmaxf(e.y, 0.0f);
+        loc = __float_as_int(e.z);
+        win = fmaf(kTcWinRel, best, kTcWinAbs * (nq + other));
+        errlim = kTcErrAbs * (nq + other);
+        // written so that NaN / inf / out-of-range norms can only make the row ambiguous, never certified
+        amb = !(nq <= kTcNormLimit && other <= kTcNormLimit && nq + other >= kTcNormFloor && second > best + win);
+    }
+
+    // ---- phase 2: certified rows — the 32 candidates of the located chunk, in the reference arithmetic -------------------
+    if (valid && !amb) {
+        float d = INFINITY;
+        int j = 0x7fffffff;
+        const int j0 = loc * kTcChunk, j1 = min(j0 + kTcChunk, R);
+        const float* pp = gP + 3 * (size_t)j0;
+        if (j0 + kTcChunk <= R && (reinterpret_cast<uintptr_t>(pp) & 15u) == 0) {
+#pragma unroll
+            for (int h = 0; h < kTcChunk / 8; ++h) {  // 8 candidates = six 16-byte loads per trip
+                float4 v[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(pp) + h * 6 + i);
+                const float c[24] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w, v[2].x, v[2].y, v[2].z, v[2].w,
+                                     v[3].x, v[3].y, v[3].z, v[3].w, v[4].x, v[4].y, v[4].z, v[4].w, v[5].x, v[5].y, v[5].z, v[5].w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    // operand order of the reference: (a - b) with a from the first cloud
+                    const float dd = dir ? sqdist3<false>(c[3 * u], c[3 * u + 1], c[3 * u + 2], qx, qy, qz)
+                                         : sqdist3<false>(qx, qy, qz, c[3 * u], c[3 * u + 1], c[3 * u + 2]);
+                    if (dd < d) { d = dd; j = j0 + h * 8 + u; }  // ascending candidates: '<' keeps the lowest index
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int jj = j0; jj < j1; ++jj) {
+                const float px = __ldg(gP + 3 * (size_t)jj), py = __ldg(gP + 3 * (size_t)jj + 1), pz = __ldg(gP + 3 * (size_t)jj + 2);
+                const float dd = dir ? sqdist3<false>(px, py, pz, qx, qy, qz) : sqdist3<false>(qx, qy, qz, px, py, pz);
+                if (dd < d) { d = dd; j = jj; }
+            }
+        }
+        // self-check of the error bound at the located minimum
+        if (!(fabsf(d - best) <= fmaf(kTcErrRel, d, errlim))) {
+            amb = true;
+            atomicAdd(p.hdr + kHdrViol, 1);
+        } else {
+            int32_t* nn = dir ? p.nnB : p.nnA;
+            if (nn) nn[(size_t)b * Q + q] = j;
+            mine += (double)d;
+        }
+    }
+
+    // ---- phase 3: ambiguous rows, one at a time, by the whole block: exact scan of every supertile within the window ---------
+    {
+        const unsigned ambmask = __ballot_sync(0xffffffffu, valid && amb);
+        if (lane == 0) s_amb[warp] = ambmask;
+        if (valid && amb) { s_iq[tid] = q; s_ilim[tid] = best + win; }
+        __syncthreads();
+        const float* tmb = p.tilemin + (size_t)kParts * ((size_t)b * ((size_t)p.nstB * p.NpA + (size_t)p.nstA * p.NpB) + (dir ? (size_t)p.nstB * p.NpA : 0));
+        for (int w = 0; w < kFinT / 32; ++w) {
+            const unsigned wmask = s_amb[w];
+            if (wmask && tid == 0) atomicAdd(p.hdr + kHdrAmb, __popc(wmask));
+            for (unsigned rem = wmask; rem; rem &= rem - 1) {
+                const int src = w * 32 + __ffs(rem) - 1;
+                const int qq = s_iq[src];
+                const float lim = s_ilim[src];  // NaN / inf -> scan everything (comparison below)
+                const float ax = __ldg(gQ + 3 * (size_t)qq), ay = __ldg(gQ + 3 * (size_t)qq + 1), az = __ldg(gQ + 3 * (size_t)qq + 2);
+                float d = INFINITY;
+                int j = 0x7fffffff;
+                if (tid == 0) s_nsel = 0;
+                __syncthreads();
+                for (int t0 = 0; t0 < nst; t0 += kFinT) {
+                    const int t = t0 + tid;
+                    if (t < nst) {
+                        float e1 = __ldcg(tmb + (size_t)t * kParts * npq + qq);   // the supertile's minimum: one partial per read-out group
+#pragma unroll
+                        for (int q4 = 1; q4 < kParts; ++q4) e1 = fminf(e1, __ldcg(tmb + ((size_t)t * kParts + q4) * npq + qq));
+                        if (!(fmaxf(e1, 0.0f) > lim)) {
+                            const int pos = atomicAdd(&s_nsel, 1);
+                            if (pos < kMaxSel) s_sel[pos] = t;
+                        }
+                    }
+                }
+                __syncthreads();
+                const int nsel = s_nsel;
+                const bool all = nsel > kMaxSel;   // tie-heavy input: more supertiles within the window than the list holds
+                const int total = all ? ((R + 3) & ~3) : nsel * kSuper;
+                for (int idx = 4 * tid; idx < total; idx += 4 * kFinT) {
+                    const int sidx = idx / kSuper, jb = all ? idx : s_sel[sidx] * kSuper + (idx - sidx * kSuper);
+                    if (jb >= R) continue;
+                    const float* pp = gP + 3 * (size_t)jb;
+                    float c[12];
+                    if (jb + 4 <= R && (reinterpret_cast<uintptr_t>(pp) & 15u) == 0) {
+                        const float4 v0 = __ldg(reinterpret_cast<const float4*>(pp));
+                        const float4 v1 = __ldg(reinterpret_cast<const float4*>(pp) + 1);
+                        const float4 v2 = __ldg(reinterpret_cast<const float4*>(pp) + 2);
+                        c[0] = v0.x; c[1] = v0.y; c[2] = v0.z; c[3] = v0.w; c[4] = v1.x; c[5] = v1.y;
+                        c[6] = v1.z; c[7] = v1.w; c[8] = v2.x; c[9] = v2.y; c[10] = v2.z; c[11] = v2.w;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int jj = min(jb + u, R - 1);  // clamped duplicates are harmless (same value, same index)
+                            c[3 * u] = __ldg(gP + 3 * (size_t)jj); c[3 * u + 1] = __ldg(gP + 3 * (size_t)jj + 1); c[3 * u + 2] = __ldg(gP + 3 * (size_t)jj + 2);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float dd = dir ? sqdist3<false>(c[3 * u], c[3 * u + 1], c[3 * u + 2], ax, ay, az)
+                                             : sqdist3<false>(ax, ay, az, c[3 * u], c[3 * u + 1], c[3 * u + 2]);
+                        const int jj = min(jb + u, R - 1);
+                        if (dd < d || (dd == d && jj < j)) { d = dd; j = jj; }
+                    }
+                }
+                // (d, j) minimum over the block, lowest j on ties (d >= 0 or +inf: bit order == value order)
+                const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(d));
+                const int jm = __reduce_min_sync(0xffffffffu, (__float_as_uint(d) == mb) ? j : 0x7fffffff);
+                if (lane == 0) { s_wd[warp] = mb; s_wj[warp] = jm; }
+                __syncthreads();
+                if (tid == src) {
+                    unsigned bd = s_wd[0];
+                    int bj = s_wj[0];
+#pragma unroll
+                    for (int u = 1; u < kFinT / 32; ++u) {
+                        const unsigned od = s_wd[u];
+                        const int oj = s_wj[u];
+                        if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+                    }
+                    int32_t* nn = dir ? p.nnB : p.nnA;
+                    if (nn) nn[(size_t)b * Q + qq] = bj;
+                    mine += (double)__uint_as_float(bd);
+                }
+                __syncthreads();  // s_wd / s_wj / s_nsel are reused by the next row
+            }
+        }
+    }
+
+    // ---- block partial sum -> the last block reduces in a fixed order (bitwise repeatable) ---------------------------------
+    mine = warp_sum(mine);
+    if (lane == 0) s_red[warp] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < kFinT / 32; ++w) s += s_red[w];
+        p.partial[blockIdx.x] = s;
+        __threadfence();
+        s_last = (atomicAdd(p.hdr + kHdrDone, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double sa = 0.0, sb = 0.0;
+    for (int kk = tid; kk < (int)gridDim.x; kk += kFinT) {
+        const double v = __ldcg(p.partial + kk);
+        if ((kk / kRT) % ipe < p.rbA) sa += v; else sb += v;
+    }
+    sa = warp_sum(sa);
+    sb = warp_sum(sb);
+    __shared__ double s_a2[kFinT / 32], s_b2[kFinT / 32];
+    if (lane == 0) { s_a2[warp] = sa; s_b2[warp] = sb; }
+    __syncthreads();
+    if (tid == 0) {
+        double ta = 0.0, tb = 0.0;
+        for (int w = 0; w < kFinT / 32; ++w) { ta += s_a2[w]; tb += s_b2[w]; }
+        const float dAB = (float)(ta / p.denomA), dBA = (float)(tb / p.denomB);  // pcloud.jl:47-48
+        if (p.terms) { p.terms[0] = dAB; p.terms[1] = dBA; }
+        const float l = __fadd_rn(__fmul_rn(p.w1, dAB), __fmul_rn(p.w2, dBA));   // pcloud.jl:50
+        if (p.peer.nranks <= 1) p.loss[0] = l;
+        s_a2[0] = (double)l;
+    }
+    if (p.peer.nranks <= 1) return;
+    // the one exchange of the sharded path, fused (see chamfer.cu: chamfer_filter_finalize_kernel)
+    __shared__ float s_v[kMaxPeerRanks];
+    __syncthreads();
+    if (tid < p.peer.nranks) s_v[tid] = peer_exchange(p.peer, tid, (float)s_a2[0]);
+    __syncthreads();
+    if (tid == 0) {
+        float sum = 0.0f;
+        for (int rr = 0; rr < p.peer.nranks; ++rr) sum = __fadd_rn(sum, s_v[rr]);
+        p.loss[0] = sum;
+    }
+}
+
+struct TcPlan {
+    int NpA, NpB, rbA, rbB, nstA, nstB, nblocks;
+    size_t off_PA, off_PB, off_rowfin, off_tilemin, off_partial, zero_from, off_hdr, off_maxn, off_done, zero_bytes, total;
+};
+
+TcPlan make_tc_plan(int B, int N, int M) {
+    TcPlan pl;
+    pl.NpA = (int)align_up((size_t)N, kItemRows);
+    pl.NpB = (int)align_up((size_t)M, kItemRows);
+    pl.rbA = pl.NpA / kItemRows;
+    pl.rbB = pl.NpB / kItemRows;
+    pl.nstA = (pl.NpA + kSuper - 1) / kSuper;
+    pl.nstB = (pl.NpB + kSuper - 1) / kSuper;
+    pl.nblocks = B * (pl.rbA + pl.rbB) * kRT;
+    size_t o = 0;
+    pl.off_hdr = o;     o = align_up(o + sizeof(int) * kHdrInts, 256);   // diagnostics first: a caller can find them
+    pl.off_maxn = o;    o = align_up(o + sizeof(unsigned) * 2 * (size_t)B, 256);
+    pl.off_done = o;    o = align_up(o + sizeof(int) * (size_t)pl.nblocks, 256);
+    pl.zero_from = 0;
+    pl.zero_bytes = o;  // header, norm maxima and completion counters are zeroed by ONE memset per call
+    pl.off_PA = o;      o = align_up(o + sizeof(float4) * (size_t)B * pl.NpA, 256);
+    pl.off_PB = o;      o = align_up(o + sizeof(float4) * (size_t)B * pl.NpB, 256);
+    pl.off_rowfin = o;  o = align_up(o + sizeof(float4) * (size_t)B * (pl.NpA + pl.NpB), 256);
+    pl.off_tilemin = o; o = align_up(o + sizeof(float) * kParts * (size_t)B * ((size_t)pl.nstB * pl.NpA + (size_t)pl.nstA * pl.NpB), 256);
+    pl.off_partial = o; o = align_up(o + sizeof(double) * (size_t)pl.nblocks, 256);
+    pl.total = o;
+    return pl;
+}
+
+constexpr size_t kTcSmem = 2 * kRT * kTQ * kRowB + kStages * kTNc * kRowB + kCStages * kTNc * 16 + 2 * kParts * kItemRows * 16 + 1024;  // 129 KB
+
+}  // namespace
+
+size_t chamfer_tc_workspace_bytes(int B, int N, int M) { return make_tc_plan(B, N, M).total; }
+#ifdef F3D_TC_PROF
+extern "C" __attribute__((visibility("default"))) int f3d_debug_read_tc(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, g_tcprof, nbytes); }
+#endif
+
+// The tensor-core sweep wants enough 256-row work items to keep every SM's pipeline full for a few items; smaller problems
+// stay on the CUDA-core sweep of chamfer.cu (one tile per CTA fills the machine from 592 tiles of 256 x 1024 pairs on).
+bool chamfer_tc_supported(int B, int N, int M) {
+    if (B <= 0 || N < 1 || M < 1) return false;
+    const TcPlan pl = make_tc_plan(B, N, M);
+    if ((long long)B * (pl.rbA + pl.rbB) * kRT > 0x3fffffffLL) return false;
+    return (long long)B * (pl.rbA + pl.rbB) >= 2 * 148 && std::min(N, M) >= 512;
+}
+
+int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M, float w1, float w2, int32_t B_total,
+                          float* loss_dev, float* terms_dev, int32_t* nnA_dev, int32_t* nnB_dev, void* ws, size_t ws_bytes, int32_t flags,
+                          cudaStream_t stream, const ChamferPeerSum* peer) {
+    const TcPlan pl = make_tc_plan(B, N, M);
+    if (!ws || ws_bytes < pl.total) return fail(F3D_ERR_WORKSPACE, "f3d_chamfer_fwd: workspace %zu < required %zu bytes", ws_bytes, pl.total);
+    unsigned char* w = static_cast<unsigned char*>(ws);
+    int dev = 0;
+    F3D_CUDA(cudaGetDevice(&dev));
+    static unsigned char attr_done[256];
+    static int sm_count[256];
+    if (dev < 0 || dev >= 256 || !attr_done[dev]) {
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        // the finalize blocks must fit beside a sweep CTA: with the smallest carveout that holds the sweep (132 KB for its
+        // 130 KB) no finalize block (2.5 KB of shared memory) finds room, and the whole finalize runs after the sweep
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        int sms = 0;
+        F3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 256) { sm_count[dev] = sms; attr_done[dev] = 1; }
+    }
+    const int sms = (dev >= 0 && dev < 256 && sm_count[dev] > 0) ? sm_count[dev] : 148;
+    F3D_CUDA(cudaMemsetAsync(w + pl.zero_from, 0, pl.zero_bytes, stream));
+
+    TcPrepParams pp;
+    pp.A = A; pp.Bp = Bp; pp.N = N; pp.M = M; pp.NpA = pl.NpA; pp.NpB = pl.NpB;
+    pp.PA = reinterpret_cast<float4*>(w + pl.off_PA);
+    pp.PB = reinterpret_cast<float4*>(w + pl.off_PB);
+    pp.maxn = reinterpret_cast<unsigned*>(w + pl.off_maxn);
+    chamfer_tc_prepare_kernel<<<dim3((std::max(pl.NpA, pl.NpB) + kPrepT - 1) / kPrepT, B, 2), kPrepT, 0, stream>>>(pp);
+    F3D_CHECK_LAUNCH("chamfer_tc_prepare_kernel");
+
+    TcSweepParams sp;
+    sp.PA = pp.PA; sp.PB = pp.PB; sp.B = B; sp.NpA = pl.NpA; sp.NpB = pl.NpB; sp.rbA = pl.rbA; sp.rbB = pl.rbB;
+    sp.rowfin = reinterpret_cast<float4*>(w + pl.off_rowfin);
+    sp.tilemin = reinterpret_cast<float*>(w + pl.off_tilemin);
+    sp.nstA = pl.nstA; sp.nstB = pl.nstB;
+    sp.done = reinterpret_cast<int*>(w + pl.off_done);
+    sp.wait_prepare = 1;
+    const int nitems = B * (pl.rbA + pl.rbB);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(std::min(nitems, sms)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kTcSmem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_tc_sweep_kernel, sp));
+    }
+    F3D_CHECK_LAUNCH("chamfer_tc_sweep_kernel");
+    if (flags & F3D_FLAG_SWEEP_ONLY) return F3D_OK;
+
+    TcFinParams fp;
+    fp.A = A; fp.Bp = Bp; fp.PA = pp.PA; fp.PB = pp.PB;
+    fp.B = B; fp.N = N; fp.M = M; fp.NpA = pl.NpA; fp.NpB = pl.NpB; fp.rbA = pl.rbA; fp.rbB = pl.rbB; fp.nstA = pl.nstA; fp.nstB = pl.nstB;
+    fp.rowfin = sp.rowfin; fp.tilemin = sp.tilemin; fp.maxn = pp.maxn; fp.done = sp.done;
+    fp.nnA = nnA_dev; fp.nnB = nnB_dev;
+    fp.partial = reinterpret_cast<double*>(w + pl.off_partial);
+    fp.hdr = reinterpret_cast<int*>(w + pl.off_hdr);
+    fp.w1 = w1; fp.w2 = w2;
+    fp.denomA = (double)N * (double)B_total;
+    fp.denomB = (double)M * (double)B_total;
+    fp.loss = loss_dev; fp.terms = terms_dev;
+    if (peer) fp.peer = *peer;
+    else { fp.peer.mailboxes = nullptr; fp.peer.nranks = 0; fp.peer.rank = 0; fp.peer.seq = 0; fp.peer.timeout_ns = 0; fp.peer.fault = nullptr; }
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(pl.nblocks); cfg.blockDim = dim3(kFinT); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+#ifdef F3D_TC_EXP_ENV
+        if (getenv("F3D_TC_NOPDL")) attr[0].val.programmaticStreamSerializationAllowed = 0;  // development: finalize strictly after the sweep
+#endif
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_tc_finalize_kernel, fp));
+    }
+    F3D_CHECK_LAUNCH("chamfer_tc_finalize_kernel");
+    return F3D_OK;
+}
+
+}  // namespace f3d

@@ -6,6 +6,7 @@
 // soname returns that same copy.
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "f3d_common.cuh"
@@ -72,6 +73,9 @@ struct Comm {
     unsigned long long** mailboxes_dev = nullptr; // device array [nranks]: every rank's mailbox as this device addresses it
     void* opened[kMaxPeerRanks] = {};             // cudaIpcOpenMemHandle mappings to close
     unsigned seq = 0;                             // steps issued so far (the same on every rank: collective calls only)
+    unsigned* fault_host = nullptr;               // page-locked, device-mapped: the step number whose exchange timed out (0 = none)
+    unsigned* fault_dev = nullptr;                // the same word as the device addresses it
+    unsigned long long timeout_ns = 0;            // deadline of one exchange; 0 = wait for ever
 };
 
 }  // namespace
@@ -116,15 +120,27 @@ extern "C" int32_t f3d_allreduce_sum_f32(void* comm, float* dev_buf, int32_t cou
     return F3D_OK;
 }
 
-bool f3d::comm_next_peer_sum(void* comm, ChamferPeerSum* out) {
+bool f3d::comm_peek_peer_sum(void* comm, ChamferPeerSum* out) {
     Comm* h = static_cast<Comm*>(comm);
-    if (!h || !h->mailboxes_dev) return false;
+    if (!h || !h->mailboxes_dev) {
+        set_error("communicator has no peer mailboxes (call f3d_comm_enable_p2p)");
+        return false;
+    }
+    if (h->fault_host && *reinterpret_cast<volatile unsigned*>(h->fault_host) != 0u) {
+        set_error("the fused cross-rank sum of step %u timed out (a peer never delivered its loss): the communicator is dead, the loss of that step was NaN",
+                  *reinterpret_cast<volatile unsigned*>(h->fault_host));
+        return false;
+    }
     out->mailboxes = h->mailboxes_dev;
     out->nranks = h->nranks;
     out->rank = h->rank;
-    out->seq = ++h->seq;  // 1, 2, ...: never 0, the value the mailboxes start with
+    out->seq = h->seq + 1;  // 1, 2, ...: never 0, the value the mailboxes start with
+    out->timeout_ns = h->timeout_ns;
+    out->fault = h->fault_dev;
     return true;
 }
+
+void f3d::comm_commit_peer_sum(void* comm) { ++static_cast<Comm*>(comm)->seq; }
 
 // Peer mailboxes: every rank allocates 2 x nranks 8-byte words, exports them with CUDA IPC, gathers everybody's handle
 // over the existing NCCL communicator and maps the peers' mailboxes (NVLink peer access).  Collective; off the hot path.
@@ -137,12 +153,24 @@ extern "C" int32_t f3d_comm_enable_p2p(void* comm, f3d_stream_t stream_) {
     if (h->nranks > kMaxPeerRanks) return fail(F3D_ERR_INVALID, "f3d_comm_enable_p2p: at most %d ranks", kMaxPeerRanks);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    {
+        // how long one exchange waits for a late peer before it gives up and marks the communicator dead: long enough for
+        // every routine stall (module load, checkpoint, evaluation on one rank); F3D_PEER_TIMEOUT_S = 0 waits for ever
+        double secs = 1800.0;
+        if (const char* env = getenv("F3D_PEER_TIMEOUT_S")) secs = atof(env);
+        h->timeout_ns = secs > 0.0 ? (unsigned long long)(secs * 1e9) : 0ull;
+    }
     // A rank whose LOCAL step fails must still take part in both collectives (with an all-zero handle / a zero vote):
     // otherwise its peers would wait in NCCL for ever.  Every rank then returns the same verdict.
     const size_t words = 2 * (size_t)h->nranks;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->mailbox), words * sizeof(unsigned long long));
+    cudaError_t e = cudaSuccess;
+    if (!h->fault_host) {
+        e = cudaHostAlloc(reinterpret_cast<void**>(&h->fault_host), 64, cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e == cudaSuccess) { *h->fault_host = 0u; e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->fault_dev), h->fault_host, 0); }
+    }
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mailbox), words * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(h->mailbox, 0, words * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mine, h->mailbox);
     if (e != cudaSuccess) { memset(&mine, 0, sizeof(mine)); cudaGetLastError(); }
@@ -200,11 +228,14 @@ extern "C" int32_t f3d_chamfer_fwd_allreduce(void* comm, const float* A, const f
                                              float w2, int32_t B_total, float* loss_dev, int32_t* nnA_dev, int32_t* nnB_dev,
                                              void* ws, size_t ws_bytes, int32_t flags, f3d_stream_t stream_) {
     if (!comm) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd_allreduce: null communicator");
-    if (flags != F3D_FLAG_NONE) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd_allreduce: only the default sweep has the fused cross-rank sum");
+    if (flags & ~F3D_FLAG_CUDA_CORES) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd_allreduce: only the default sweeps have the fused cross-rank sum");
     ChamferPeerSum peer;
-    if (!comm_next_peer_sum(comm, &peer)) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd_allreduce: communicator has no peer mailboxes (call f3d_comm_enable_p2p)");
-    return chamfer_fwd_launch(A, Bp, B, N, M, w1, w2, B_total, loss_dev, nullptr, nnA_dev, nnB_dev, ws, ws_bytes, flags,
-                              static_cast<cudaStream_t>(stream_), nullptr, &peer);
+    if (!comm_peek_peer_sum(comm, &peer)) return F3D_ERR_NCCL;  // the error string is set
+    // validate and launch first; the step number advances only once the finalize that sends this rank's word is in the stream
+    const int32_t rc = chamfer_fwd_launch(A, Bp, B, N, M, w1, w2, B_total, loss_dev, nullptr, nnA_dev, nnB_dev, ws, ws_bytes, flags,
+                                          static_cast<cudaStream_t>(stream_), nullptr, &peer);
+    if (rc == F3D_OK) comm_commit_peer_sum(comm);
+    return rc;
 }
 
 extern "C" int32_t f3d_comm_destroy(void* comm) {
@@ -215,6 +246,7 @@ extern "C" int32_t f3d_comm_destroy(void* comm) {
         if (h->opened[r]) cudaIpcCloseMemHandle(h->opened[r]);
     if (h->mailboxes_dev) cudaFree(h->mailboxes_dev);
     if (h->mailbox) cudaFree(h->mailbox);
+    if (h->fault_host) cudaFreeHost(h->fault_host);
     int rc = api ? api->comm_destroy(h->nccl_comm) : 0;
     delete h;
     if (rc != 0) return nccl_fail(api, rc, "ncclCommDestroy");

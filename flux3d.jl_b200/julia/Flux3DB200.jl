@@ -2,7 +2,9 @@
 # CuArray{Float32} storage and `ccall` libflux3d_b200.so (include/flux3d_b200.h).
 #
 # STATUS: written against Flux3D v0.1.6 + CUDA.jl, NOT executed — the build image has no Julia
-# (SURVEY.md §0 fact 2).  The same C symbols are exercised from Python/ctypes by tests/ and bench.py.
+# (SURVEY.md §0 fact 2).  The same C symbols are exercised from Python/ctypes by tests/ and bench.py, and
+# tests/test_julia_shim.py checks every ccall in this file (symbol, return type, argument count and C types) against
+# include/flux3d_b200.h — the only verification possible without a Julia binary.
 #
 # Usage (a maintainer adds ONE line to src/Flux3D.jl after the includes):
 #     include(joinpath(ENV["FLUX3D_B200_HOME"], "julia", "Flux3DB200.jl"))
@@ -10,7 +12,7 @@
 # so no copies or permutes are made.  Indices come back 0-based Int32; +1 is applied here.
 module Flux3DB200
 
-using CUDA, Zygote
+using CUDA, Zygote, NNlib
 import Flux3D
 import Flux3D: TriMesh, PointCloud, get_verts_packed, get_verts_padded, get_faces_packed, get_faces_padded
 
@@ -73,7 +75,10 @@ Zygote.@adjoint function Flux3D._chamfer_distance(A::CuArray{Float32,3}, B::CuAr
 end
 
 # ---- chamfer_distance on host Arrays (src/metrics/pcloud.jl:28-37 called with `Array`s) -----------------------
-# One C call: the sweep grid pulls the (page-locked) arrays over PCIe itself and stores the loss into mapped host memory.
+# OPT-IN: Flux3D.chamfer_distance(::Array, ::Array) itself is NOT overridden — the reference's CPU method keeps working
+# (and stays differentiable on the CPU, test/metrics.jl:112-114) on machines without a B200.  A caller who wants host
+# arrays swept on the GPU calls Flux3DB200.chamfer_distance_host: one C call, the sweep grid pulls the page-locked arrays
+# over PCIe itself and stores the loss into mapped host memory.  Page-lock ONCE, outside the hot loop, with pin_host!.
 const _pipe = Ref{Ptr{Cvoid}}(C_NULL)
 function pipe_handle()
     if _pipe[] == C_NULL
@@ -82,12 +87,12 @@ function pipe_handle()
     return _pipe[]
 end
 
-function Flux3D.chamfer_distance(A::Array{Float32,3}, B::Array{Float32,3}; w1::Number = 1.0, w2::Number = 1.0)
+pin_host!(A::Array{Float32,3}) = (CUDA.pin(A); A)   # cudaHostRegister: lets the device read the array in place
+
+function chamfer_distance_host(A::Array{Float32,3}, B::Array{Float32,3}; w1::Number = 1.0, w2::Number = 1.0)
     (_, N, Bn) = size(A); M = size(B, 2)
     size(B, 3) == Bn || error("batch sizes differ: $Bn vs $(size(B, 3))")
-    # page-lock once per array (no-op if already pinned): lets the device read the arrays in place.  Pageable arrays also
-    # work — the library then copies them with cudaMemcpyAsync first.
-    CUDA.pin(A); CUDA.pin(B)
+    # pageable arrays also work — the library then copies them with cudaMemcpyAsync first
     nbytes = ccall((:f3d_chamfer_pipe_workspace_bytes, LIB), Csize_t, (Int32, Int32, Int32), Bn, N, M)
     ws = workspace((:chamfer_pipe, Bn, N, M), nbytes)
     out = Ref{Float32}(0f0)
@@ -133,14 +138,18 @@ function Flux3D._nearest_neighbors(x::CuArray{Float32,3}, y::CuArray{Float32,3})
 end
 
 # ---- kNN graph: replaces CreateSingleKNNGraph / the EdgeConv prologue (src/models/dgcnn.jl:3-9, 32-45) ----
-function knn_graph(X::CuArray{Float32,3}, K::Int; gathered = false, edge = false)
+const FLAG_EDGE_MLP_LAYOUT = Int32(32)
+function knn_graph(X::CuArray{Float32,3}, K::Int; gathered = false, edge = false, mlp_layout = false)
     (F, N, Bn) = size(X)
     idx = CuArray{Int32}(undef, K, N, Bn)
     G = gathered ? CuArray{Float32}(undef, F, K, N, Bn) : nothing
-    E = edge ? CuArray{Float32}(undef, 2F, K, N, Bn) : nothing
+    # edge features: (2F, K, N, B) == cat(X, KNNGraph - X; dims=1) (:45), or — mlp_layout — already permuted and reshaped to
+    # the (K*N, 2F, B) array the Conv1x1 MLP consumes (:46-52): C [B][2F][N][K]
+    E = edge ? (mlp_layout ? CuArray{Float32}(undef, K * N, 2F, Bn) : CuArray{Float32}(undef, 2F, K, N, Bn)) : nothing
     check(ccall((:f3d_knn_graph, LIB), Int32,
         (Ptr{Float32}, Int32, Int32, Int32, Int32, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Cvoid}, Csize_t, Int32, Ptr{Cvoid}),
-        devptr(X), Bn, N, F, K, devptr(idx), C_NULL, gathered ? devptr(G) : C_NULL, edge ? devptr(E) : C_NULL, C_NULL, 0, 0, cur_stream()))
+        devptr(X), Bn, N, F, K, devptr(idx), C_NULL, gathered ? devptr(G) : C_NULL, edge ? devptr(E) : C_NULL, C_NULL, 0,
+        (edge && mlp_layout) ? FLAG_EDGE_MLP_LAYOUT : Int32(0), cur_stream()))
     return idx, G, E
 end
 
@@ -148,11 +157,34 @@ Flux3D.CreateSingleKNNGraph(X::CuArray{Float32,2}, K::Int) =
     dropdims(knn_graph(reshape(X, size(X, 1), size(X, 2), 1), K; gathered = true)[2]; dims = 4)
 Zygote.@nograd knn_graph
 
-# EdgeConv on device arrays: the prologue (:36-45) is one kernel; the MLP/MaxPool tail (:46-61) is unchanged.
+# (K*N, 2F, B) edge features from X and the (constant) neighbour indices.  Differentiable in X like the reference, where
+# only CreateSingleKNNGraph is @nograd (:9) and X flows through cat(X, KNNGraph - X) (:39-45):
+#   E[(k,n), c, b]     = X[c, n, b]                      (c <= F)
+#   E[(k,n), F + c, b] = X[c, idx[k,n,b], b] - X[c, n, b]
+edge_features_mlp(X::CuArray{Float32,3}, K::Int) = knn_graph(X, K; edge = true, mlp_layout = true)[3]
+Zygote.@adjoint function edge_features_mlp(X::CuArray{Float32,3}, K::Int)
+    (F, N, Bn) = size(X)
+    idx, _, E = knn_graph(X, K; edge = true, mlp_layout = true)
+    function back(g)
+        g4 = reshape(CuArray{Float32}(g), K, N, 2F, Bn)                    # (k, n, c, b)
+        gc = permutedims(dropdims(sum(g4[:, :, 1:F, :]; dims = 1); dims = 1), (2, 1, 3))          # centre halves: (F, N, B)
+        gd = g4[:, :, F+1:2F, :]                                            # (k, n, c, b): gradient of x_j - x_i
+        gX = gc .- permutedims(dropdims(sum(gd; dims = 1); dims = 1), (2, 1, 3))
+        # scatter-add of the neighbour halves: gX[:, idx[k,n,b], b] += gd[k, n, :, b]
+        lin = vec(Int.(idx) .+ 1 .+ reshape((0:Bn-1) .* N, 1, 1, Bn))                              # (K*N*B,) columns of reshape(gX, F, N*B)
+        vals = reshape(permutedims(gd, (3, 1, 2, 4)), F, K * N * Bn)
+        gXf = reshape(gX, F, N * Bn)
+        NNlib.scatter!(+, gXf, vals, lin)
+        return (reshape(gXf, F, N, Bn), nothing)
+    end
+    return E, back
+end
+
+# EdgeConv on device arrays: the prologue AND the permute/reshape (:36-52) are one kernel — the (K*N, 2F, B) array is
+# written once, in the layout the MLP reads; the MLP/MaxPool tail (:54-68) is unchanged.
 function (m::Flux3D.EdgeConv)(X::CuArray{Float32,3})
     F, N, B = size(X)
-    E = Zygote.ignore(() -> knn_graph(X, m.K; edge = true)[3])      # (2F, K, N, B) == cat(X, KNNGraph - X; dims=1)
-    Xe = reshape(PermutedDimsArray(E, (2, 3, 1, 4)), N * m.K, 2F, B)
+    Xe = edge_features_mlp(X, m.K)
     Xe = m.mlp(Xe)
     an = size(Xe, 2)
     Xe = reshape(Xe, m.K, an * N, B)
@@ -186,9 +218,11 @@ function topology(m::TriMesh)
     end
 end
 
-# laplacian_loss — src/metrics/mesh.jl:9-15 (the reference copies verts to the host and runs a CPU SpMM)
-function Flux3D.laplacian_loss(m::TriMesh{Float32,R,CuArray}) where {R}
-    t = topology(m); verts = get_verts_packed(m); nV = size(verts, 2)
+# laplacian_loss — src/metrics/mesh.jl:9-15 (the reference copies verts to the host and runs a CPU SpMM).  The kernel works on
+# the packed verts; get_verts_packed stays on the Zygote tape (examples/fit_mesh.jl:78-84 differentiates through it), the
+# array-level function below carries the adjoint.
+function _laplacian_loss_dev(verts::CuArray{Float32,2}, t::Topology)
+    nV = size(verts, 2)
     ws = workspace((:lap, nV), ccall((:f3d_laplacian_workspace_bytes, LIB), Csize_t, (Int32,), nV))
     loss = CUDA.zeros(Float32, 1)
     check(ccall((:f3d_laplacian_loss, LIB), Int32,
@@ -196,6 +230,55 @@ function Flux3D.laplacian_loss(m::TriMesh{Float32,R,CuArray}) where {R}
         devptr(verts), devptr(t.rowptr), devptr(t.colidx), devptr(t.vals), nV, 0, devptr(loss), devptr(ws), length(ws), cur_stream()))
     return CUDA.@allowscalar loss[1]
 end
+Zygote.@adjoint function _laplacian_loss_dev(verts::CuArray{Float32,2}, t::Topology)
+    function back(g)
+        nV = size(verts, 2)
+        ws = workspace((:lap, nV), ccall((:f3d_laplacian_workspace_bytes, LIB), Csize_t, (Int32,), nV))
+        gout = CuArray(Float32[g]); gv = similar(verts)
+        check(ccall((:f3d_laplacian_loss_bwd, LIB), Int32,
+            (Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Int32, Int32, Ptr{Float32}, Ptr{Float32}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+            devptr(verts), devptr(t.rowptr), devptr(t.colidx), devptr(t.vals), nV, 0, devptr(gout), devptr(gv), devptr(ws), length(ws), cur_stream()))
+        return (gv, nothing)
+    end
+    return _laplacian_loss_dev(verts, t), back
+end
+Flux3D.laplacian_loss(m::TriMesh{Float32,R,CuArray}) where {R} =
+    _laplacian_loss_dev(get_verts_packed(m), Zygote.ignore(() -> topology(m)))
+
+# edge_loss — src/metrics/mesh.jl:24-32: mean_e (|v_e1 - v_e2| - target)^2 over the unique edges
+function _edge_loss_dev(verts::CuArray{Float32,2}, t::Topology, target::Float32)
+    ws = workspace((:edge, t.nE), ccall((:f3d_edge_loss_workspace_bytes, LIB), Csize_t, (Int32,), t.nE))
+    loss = CUDA.zeros(Float32, 1)
+    check(ccall((:f3d_edge_loss, LIB), Int32,
+        (Ptr{Float32}, Ptr{Int32}, Int32, Int32, Float32, Ptr{Float32}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        devptr(verts), devptr(t.edges), t.nE, 0, target, devptr(loss), devptr(ws), length(ws), cur_stream()))
+    return CUDA.@allowscalar loss[1]
+end
+Zygote.@adjoint function _edge_loss_dev(verts::CuArray{Float32,2}, t::Topology, target::Float32)
+    function back(g)
+        gout = CuArray(Float32[g]); gv = similar(verts)
+        check(ccall((:f3d_edge_loss_bwd, LIB), Int32,
+            (Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Int32, Int32, Float32, Ptr{Float32}, Ptr{Float32}, Ptr{Cvoid}),
+            devptr(verts), devptr(t.rowptr), devptr(t.colidx), size(verts, 2), t.nE, target, devptr(gout), devptr(gv), cur_stream()))
+        return (gv, nothing, nothing)
+    end
+    return _edge_loss_dev(verts, t, target), back
+end
+Flux3D.edge_loss(m::TriMesh{Float32,R,CuArray}, target_length::Number = 0.0) where {R} =
+    _edge_loss_dev(get_verts_packed(m), Zygote.ignore(() -> topology(m)), Float32(target_length))
+
+# compute_faces_normals_packed / compute_faces_areas_packed — src/rep/mesh.jl:689-700, 765-780: one launch for both
+function faces_areas_normals(m::TriMesh{Float32,R,CuArray}; areas::Bool, normals::Bool) where {R}
+    t = topology(m); verts = get_verts_packed(m); nF = size(t.faces, 2)
+    a = areas ? CuArray{Float32}(undef, nF) : nothing
+    n = normals ? CuArray{Float32}(undef, 3, nF) : nothing
+    check(ccall((:f3d_faces_areas_normals, LIB), Int32,
+        (Ptr{Float32}, Ptr{Int32}, Int32, Int32, Ptr{Float32}, Ptr{Float32}, Ptr{Cvoid}),
+        devptr(verts), devptr(t.faces), size(verts, 2), nF, areas ? devptr(a) : C_NULL, normals ? devptr(n) : C_NULL, cur_stream()))
+    return a, n
+end
+Flux3D.compute_faces_normals_packed(m::TriMesh{Float32,R,CuArray}) where {R} = faces_areas_normals(m; areas = false, normals = true)[2]
+Flux3D.compute_faces_areas_packed(m::TriMesh{Float32,R,CuArray}; eps::Number = 1e-6) where {R} = faces_areas_normals(m; areas = true, normals = false)[1]
 
 # compute_verts_normals_packed — src/rep/mesh.jl:589-618.  mode 0 = what the reference computes on the CPU
 # (last face per corner slot), mode 1 = what its docstring says (sum over incident faces).
@@ -207,21 +290,46 @@ function Flux3D.compute_verts_normals_packed(m::TriMesh{Float32,R,CuArray}; mode
     return out
 end
 
-# sample_points — src/transforms/mesh_func.jl:21-58: one launch for the whole batch, device RNG (Philox)
-function Flux3D.sample_points(m::TriMesh{Float32,R,CuArray}, num_samples::Int = 5000; eps::Number = 1e-6,
-                              seed::UInt64 = rand(UInt64), offset::UInt64 = UInt64(0)) where {R}
-    verts = get_verts_padded(m)                                           # (3, V, N)
-    faces = CuArray(Int32.(get_faces_padded(m)) .- Int32(1))              # (3, F, N) local ids, pad = -1
-    vlen = CuArray(Int32.(m._verts_len)); flen = CuArray(Int32.(m._faces_len))
-    samples = similar(verts, 3, num_samples, m.N)
-    nws = ccall((:f3d_sample_points_workspace_bytes, LIB), Csize_t, (Int32, Int32), m.N, m.F)
-    ws = workspace((:sample, m.N, m.F), nws)
+# sample_points — src/transforms/mesh_func.jl:21-58: one launch for the whole batch, device RNG (Philox).  The padded verts
+# stay on the Zygote tape (get_verts_padded); the array-level function carries the adjoint (the face draws are constants,
+# :47 is @ignore): gverts[:, faces[k, face_s], mesh] += w_k * gsamples[:, s, mesh].
+function _sample_points_dev(verts::CuArray{Float32,3}, faces::CuArray{Int32,3}, vlen::CuVector{Int32}, flen::CuVector{Int32},
+                            num_samples::Int, eps::Float64, seed::UInt64, offset::UInt64; want_aux::Bool = false)
+    (_, V, Nm) = size(verts); F = size(faces, 2)
+    samples = similar(verts, 3, num_samples, Nm)
+    fidx = want_aux ? CuArray{Int32}(undef, num_samples, Nm) : nothing
+    bary = want_aux ? CuArray{Float32}(undef, 3, num_samples, Nm) : nothing
+    nws = ccall((:f3d_sample_points_workspace_bytes, LIB), Csize_t, (Int32, Int32), Nm, F)
+    ws = workspace((:sample, Nm, F), nws)
     check(ccall((:f3d_sample_points, LIB), Int32,
         (Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Int32, Int32, Int32, Float64, UInt64, UInt64,
          Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
-        devptr(verts), devptr(faces), devptr(vlen), devptr(flen), m.N, m.V, m.F, num_samples, Float64(eps), seed, offset,
-        C_NULL, C_NULL, C_NULL, devptr(samples), C_NULL, C_NULL, devptr(ws), length(ws), cur_stream()))
-    return samples
+        devptr(verts), devptr(faces), devptr(vlen), devptr(flen), Nm, V, F, num_samples, eps, seed, offset,
+        C_NULL, C_NULL, C_NULL, devptr(samples), want_aux ? devptr(fidx) : C_NULL, want_aux ? devptr(bary) : C_NULL,
+        devptr(ws), length(ws), cur_stream()))
+    return samples, fidx, bary
+end
+Zygote.@adjoint function _sample_points_dev(verts::CuArray{Float32,3}, faces::CuArray{Int32,3}, vlen::CuVector{Int32}, flen::CuVector{Int32},
+                                           num_samples::Int, eps::Float64, seed::UInt64, offset::UInt64)
+    samples, fidx, bary = _sample_points_dev(verts, faces, vlen, flen, num_samples, eps, seed, offset; want_aux = true)
+    (_, V, Nm) = size(verts); F = size(faces, 2)
+    function back(g)
+        gs = CuArray{Float32}(g[1]); gv = CUDA.zeros(Float32, 3, V, Nm)      # accumulated into: zeroed first
+        check(ccall((:f3d_sample_points_bwd, LIB), Int32,
+            (Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Int32}, Int32, Int32, Int32, Int32, Ptr{Float32}, Ptr{Cvoid}),
+            devptr(gs), devptr(fidx), devptr(bary), devptr(faces), Nm, V, F, num_samples, devptr(gv), cur_stream()))
+        return (gv, nothing, nothing, nothing, nothing, nothing, nothing, nothing)
+    end
+    return (samples, nothing, nothing), back
+end
+function Flux3D.sample_points(m::TriMesh{Float32,R,CuArray}, num_samples::Int = 5000; eps::Number = 1e-6,
+                              seed::UInt64 = rand(UInt64), offset::UInt64 = UInt64(0)) where {R}
+    verts = get_verts_padded(m)                                           # (3, V, N), differentiable
+    faces, vlen, flen = Zygote.ignore() do
+        (CuArray(Int32.(get_faces_padded(m)) .- Int32(1)),                # (3, F, N) local ids, pad = -1
+         CuArray(Int32.(m._verts_len)), CuArray(Int32.(m._faces_len)))
+    end
+    return _sample_points_dev(verts, faces, vlen, flen, num_samples, Float64(eps), seed, offset)[1]
 end
 
 # _packed_to_padded / _padded_to_packed — src/rep/utils.jl:131-185 — on the device (one launch each, no host loop).

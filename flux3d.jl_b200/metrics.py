@@ -13,6 +13,8 @@ FLAG_NONE = 0
 FLAG_FMA = 1  # non-reference arithmetic (fused multiply-add distances); see include/flux3d_b200.h
 FLAG_SWEEP_ONLY = 2  # measurement aid: launch only the sweep kernel
 FLAG_EXACT_SWEEP = 4  # every pair in the reference arithmetic (cross-check of the default filtered sweep)
+FLAG_TENSOR = 8  # force the tensor-core (tcgen05) filter path for any shape (kNN graph, chamfer sweep)
+FLAG_CUDA_CORES = 16  # chamfer: keep the filter sweep on the CUDA cores also for large problems (A/B aid, cross-check)
 
 _workspace = _lib.workspace
 _stream_ptr = _lib.stream_ptr

@@ -64,7 +64,11 @@ enum {
     /* f3d_knn_graph: take the tensor-core (tcgen05) filter path whenever the shape allows it (N <= 1024, F <= 64,
        K <= 31), also for narrow features (F < 16) where the CUDA-core kernel is the default because the work is
        selection-bound.  Results are identical either way. */
-    F3D_FLAG_TENSOR = 8
+    F3D_FLAG_TENSOR = 8,
+    /* f3d_chamfer_fwd: keep the filter sweep on the CUDA cores (packed-FP32 FFMA2 expanded form, chamfer.cu) also for
+       problems large enough for the tensor-core sweep (tcgen05 split-TF32 filter, chamfer_tc.cu), which is the default
+       from 296 work items of 256 query rows on.  Results are bit-identical either way. */
+    F3D_FLAG_CUDA_CORES = 16
 };
 
 enum {

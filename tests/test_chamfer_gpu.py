@@ -18,16 +18,35 @@ def _run(f3d, A, B, w1=1.0, w2=1.0, flags=0):
     return float(loss.item()), terms.cpu().numpy(), nnA.cpu().numpy(), nnB.cpu().numpy()
 
 
+def _run_tc(f3d, A, B, w1=1.0, w2=1.0):
+    """The tensor-core sweep (chamfer_tc.cu) forced for any shape; also returns its diagnostics: (ambiguous rows,
+    rows whose exact minimum fell outside the filter's error bound — must be 0)."""
+    tA = torch.from_numpy(A).cuda()
+    tB = torch.from_numpy(B).cuda()
+    loss, terms, nnA, nnB = f3d.chamfer_forward_raw(tA, tB, w1, w2, flags=f3d.FLAG_TENSOR)
+    torch.cuda.synchronize()
+    ws = f3d._lib.workspace(("chamfer", A.shape[0], A.shape[1], B.shape[1]), 256, tA.device)
+    hdr = ws[:12].cpu().numpy().view(np.int32)
+    return float(loss.item()), terms.cpu().numpy(), nnA.cpu().numpy(), nnB.cpu().numpy(), int(hdr[1]), int(hdr[2])
+
+
 def _check(f3d, oracle, A, B, w1=1.0, w2=1.0, both=True):
-    """Default path (filtered sweep + certified exact finalize) AND the all-exact sweep vs the oracle."""
+    """Three sweeps vs the oracle: the tensor-core filter (tcgen05), the CUDA-core filter (both with the certified exact
+    finalize) and the all-exact sweep — all three must agree bit for bit."""
     ol, onA, onB, oterms = oracle.chamfer_distance(A, B, w1, w2, return_all=True)
+    lt, tt, at, bt, n_amb, n_viol = _run_tc(f3d, A, B, w1, w2)
+    assert np.array_equal(at, onA), f"tensor-core path: nn_for_A mismatch at {np.argwhere(at != onA)[:5]}"
+    assert np.array_equal(bt, onB), f"tensor-core path: nn_for_B mismatch at {np.argwhere(bt != onB)[:5]}"
+    assert abs(lt - float(ol)) <= RTOL * abs(float(ol)) + 1e-30, (lt, float(ol))
+    assert n_viol == 0, f"{n_viol} certified rows outside the tensor-core filter's error bound"
     if both:
         l2, t2, a2, b2 = _run(f3d, A, B, w1, w2, flags=f3d.FLAG_EXACT_SWEEP)
         assert np.array_equal(a2, onA) and np.array_equal(b2, onB), "exact-sweep path: index mismatch"
         assert abs(l2 - float(ol)) <= RTOL * abs(float(ol)) + 1e-30
-    loss, terms, nnA, nnB = _run(f3d, A, B, w1, w2)
+    loss, terms, nnA, nnB = _run(f3d, A, B, w1, w2, flags=f3d.FLAG_CUDA_CORES)
     if both:
         assert loss == l2 and np.array_equal(terms, t2)  # the two paths agree bit for bit
+    assert np.allclose(tt, terms, rtol=1e-6, atol=0)      # (the tensor-core path sums its rows in another fixed order)
     assert np.array_equal(nnA, onA), f"nn_for_A mismatch at {np.argwhere(nnA != onA)[:5]}"
     assert np.array_equal(nnB, onB), f"nn_for_B mismatch at {np.argwhere(nnB != onB)[:5]}"
     assert abs(loss - float(ol)) <= RTOL * abs(float(ol)) + 1e-30, (loss, float(ol))
