@@ -1,31 +1,37 @@
 #!/usr/bin/env python
 """bench.py — the measurement contract.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg5] [--no-ops]
 
 Metric (BASELINE.json): Chamfer point-pairs/s = B*N*M / t, whole job over all N GPUs.
-A step = one chamfer_distance forward (both directions + the scalar loss; for N>1 also the one all-reduce of
-the per-shard loss) over one batch of synthetic clouds.  Workload per GPU (weak scaling): cfg2 = BASELINE
-configs[1], B=32 N=M=4096 Float32, U[0,1)^3, seeds 201/202 (+rank); --workload cfg5 gives the per-GPU shard of
-configs[4] (B=32 per GPU, N=M=8192).
+A step = one chamfer_distance forward (both directions + the scalar loss; for N>1 also the one cross-rank sum of the per-shard
+loss) over one batch of synthetic clouds.  Workload per GPU (weak scaling): cfg2 = BASELINE configs[1], B=32 N=M=4096 Float32,
+U[0,1)^3, seeds 201/202 (+1000*rank); --workload cfg5 gives the per-GPU shard of configs[4] (B=32 per GPU, N=M=8192, seeds
+501/502 (+1000*rank)).
 
-value      device-timed (CUDA events around every step, summed; inputs resident in HBM; L2 flushed between steps
-           outside the event pairs), max over ranks.
-e2e        the same step through the public API flux3d_b200.chamfer_distance with PINNED HOST inputs: H2D of
-           both clouds and the D2H read of the loss are inside the timed region (C ABI: f3d_chamfer_pipe_run —
-           the batch crosses PCIe in 4 chunks, chunk k+1 in flight while chunk k is swept).
-roofline   the dominant kernel (chamfer_filter_sweep_kernel) timed alone, live, with CUDA events on its launch stream
-           (F3D_FLAG_SWEEP_ONLY).  The binding roof is FP32 issue, not HBM (0.006 algorithmic bytes per pair):
-           achieved = ALGORITHMIC 8 lane-instructions/pair (3 FSUB, 3 FMUL, 2 FADD: the reference's bit-exact direct
-           form; the two min-updates not counted) * pairs / t against SMs*128 lanes*f_max.  The kernel
-           reaches the same bit-exact result with 4 executed FP32 lane-ops per pair (expanded-form filter +
-           certified exact re-evaluation), reported as roofline.executed; the HBM view BASELINE.json asks for is
-           reported beside it under roofline.hbm.
-cpu_baseline  the reference's CPU algorithm (per batch element a KD-tree build + 1-NN queries per direction,
-           serial, src/metrics/pcloud.jl:54-70) restated with scipy's cKDTree, 1 thread, on this box's host cores.
+value      device-timed (CUDA events around every step, summed; inputs resident in HBM; L2 flushed between steps outside the
+           event pairs), max over ranks.
+e2e        the same step through the public API flux3d_b200.chamfer_distance with PINNED HOST inputs: H2D of both clouds and
+           the D2H read of the loss are inside the timed region (C ABI: f3d_chamfer_pipe_run — the grid pulls the clouds over
+           PCIe itself while it sweeps what has landed; the loss comes back through mapped host memory).
+checked    BOTH losses (device-resident and end to end) are compared with the reference's CPU algorithm (KD-tree 1-NN per batch
+           element and direction, src/metrics/pcloud.jl:54-70) on the GLOBAL batch of all ranks, outside the timed region, at
+           every N: a relative difference above 1e-5 makes bench.py exit non-zero.
+roofline   the dominant kernel (chamfer_tc_sweep_kernel: the filter sweep as a split-TF32 GEMM on the tensor cores) timed alone,
+           live, with CUDA events on its launch stream (F3D_FLAG_SWEEP_ONLY; includes the 3 us operand-preparation grid in front
+           of it).  bound = tensor: achieved = EXECUTED tensor FLOPs (2 directions x K=16 x 2 = 64 FLOP per pair) / t against
+           the measured dense bf16 GEMM rate / 2 (TF32 runs at half the bf16 rate).  Beside it: the TMEM read-out roof that
+           actually binds the design (8 accumulator bytes per pair against the measured tcgen05.ld rate), the FP32-issue
+           convention of SURVEY §8d (8 lane-instructions per pair; what round 1 reported), and the HBM view BASELINE.json asks for.
+cpu_baseline  the reference's CPU algorithm restated with scipy's cKDTree, 1 thread, on this box's host cores.
+ops        (N=1 only, outside the headline timed region, same process and clocks) the other BASELINE configs: kNN graph cfg3
+           (F=3 and F=64; indices only and with the edge features in the MLP layout), sample_points / laplacian_loss /
+           compute_verts_normals_packed at cfg4, each with the CPU port timed beside it.
+cfg5       (N>1) a sub-record for BASELINE configs[4] (B=32 per GPU, N=M=8192): step time with the cross-rank sum, the same
+           shard without any exchange (= the single-GPU time), their ratio, and the loss checked against the CPU port.
 
---impl reference times that same CPU restatement with all host threads (the reference is pure Julia; no Julia
-exists in this image) and prints the same line with "impl": "reference".
+--impl reference times that same CPU restatement with all host threads (the reference is pure Julia; no Julia exists in this
+image) and prints the same line with "impl": "reference".
 """
 import argparse
 import json
@@ -48,8 +54,14 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured")
-    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), bf16_tflops=float(d.get("bf16_tflops", 1590.0)),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, bf16_tflops=1590.0, source="fallback")
+
+
+def workload_label(wl):
+    w = WORKLOADS[wl]
+    return f"chamfer_distance B={w['B']}/GPU N={w['N']} M={w['M']} Float32 ({wl}), U[0,1)^3, forward incl. loss reduction"
 
 
 def make_inputs(wl, rank):
@@ -58,6 +70,19 @@ def make_inputs(wl, rank):
     A = np.random.default_rng(w["seeds"][0] + 1000 * rank).random((w["B"], w["N"], 3), dtype=np.float32)
     B = np.random.default_rng(w["seeds"][1] + 1000 * rank).random((w["B"], w["M"], 3), dtype=np.float32)
     return A, B
+
+
+def global_reference_loss(wl, world):
+    """The reference's CPU algorithm on the global batch of all ranks (rank r holds make_inputs(wl, r))."""
+    import numpy as np
+    parts = [make_inputs(wl, r) for r in range(world)]
+    return kdtree_step(np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), -1)
+
+
+def tc_path(B, N, M):
+    """Mirror of chamfer_tc_supported (csrc/chamfer_tc.cu): does f3d_chamfer_fwd take the tensor-core sweep for this shape?"""
+    items = B * ((N + 255) // 256 + (M + 255) // 256)
+    return items >= 2 * 148 and min(N, M) >= 512
 
 
 SAMPLER_SRC = r"""
@@ -142,14 +167,96 @@ def run_reference(args):
         "impl": "reference", "metric": "chamfer_point_pairs_per_sec", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"chamfer_distance B={wl['B']} N={wl['N']} M={wl['M']} Float32 ({args.workload})",
+        "config": {"workload": workload_label(args.workload),
                    "note": "reference CPU algorithm (KD-tree 1-NN per batch element and direction, "
                            "src/metrics/pcloud.jl:54-70) restated with scipy cKDTree; the Julia reference cannot run "
-                           "in this image; rank 0 only, one full batch per step"},
+                           "in this image; rank 0 only, one full batch of one GPU's workload per step"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"full batch per step, {args.steps} steps, cKDTree workers=-1"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "loss": loss}))
+
+
+def ops_block(steps, flush, pk):
+    """BASELINE configs[2] and [3] (kNN graph cfg3; sample_points / laplacian_loss / verts normals cfg4): device time per call
+    (CUDA events, median, L2 flushed between calls), algorithmic bytes and HBM fraction, and the CPU port timed beside it."""
+    import numpy as np
+    import torch
+
+    import flux3d_b200 as f3d
+    from oracle import oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fixtures import pad, teapots
+
+    def timed(fn):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for e0, e1 in evs:
+            flush.zero_()
+            e0.record()
+            fn()
+            e1.record()
+        torch.cuda.synchronize()
+        ts = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+        return ts[len(ts) // 2] * 1e3
+
+    def cpu_time(fn, min_s=0.6):
+        fn()
+        t0 = time.perf_counter()
+        n = 0
+        while n < 2 or time.perf_counter() - t0 < min_s:
+            fn()
+            n += 1
+        return (time.perf_counter() - t0) / n * 1e6
+
+    out = []
+
+    def report(name, units, unit_name, us, alg_bytes, cpu_us=None, cpu_note=""):
+        line = {"op": name, "us_per_call": round(us, 2), "value": units / (us * 1e-6), "unit": unit_name + "/s", "algorithmic_bytes": alg_bytes,
+                "hbm_frac_of_measured": alg_bytes / (us * 1e-6) / 1e9 / pk["hbm_gbs"]}
+        if cpu_us is not None:
+            line["cpu_port"] = {"us_per_call": round(cpu_us, 1), "value": units / (cpu_us * 1e-6), "cores": O.num_threads(), "note": cpu_note}
+        out.append(line)
+
+    rng = np.random.default_rng(301)
+    X3 = rng.standard_normal((32, 1024, 3)).astype(np.float32)
+    X3 = ((X3 - X3.mean(1, keepdims=True)) / X3.std(axis=(1, 2), keepdims=True)).astype(np.float32)
+    X64 = np.random.default_rng(302).standard_normal((32, 1024, 64)).astype(np.float32)
+    for F, X in ((3, X3), (64, X64)):
+        t = torch.from_numpy(X).cuda()
+        B, N, _ = X.shape
+        us = timed(lambda: f3d.knn_graph(t, 20))
+        cpu = cpu_time(lambda: O.knn_graph(X[:2], 20)) * (B / 2)
+        report(f"knn_graph cfg3 F={F} K=20 (idx)", B * N * N, "pairs", us, X.nbytes + B * N * 20 * 4, cpu, "oracle brute force, first 2 clouds scaled to 32")
+        us = timed(lambda: f3d.knn_graph(t, 20, want_edge=True, mlp_layout=True))
+        report(f"knn_graph cfg3 F={F} K=20 + edge features in the MLP layout (K*N,2F,B)", B * N * N, "pairs", us, X.nbytes + B * N * 20 * (4 + 8 * F))
+    gold = os.path.join(ROOT, "tests", "golden")
+    vl, fl = teapots(16, gold, O)
+    m = f3d.TriMesh(vl, fl)
+    m._topology(); m.get_verts_padded(); m.faces_padded_device(); m._topo_device("rowptr"); m._topo_device("v2c")
+    nV, nF, nE = 16 * 1202, 16 * 2256, 16 * 3456
+    vp, fp, vlen, flen = pad(vl, fl)
+    vpk = np.concatenate(vl)
+    fpk = m.get_faces_packed()
+    us = timed(lambda: f3d.sample_points(m, 10000, seed=401))
+    report("sample_points cfg4 (16 meshes x 10000)", 160000, "samples", us, nV * 12 + nF * 12 + 160000 * 12,
+           cpu_time(lambda: O.sample_points(vp, fp, vlen, flen, 10000, seed=401)), "oracle, 1 thread")
+    us = timed(lambda: f3d.laplacian_loss(m))
+    report("laplacian_loss cfg4", nV, "vertices", us, nV * 12 + (2 * nE + nV) * 8 + (nV + 1) * 4 + 4,
+           cpu_time(lambda: O.laplacian_loss(vpk, fpk)), "oracle incl. its topology build, 1 thread")
+    us = timed(lambda: m.compute_verts_normals_packed(0))
+    report("compute_verts_normals_packed cfg4 (REFERENCE_CPU)", nV, "vertices", us, nV * 12 + nF * 12 + nV * 12 + nF * 12 + (nV + 1) * 4,
+           cpu_time(lambda: O.verts_normals(vpk, fpk, 0)), "oracle, 1 thread")
+    us = timed(lambda: f3d.edge_loss(m))
+    report("edge_loss cfg4", nE, "edges", us, nV * 12 + nE * 8 + 4)
+    A = torch.rand((32, 4096, 3), device="cuda", requires_grad=True)
+    Bc = torch.rand((32, 4096, 3), device="cuda", requires_grad=True)
+    loss = f3d.chamfer_distance(A, Bc)
+    us = timed(lambda: torch.autograd.grad(loss, (A, Bc), retain_graph=True))
+    report("chamfer backward cfg2", 2 * 32 * 4096, "points", us, 2 * 32 * 4096 * (12 + 4 + 12) + 2 * 32 * 4096 * 12)
+    return out
 
 
 def run_b200(args):
@@ -170,14 +277,7 @@ def run_b200(args):
     if multi:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    wl = WORKLOADS[args.workload]
-    Bn, N, M = wl["B"], wl["N"], wl["M"]
-    B_total = Bn * world
-    hA, hB = make_inputs(args.workload, rank)
-    pA, pB = torch.from_numpy(hA).pin_memory(), torch.from_numpy(hB).pin_memory()
-    dA, dB = pA.to(dev), pB.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    out = (torch.empty(3, dtype=torch.float32, device=dev), None, None)
     stream = torch.cuda.current_stream(dev)
 
     # N > 1: the single exchange of the path (the sum of the shard losses) is fused into the finalize kernel — peer
@@ -197,12 +297,6 @@ def run_b200(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks take the same path
         if ok.item() == 0.0:
             comm, exchange = None, "nccl_allreduce"
-
-    def step(flags=0):
-        if multi and not flags:
-            return f3d.chamfer_distance_sharded(dA, dB, B_total, comm=comm).reshape(1)
-        loss, _, _, _ = f3d.chamfer_forward_raw(dA, dB, 1.0, 1.0, batch_total=B_total, want_indices=False, flags=flags, out=out)
-        return loss
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -226,79 +320,154 @@ def run_b200(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    def measure(workload, steps, warmup, with_e2e, with_sweep):
+        """Device-timed step, optionally the sweep alone and the end-to-end step, for one workload; losses returned for the check."""
+        wl = WORKLOADS[workload]
+        Bn = wl["B"]
+        B_total = Bn * world
+        hA, hB = make_inputs(workload, rank)
+        pA, pB = torch.from_numpy(hA).pin_memory(), torch.from_numpy(hB).pin_memory()
+        dA, dB = pA.to(dev), pB.to(dev)
+        out = (torch.empty(3, dtype=torch.float32, device=dev), None, None)
+
+        def step(flags=0, local_only=False):
+            if multi and not flags and not local_only:
+                return f3d.chamfer_distance_sharded(dA, dB, B_total, comm=comm).reshape(1)
+            loss, _, _, _ = f3d.chamfer_forward_raw(dA, dB, 1.0, 1.0, batch_total=B_total, want_indices=False, flags=flags, out=out)
+            return loss
+
+        for _ in range(max(warmup, 3)):
+            step()
+        res = {"B": Bn, "B_total": B_total, "N": wl["N"], "M": wl["M"], "h2d": int(pA.nbytes + pB.nbytes)}
+        res["total_ms"] = timed(step, steps)
+        res["loss"] = float(step().item())
+        if multi:
+            for _ in range(3):
+                step(local_only=True)
+            res["local_ms"] = timed(lambda: step(local_only=True), steps)   # the same shard with no exchange at all
+        if with_sweep:
+            for _ in range(3):
+                step(f3d.metrics.FLAG_SWEEP_ONLY)
+            res["sweep_ms"] = timed(lambda: step(f3d.metrics.FLAG_SWEEP_ONLY), steps) / steps
+        if with_e2e:
+            # end to end through the public API: pinned host inputs -> H2D -> kernels -> D2H of the loss
+            def e2e_step():
+                with torch.no_grad():
+                    if multi:
+                        return float(f3d.chamfer_distance_sharded(pA, pB, B_total, comm=comm, to_host=comm is not None).item())
+                    return float(f3d.chamfer_distance(pA, pB).item())
+            for _ in range(3):
+                e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                res["e2e_loss"] = e2e_step()
+            torch.cuda.synchronize(dev)
+            e2e_s = time.perf_counter() - t0
+            if multi:
+                t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_s = float(t.item())
+            res["e2e_s"] = e2e_s
+        return res
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    total_ms = timed(step, args.steps)
-    loss_val = float(step().item())
-    # dominant kernel alone (live, CUDA events on the launch stream)
-    for _ in range(3):
-        step(f3d.metrics.FLAG_SWEEP_ONLY)
-    sweep_ms = timed(lambda: step(f3d.metrics.FLAG_SWEEP_ONLY), args.steps) / args.steps
-    # end to end through the public API: pinned host inputs → H2D → kernels → D2H of the loss
-    def e2e_step():
-        with torch.no_grad():
-            # host arrays in: f3d_chamfer_pipe_run uploads chunk k+1 while chunk k is swept (one C call per step)
-            if multi:
-                return float(f3d.chamfer_distance_sharded(pA, pB, B_total, comm=comm, to_host=comm is not None).item())
-            return float(f3d.chamfer_distance(pA, pB).item())
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_loss = e2e_step()
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    if multi:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    r = measure(args.workload, args.steps, args.warmup, True, True)
     clocks = sampler.stop() if rank == 0 else None
+    sub = None
+    if multi and args.workload != "cfg5":
+        sub = measure("cfg5", max(5, args.steps // 2), 3, False, False)   # BASELINE configs[4]: B=32 per GPU, N=M=8192
+
+    # ---- parity, at every N, outside the timed region: both losses against the reference's CPU algorithm on the GLOBAL batch ----
+    verdict = torch.zeros(1, device=dev)
+    checks = {}
+    if rank == 0:
+        ref = global_reference_loss(args.workload, world)
+        checks[args.workload] = {"reference_cpu_loss": ref, "loss": r["loss"], "e2e_loss": r["e2e_loss"],
+                                 "rel_err": abs(r["loss"] - ref) / ref, "e2e_rel_err": abs(r["e2e_loss"] - ref) / ref, "tolerance": 1e-5}
+        bad = not (checks[args.workload]["rel_err"] <= 1e-5 and checks[args.workload]["e2e_rel_err"] <= 1e-5)
+        if sub is not None:
+            ref5 = global_reference_loss("cfg5", world)
+            checks["cfg5"] = {"reference_cpu_loss": ref5, "loss": sub["loss"], "rel_err": abs(sub["loss"] - ref5) / ref5, "tolerance": 1e-5}
+            bad = bad or not checks["cfg5"]["rel_err"] <= 1e-5
+        verdict[0] = 1.0 if bad else 0.0
+    if multi:
+        dist.broadcast(verdict, 0)
 
     if rank == 0:
         pk = peaks()
+        Bn, N, M, B_total = r["B"], r["N"], r["M"], r["B_total"]
+        steps = args.steps
         pairs_step = B_total * N * M
-        value = pairs_step * args.steps / (total_ms * 1e-3)
+        value = pairs_step * steps / (r["total_ms"] * 1e-3)
         pairs_launch = Bn * N * M
+        sweep_s = r["sweep_ms"] * 1e-3
+        tensor_path = tc_path(Bn, N, M)
         lane_peak = SMS * LANES * pk["sm_max_mhz"] * 1e6
-        achieved = LANE_INSTR_PER_PAIR * pairs_launch / (sweep_ms * 1e-3)
         alg_bytes = 12 * Bn * (N + M) + 4
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(args.workload)
+        tf32_peak = pk["bf16_tflops"] / 2.0
+        tmem_peak = 920.0 * SMS * pk["sm_max_mhz"] * 1e6 / 1e12   # TB/s: 920 B/clk/SM measured with tcgen05.ld alone (profiles/r02_tc_probe2.txt)
+        if tensor_path:
+            flops = 64.0 * pairs_launch
+            roofline = {"bound": "tensor", "kernel": "chamfer_tc_sweep_kernel", "achieved": flops / sweep_s / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": flops / sweep_s / 1e12 / tf32_peak,
+                        "note": "EXECUTED tensor FLOPs: 2 directions x K=16 (two-piece TF32 split of x,y,z and the norms) x 2 per pair; peak = measured dense bf16 "
+                                f"GEMM rate / 2 ({pk['source']}): kind::tf32 runs at half the bf16 rate.  A 128x256x8 tcgen05.mma measures 293 cycles = 87 % of "
+                                "that rate when issued alone (profiles/r02_tc_probe2.txt); smaller ones cost 245 cycles whatever their size",
+                        "tmem_readout": {"bound": "tmem", "achieved": 8.0 * pairs_launch / sweep_s / 1e12, "peak": tmem_peak, "unit": "TB/s",
+                                         "frac": 8.0 * pairs_launch / sweep_s / 1e12 / tmem_peak,
+                                         "note": "every pair's filter value leaves TMEM once per direction (4 B each) through tcgen05.ld"}}
+        else:
+            roofline = {"bound": "fp32_issue", "kernel": "chamfer_filter_sweep_kernel", "achieved": 4 * pairs_launch / sweep_s / 1e12, "peak": lane_peak / 1e12,
+                        "unit": "Tlane-instr/s", "frac": 4 * pairs_launch / sweep_s / lane_peak, "note": "executed: 3 FFMA2 + 1 FADD2 per two pairs"}
+        roofline.update({
+            "kernel_ms": r["sweep_ms"], "kernel_share_of_step": r["sweep_ms"] / (r["total_ms"] / steps), "pairs_per_s_kernel": pairs_launch / sweep_s,
+            "traffic": traffic,
+            "fp32_issue_convention": {"lane_instr_per_pair": LANE_INSTR_PER_PAIR, "achieved": LANE_INSTR_PER_PAIR * pairs_launch / sweep_s / 1e12,
+                                      "peak": lane_peak / 1e12, "unit": "Tlane-instr/s", "frac": LANE_INSTR_PER_PAIR * pairs_launch / sweep_s / lane_peak,
+                                      "note": "SURVEY 8d / round-1 convention: ALGORITHMIC 8 FP32 lane-instructions per pair of the bit-exact direct form against "
+                                              f"{SMS} SMs x {LANES} lanes x {pk['sm_max_mhz']:.0f} MHz; it can exceed 1 now that the pairs are filtered on the tensor pipe"},
+            "hbm": {"bound": "hbm", "achieved": alg_bytes / sweep_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / sweep_s / 1e9 / pk["hbm_gbs"],
+                    "algorithmic_bytes": alg_bytes, "note": f"of {pk['source']}; 0.006 B/pair: HBM cannot bind a brute-force sweep"}})
         line = {
             "metric": "chamfer_point_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": r["total_ms"] / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"chamfer_distance B={Bn}/GPU (global {B_total}) N={N} M={M} Float32 ({args.workload}), "
-                                   "U[0,1)^3, forward incl. loss reduction" + (f" + cross-rank loss sum ({exchange})" if multi else ""),
+            "config": {"workload": workload_label(args.workload), "global_batch": B_total,
+                       "exchange": (f"cross-rank loss sum ({exchange})" if multi else "none"),
                        "parallelism": f"batch-sharded x{world}", "l2": "flushed between steps (256 MiB memset outside the event pairs)",
                        "arithmetic": "results bit-identical to the direct form ((dx*dx)+(dy*dy))+(dz*dz) without FMA contraction "
-                                     "(expanded-form FP32 filter, every reported distance/index re-evaluated exactly)"},
+                                     "(split-TF32 tensor-core filter, every reported distance/index re-evaluated exactly in FP32)"},
             "clocks": clocks,
-            "e2e": {"value": pairs_step * args.steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(pA.nbytes + pB.nbytes),
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": 2 * args.steps,  # chamfer_filter_sweep_kernel + chamfer_filter_finalize_kernel per step (+1 memset node)
-            "roofline": {"bound": "fp32_issue", "kernel": "chamfer_filter_sweep_kernel", "achieved": achieved / 1e12,
-                         "peak": lane_peak / 1e12, "unit": "Tlane-instr/s", "frac": achieved / lane_peak,
-                         "kernel_ms": sweep_ms, "kernel_share_of_step": sweep_ms / (total_ms / args.steps),
-                         "pairs_per_s_kernel": pairs_launch / (sweep_ms * 1e-3),
-                         "peak_source": f"{SMS} SMs x {LANES} lanes x {pk['sm_max_mhz']:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz, {pk['source']})",
-                         "traffic": traffic,
-                         "executed": {"fp32_lane_ops_per_pair": 4, "achieved": 4 * pairs_launch / (sweep_ms * 1e-3) / 1e12,
-                                      "frac": 4 * pairs_launch / (sweep_ms * 1e-3) / lane_peak,
-                                      "note": "3 FFMA2 + 1 FADD2 per two pairs actually issued by the filter sweep"},
-                         "hbm": {"bound": "hbm", "achieved": alg_bytes / (sweep_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                 "frac": alg_bytes / (sweep_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes": alg_bytes,
-                                 "note": f"of {pk['source']}; 0.006 B/pair: HBM cannot bind a brute-force sweep"}},
-            "loss": loss_val, "e2e_loss": e2e_loss,
+            "e2e": {"value": pairs_step * steps / r["e2e_s"], "unit": "pairs/s", "h2d_bytes_per_step": r["h2d"],
+                    "d2h_bytes_per_step": 4, "ms_per_step": r["e2e_s"] / steps * 1e3},
+            # kernels of this library per device-timed step: operand preparation, tensor-core sweep, certify, cleanup (+ 1 memset node);
+            # the CUDA-core path (small problems): sweep + finalize
+            "gpu_launches": (4 if tensor_path else 2) * steps,
+            "roofline": roofline,
+            "loss": r["loss"], "e2e_loss": r["e2e_loss"], "checked": checks,
         }
+        if sub is not None:
+            p5 = sub["B_total"] * sub["N"] * sub["M"]
+            n5 = max(5, args.steps // 2)
+            line["cfg5"] = {"workload": workload_label("cfg5"), "global_batch": sub["B_total"], "steps": n5,
+                            "ms_per_step": sub["total_ms"] / n5, "value": p5 * n5 / (sub["total_ms"] * 1e-3), "unit": "pairs/s",
+                            "ms_per_step_no_exchange": sub["local_ms"] / n5,
+                            "efficiency_vs_single_gpu_shard": sub["local_ms"] / sub["total_ms"],
+                            "loss": sub["loss"],
+                            "workspace_note": "per GPU: compact operands 8.4 MB + locator triples 8.4 MB + supertile minima 33.6 MB (L2-resident); "
+                                              "DRAM bytes of the sweep at this size: profiles/traffic.json cfg5"}
+        if multi:
+            line["ms_per_step_no_exchange"] = r["local_ms"] / steps
         if world == 1 and not args.no_cpu_baseline:
             # bounded CPU sample: first 8 batch elements of the same workload, 1 thread (the reference is serial)
+            hA, hB = make_inputs(args.workload, 0)
             nb = min(8, Bn)
             kdtree_step(hA[:1], hB[:1], 1)
             t0 = time.perf_counter()
@@ -317,11 +486,20 @@ def run_b200(args):
                                     "host_cores_available": os.cpu_count(),
                                     "brute_force_oracle_all_cores": {"value": nb * N * M / dt_bf, "unit": "pairs/s",
                                                                      "cores": O.num_threads()}}
+        if world == 1 and not args.no_ops:
+            try:
+                line["ops"] = ops_block(20, flush, pk)
+            except Exception as e:  # pragma: no cover — the headline line must still be printed
+                line["ops"] = {"error": repr(e)}
         print(json.dumps(line))
     if multi:
         if comm is not None:
             comm.close()
         dist.destroy_process_group()
+    if verdict.item() != 0.0:
+        if rank == 0:
+            print(f"bench.py: loss check against the CPU reference FAILED: {json.dumps(checks)}", file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -332,6 +510,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ops", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -4,11 +4,20 @@
 // subtract/square -> mean; the indices are constants, :45 is @ignore):
 //   gA_i = cA (A_i - B_nnA(i))  -  Σ_{j : nnB(j) = i} cB (B_j - A_i),   cA = 2 w1 g / (N B_total)
 //   gB_j = cB (B_j - A_nnB(j))  -  Σ_{i : nnA(i) = j} cA (A_i - B_j),   cB = 2 w2 g / (M B_total)
-// HBM-bound (reads 2 clouds + 2 index arrays, writes 2 gradients: 32 B per point).  Two launches:
-// the direct terms overwrite the outputs (no memset needed), then the scatter terms are added with
-// RED.ADD.F32.  The scatter order is not fixed, so the last bit of a gradient entry that receives
-// several contributions may vary run to run (the reference pins this to atol 1e-2 / rtol 1e-3,
-// test/metrics.jl:112-114).
+// HBM-bound (reads 2 clouds + 2 index arrays, writes 2 gradients: 32 B per point).
+//
+// Default (clouds of up to 8 192 points): ONE launch, no atomics, bitwise repeatable.  CTA = (batch element, which
+// gradient).  The scatter term is turned into a gather: the CTA sorts the (target, source) pairs of its element by
+// target with a stable block radix sort (cub::BlockRadixSort — sources of one target stay in ascending order), then every
+// target point finds its segment with a binary search in shared memory and subtracts its sources' contributions from
+// the direct term in that fixed order; every gradient entry is written exactly once.
+// Larger clouds: two launches — the direct terms overwrite the outputs, then the scatter terms are added with
+// RED.ADD.F32 (order not fixed: the last bit of an entry that receives several contributions may vary run to run; the
+// reference pins this to atol 1e-2 / rtol 1e-3, test/metrics.jl:112-114).
+#include <algorithm>
+
+#include <cub/block/block_radix_sort.cuh>
+
 #include "f3d_common.cuh"
 
 namespace f3d {
@@ -57,6 +66,68 @@ __global__ void __launch_bounds__(kBT) chamfer_bwd_kernel(BwdParams p) {
     }
 }
 
+// ---- sorted gather: grid (B, 2); y = 0 computes gA (targets: points of A, sources: points of B through nnB), y = 1 gB ----
+template <int kItems>
+__global__ void __launch_bounds__(kBT) chamfer_bwd_sorted_kernel(BwdParams p) {
+    using Sort = cub::BlockRadixSort<int, kBT, kItems, int>;
+    constexpr int kCap = kBT * kItems;
+    extern __shared__ __align__(16) unsigned char bwd_smem[];
+    typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(bwd_smem);
+    int* sk = reinterpret_cast<int*>(bwd_smem);   // the sorted keys / values take the sort's scratch over afterwards
+    int* sv = sk + kCap;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const bool forA = blockIdx.y == 0;
+    const int nT = forA ? p.N : p.M, nS = forA ? p.M : p.N;               // targets / sources of this element
+    const float* T = (forA ? p.A : p.Bp) + (size_t)b * nT * 3;
+    const float* S = (forA ? p.Bp : p.A) + (size_t)b * nS * 3;
+    const int32_t* nnT = (forA ? p.nnA : p.nnB) + (size_t)b * nT;         // target -> its nearest source (direct term)
+    const int32_t* nnS = (forA ? p.nnB : p.nnA) + (size_t)b * nS;         // source -> the target it pulls on (scatter term)
+    float* G = (forA ? p.gA : p.gB) + (size_t)b * nT * 3;
+    const float g = __ldg(p.gout);
+    const float cT = (forA ? p.cA : p.cB) * g, cS = (forA ? p.cB : p.cA) * g;
+    int keys[kItems], vals[kItems];
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {   // blocked arrangement: thread t holds sources t*kItems .. +kItems-1 (ascending: the sort is stable)
+        const int j = tid * kItems + k;
+        keys[k] = j < nS ? __ldg(nnS + j) : 0x7fffffff;
+        vals[k] = j;
+    }
+    int bits = 1;
+    while ((1 << bits) < nT) ++bits;
+    Sort(tmp).Sort(keys, vals, 0, bits < 31 ? bits + 1 : 31);   // (+1: the padding key 0x7fffffff need not sort last — it is never looked up — but keep real keys exact)
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) { sk[tid * kItems + k] = keys[k]; sv[tid * kItems + k] = vals[k]; }
+    __syncthreads();
+    for (int i = tid; i < nT; i += kBT) {
+        const float tx = __ldg(T + 3 * i), ty = __ldg(T + 3 * i + 1), tz = __ldg(T + 3 * i + 2);
+        const int o = __ldg(nnT + i);
+        float gx = cT * (tx - __ldg(S + 3 * o)), gy = cT * (ty - __ldg(S + 3 * o + 1)), gz = cT * (tz - __ldg(S + 3 * o + 2));
+        int lo = 0, hi = nS;              // first position with key >= i among the nS real entries (padding keys sort after them or are skipped)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (sk[mid] < i) lo = mid + 1; else hi = mid;
+        }
+        for (int e = lo; e < nS && sk[e] == i; ++e) {   // ascending source index: a fixed summation order
+            const int j = sv[e];
+            gx -= cS * (__ldg(S + 3 * j) - tx);
+            gy -= cS * (__ldg(S + 3 * j + 1) - ty);
+            gz -= cS * (__ldg(S + 3 * j + 2) - tz);
+        }
+        G[3 * i] = gx; G[3 * i + 1] = gy; G[3 * i + 2] = gz;
+    }
+}
+
+template <int kItems>
+int32_t launch_sorted(const BwdParams& p, int B, cudaStream_t stream) {
+    using Sort = cub::BlockRadixSort<int, kBT, kItems, int>;
+    const size_t smem = std::max(sizeof(typename Sort::TempStorage), sizeof(int) * 2 * (size_t)kBT * kItems);
+    F3D_CUDA(cudaFuncSetAttribute(chamfer_bwd_sorted_kernel<kItems>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    chamfer_bwd_sorted_kernel<kItems><<<dim3(B, 2), kBT, smem, stream>>>(p);
+    F3D_CHECK_LAUNCH("chamfer_bwd_sorted_kernel");
+    return F3D_OK;
+}
+
 }  // namespace
 }  // namespace f3d
 
@@ -75,6 +146,12 @@ extern "C" int32_t f3d_chamfer_bwd(const float* A, const float* Bp, int32_t B, i
     p.cB = (float)(2.0 * (double)w2 / ((double)M * (double)B_total));
     p.gA = gA; p.gB = gB;
     p.totA = (long)B * N; p.totB = (long)B * M;
+    const int big = std::max(N, M);
+    if (B <= 65535 && big <= kBT * 32) {   // sorted gather: one launch, no atomics, bitwise repeatable
+        if (big <= kBT * 4) return launch_sorted<4>(p, B, stream);
+        if (big <= kBT * 16) return launch_sorted<16>(p, B, stream);
+        return launch_sorted<32>(p, B, stream);
+    }
     const long tot = p.totA + p.totB;
     const unsigned grid = (unsigned)((tot + kBT - 1) / kBT);
     chamfer_bwd_kernel<false><<<grid, kBT, 0, stream>>>(p);

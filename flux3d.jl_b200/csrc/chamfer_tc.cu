@@ -68,7 +68,8 @@ constexpr int kTcThreads = (kEpiWarps + kConvWarps + 4) * 32;   // 768: six warp
 constexpr int kLaunchRegs = 72, kEpiRegs = F3D_TC_EPI_REGS, kAuxRegs = 40;
 static_assert(kTcThreads * kLaunchRegs >= kEpiWarps * 32 * kEpiRegs + (kTcThreads - kEpiWarps * 32) * kAuxRegs, "register budget");
 static_assert(kItemRows == kTNc, "the query rows of an item travel as one 256-point compact tile");
-constexpr int kFinT = 128;                  // finalize block = one row tile
+constexpr int kFinT = 64;                   // finalize block = half a row tile
+constexpr int kFinPitch = 400;              // bytes per staged chunk in the finalize (384 B of data)
 constexpr float kPadN = 1.0e30f;            // |p'|² of padded points: never a minimum for in-contract inputs
 constexpr float kTcNormLimit = 1.0e29f, kTcNormFloor = 1.0e-30f;  // outside: certify nothing (overflow / underflow of the pieces)
 // Certificate: |f - d| <= kErrAbs (nq + nc) + 5.001 u d  (u = 2^-24; d = the reference-arithmetic distance).  35 u =
@@ -81,7 +82,7 @@ constexpr float kTcWinAbs = 4.2e-6f;        // >= 70.1 u = 4.178e-6
 constexpr float kTcWinRel = 6.2e-7f;        // >= 10.01 u
 constexpr float kTcErrAbs = 2.1e-6f, kTcErrRel = 3.1e-7f;
 // workspace header (ints); the first three words are diagnostics a caller may read after the call
-constexpr int kHdrDone = 0, kHdrAmb = 1, kHdrViol = 2, kHdrInts = 64;
+constexpr int kHdrDone = 0, kHdrAmb = 1, kHdrViol = 2, kHdrStarted = 32, kHdrInts = 64;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -202,6 +203,31 @@ __device__ __forceinline__ void split_tf32(float x, float& h, float& l) {
     l = rn_tf32(__fsub_rn(x, h));
 }
 
+// The locator record of a query row: the two smallest chunk minima with their chunk ids and the third smallest value.
+//   b2 > b1 + window              => the exact argmin lies in chunk c1
+//   else b3 > b1 + window         => it lies in chunk c1 or c2 (two rescans instead of one; ~0.4 % of rows on uniform clouds)
+//   else                          => ambiguous: every supertile within the window is scanned (cleanup kernel; ties, degenerate input)
+struct Loc3 {
+    float b1, b2, b3;
+    int c1, c2;
+};
+__device__ __forceinline__ void loc3_insert(Loc3& l, float m, int chunk) {   // strict '<': the EARLIEST chunk reaching a value keeps it
+    const bool lt1 = m < l.b1, lt2 = m < l.b2;
+    l.b3 = fminf(l.b3, fmaxf(l.b2, m));
+    l.c2 = lt1 ? l.c1 : (lt2 ? chunk : l.c2);
+    l.b2 = fminf(l.b2, fmaxf(l.b1, m));
+    l.c1 = lt1 ? chunk : l.c1;
+    l.b1 = fminf(l.b1, m);
+}
+__device__ __forceinline__ float4 loc3_pack(const Loc3& l) { return make_float4(l.b1, l.b2, l.b3, __int_as_float(l.c1 | (l.c2 << 16))); }
+__device__ __forceinline__ Loc3 loc3_unpack(const float4 v) {
+    Loc3 l;
+    l.b1 = v.x; l.b2 = v.y; l.b3 = v.z;
+    const int pk = __float_as_int(v.w);
+    l.c1 = pk & 0xffff; l.c2 = (pk >> 16) & 0xffff;
+    return l;
+}
+
 // ---- prepare: compact operands {x', y', z', |p'|²} of both clouds, once per call ---------------------------------------
 struct TcPrepParams {
     const float* A;    // [B][N][3]
@@ -248,6 +274,116 @@ __global__ void __launch_bounds__(kPrepT) chamfer_tc_prepare_kernel(TcPrepParams
     if (lane == 0) atomicMax(p.maxn + (size_t)(isA ? 0 : 1) * gridDim.y + b, __float_as_uint(mx));
 }
 
+// ---- host arrays: upload + prepare in ONE grid that runs beside the sweep (f3d_chamfer_pipe_run) --------------------------
+// The first U CTAs to start (roles go by start ticket, so whoever waits below waits for CTAs that are already running) pull
+// both clouds out of page-locked host memory over PCIe, batch element by batch element, into the staging copies the finalize
+// reads, and count every element as it lands; the other P CTAs wait for an element, centre it, write its compact operands
+// and count it as prepared.  The sweep's producer (launched programmatically right behind this grid) waits per ELEMENT:
+// it sweeps element b while elements b+1.. are still crossing PCIe.
+struct TcUploadParams {
+    TcPrepParams pp;          // A / Bp here are the device staging copies (written by the uploaders)
+    const float* hA;          // the host arrays as the device addresses them
+    const float* hB;
+    float* dA;
+    float* dB;
+    int B, U, P;
+    unsigned* arrived;        // [B]  uploader CTAs that have delivered their share of the element (target U)
+    int* prepared;            // [B]  preparer CTAs that have written their share of its operands (target P)
+    int* hdr;
+};
+__device__ __forceinline__ float4 ld_host_f4(const float* p) {
+    float4 v;  // volatile: never served from a stale cache line of a previous call's bytes at the same host address
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_host_f1(const float* p) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+// floats [s, e) of src -> dst (same index space, both bases 16-byte aligned): scalar head / tail, 16-byte body, four loads in flight
+__device__ __forceinline__ void upload_span(const float* __restrict__ src, float* __restrict__ dst, size_t s, size_t e, int u, int U, int tid, int nthreads) {
+    size_t s4 = (s + 3) & ~(size_t)3, e4 = e & ~(size_t)3;
+    if (s4 > e4) s4 = e4 = e;  // fewer than one aligned quad: everything is "head"
+    if (u == 0) {
+        if (s + tid < s4) dst[s + tid] = ld_host_f1(src + s + tid);    // < 4 floats each
+        if (e4 + tid < e && e4 >= s4) dst[e4 + tid] = ld_host_f1(src + e4 + tid);
+    }
+    const size_t n4 = (e4 - s4) >> 2, stride = (size_t)U * nthreads;
+    for (size_t i = (size_t)u * nthreads + tid; i < n4; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i + k * stride < n4) v[k] = ld_host_f4(src + s4 + 4 * (i + k * stride));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i + k * stride < n4) __stcg(reinterpret_cast<float4*>(dst + s4) + i + k * stride, v[k]);
+    }
+}
+constexpr int kUpT = 256;
+__global__ void __launch_bounds__(kUpT) chamfer_tc_upload_prepare_kernel(TcUploadParams p) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the sweep becomes resident beside this grid; its producer waits per element
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) s_ticket = atomicAdd(p.hdr + kHdrStarted, 1);
+    __syncthreads();
+    const int ticket = s_ticket;
+    const TcPrepParams& q = p.pp;
+    if (ticket < p.U) {
+        const size_t ea = (size_t)q.N * 3, eb = (size_t)q.M * 3;
+        for (int b = 0; b < p.B; ++b) {
+            upload_span(p.hA, p.dA, b * ea, (b + 1) * ea, ticket, p.U, tid, kUpT);
+            upload_span(p.hB, p.dB, b * eb, (b + 1) * eb, ticket, p.U, tid, kUpT);
+            __threadfence();   // this thread's stores are visible device-wide ...
+            __syncthreads();   // ... for every thread of the CTA ...
+            if (tid == 0) atomicAdd(p.arrived + b, 1u);  // ... before the element counts as delivered by this CTA
+        }
+        return;
+    }
+    const int v = ticket - p.U;
+    for (int b = 0; b < p.B; ++b) {
+        if (tid == 0) {
+            const int* f = reinterpret_cast<const int*>(p.arrived) + b;
+            while (ld_acquire_i32(f) < p.U) __nanosleep(100);
+        }
+        __syncthreads();
+        const float* gA = q.A + (size_t)b * q.N * 3;
+        const float* gB = q.Bp + (size_t)b * q.M * 3;
+        // the same centre, with the same operations, as chamfer_tc_prepare_kernel (the staging copies were written by other SMs: L2 loads)
+        const int ia = (int)(((long)lane * q.N) >> 5), ib = (int)(((long)lane * q.M) >> 5);
+        float cx = __ldcg(gA + 3 * ia) + __ldcg(gB + 3 * ib);
+        float cy = __ldcg(gA + 3 * ia + 1) + __ldcg(gB + 3 * ib + 1);
+        float cz = __ldcg(gA + 3 * ia + 2) + __ldcg(gB + 3 * ib + 2);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cx += __shfl_xor_sync(0xffffffffu, cx, o);
+            cy += __shfl_xor_sync(0xffffffffu, cy, o);
+            cz += __shfl_xor_sync(0xffffffffu, cz, o);
+        }
+        cx *= (1.0f / 64.0f); cy *= (1.0f / 64.0f); cz *= (1.0f / 64.0f);
+        // points of both clouds, padded: [0, NpA) of A, then [0, NpB) of B; this CTA takes every P-th block of 256
+        const int total = q.NpA + q.NpB;
+        for (int i0 = v * kUpT; i0 < total; i0 += p.P * kUpT) {
+            const int i = i0 + tid;                    // NpA is a multiple of 256: a block never straddles the two clouds
+            const bool isA = i0 < q.NpA;
+            const int k = isA ? i : i - q.NpA, n = isA ? q.N : q.M, np = isA ? q.NpA : q.NpB;
+            float x = 0.f, y = 0.f, z = 0.f, nrm = kPadN, mx = 0.f;
+            if (k < n) {
+                const float* src = (isA ? gA : gB) + 3 * (size_t)k;
+                x = __ldcg(src) - cx; y = __ldcg(src + 1) - cy; z = __ldcg(src + 2) - cz;
+                nrm = fmaf(z, z, fmaf(y, y, x * x));
+                mx = nrm;
+            }
+            (isA ? q.PA : q.PB)[(size_t)b * np + k] = make_float4(x, y, z, nrm);
+            mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));
+            if (lane == 0) atomicMax(q.maxn + (size_t)(isA ? 0 : 1) * p.B + b, __float_as_uint(mx));
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(p.prepared + b, 1);
+    }
+}
+
 // ---- sweep -------------------------------------------------------------------------------------------------------------
 #ifdef F3D_TC_PROF
 // development: cycles every role spends waiting / working, per CTA (read back with f3d_debug_read_tc)
@@ -265,11 +401,13 @@ struct TcSweepParams {
     const float4* PB;
     int B, NpA, NpB;       // padded cloud sizes (multiples of 256)
     int rbA, rbB;          // 256-row blocks per batch element: NpA / 256, NpB / 256
-    float4* rowfin;        // [B][NpA + NpB]  {b1, b2, c1 (int bits), -}: rows of A (searching B), then rows of B (searching A)
+    float4* rowfin;        // [B][NpA + NpB]  {b1, b2, b3, c1 | c2 << 16}: rows of A (searching B), then rows of B (searching A)
     float* tilemin;        // [B][ (nstB*NpA + nstA*NpB) * kParts ]  per supertile of the searched cloud, read-out group and row
     int nstA, nstB;        // supertiles of cloud A / B
     int* done;             // [B*(rbA+rbB)*kRT]  read-out warps that have published a row tile (target 4)
     int wait_prepare;      // launched programmatically behind the prepare grid
+    const int* prepared;   // upload mode: [B] preparer CTAs that have written an element's operands (target prepared_target); else null
+    int prepared_target;
 };
 
 __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p) {
@@ -316,6 +454,10 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
                 const float4* Pq = (dir ? p.PB : p.PA) + (size_t)b * npq + (size_t)rb * kItemRows;
                 const float4* Pc = (dir ? p.PA : p.PB) + (size_t)b * npc;
                 const int ntiles = npc / kTNc;
+                if (p.prepared) {   // upload mode: this batch element may still be crossing PCIe
+                    while (ld_acquire_i32(p.prepared + b) < p.prepared_target) __nanosleep(100);
+                    asm volatile("fence.proxy.async;" ::: "memory");   // the operands were written with generic stores; the TMA reads them through the async proxy
+                }
                 for (int t = -1; t < ntiles; ++t, ++h) {   // t = -1: the item's 256 query rows
                     const unsigned s = h % kCStages, n = h / kCStages;
                     mbar_wait(&cempty[s], (n & 1) ^ 1);
@@ -436,16 +578,16 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             const float4* src = s_pub + pb * kParts * kItemRows;
 #pragma unroll 2
             for (int rin = lane; rin < kItemRows; rin += 32) {
-                float4 e = src[rin];
+                Loc3 e = loc3_unpack(src[rin]);
 #pragma unroll
                 for (int q = 1; q < kParts; ++q) {
-                    // disjoint chunk sets: b2 = minimum over every chunk other than the one holding the overall minimum (a tie
-                    // between quarters gives b2 == b1, i.e. an ambiguous row — which chunk c1 then names does not matter)
-                    const float4 o = src[q * kItemRows + rin];
-                    if (o.x < e.x) { e.y = fminf(e.x, o.y); e.x = o.x; e.z = o.z; }
-                    else e.y = fminf(e.y, o.x);
+                    // disjoint chunk sets: insert the quarter's two located chunk minima; its third value can only be third or later
+                    const Loc3 o = loc3_unpack(src[q * kItemRows + rin]);
+                    loc3_insert(e, o.b1, o.c1);
+                    loc3_insert(e, o.b2, o.c2);
+                    e.b3 = fminf(e.b3, o.b3);
                 }
-                out[rin] = e;
+                out[rin] = loc3_pack(e);
             }
             __syncwarp();
             if (lane == 0) {
@@ -477,10 +619,10 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             const int rin = quad * 32 + lane;               // row within its row tile
             float* tm = p.tilemin + (size_t)kParts * ((size_t)b * ((size_t)p.nstB * p.NpA + (size_t)p.nstA * p.NpB) + (dir ? (size_t)p.nstB * p.NpA : 0)) +
                         (size_t)rb * kItemRows + rin;
-            float b1[kRT], b2[kRT], stmin[kRT];
-            int c1[kRT];
+            Loc3 loc[kRT];
+            float stmin[kRT];
 #pragma unroll
-            for (int r = 0; r < kRT; ++r) { b1[r] = INFINITY; b2[r] = INFINITY; stmin[r] = INFINITY; c1[r] = 0; }
+            for (int r = 0; r < kRT; ++r) { loc[r].b1 = INFINITY; loc[r].b2 = INFINITY; loc[r].b3 = INFINITY; loc[r].c1 = 0; loc[r].c2 = 0; stmin[r] = INFINITY; }
             for (int t = 0; t < ntiles; ++t, ++g) {
 #pragma unroll
                 for (int r = 0; r < kRT; ++r) {
@@ -499,9 +641,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
                     for (int q = 0; q < 2; ++q) {
                         const float m = min32(v[q]);
                         const int chunk = t * (kTNc / kTcChunk) + part * (kTNc / kParts / kTcChunk) + q;
-                        b2[r] = fminf(b2[r], fmaxf(b1[r], m));
-                        c1[r] = m < b1[r] ? chunk : c1[r];        // strict: the EARLIEST chunk (of this quarter) that reaches the minimum
-                        b1[r] = fminf(b1[r], m);
+                        loc3_insert(loc[r], m, chunk);
                         stmin[r] = fminf(stmin[r], m);
                     }
                     tc_fence_before();
@@ -522,7 +662,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             mbar_wait(&pub_empty[pb], ((it >> 1) & 1) ^ 1);
 #pragma unroll
             for (int r = 0; r < kRT; ++r)
-                s_pub[(pb * kParts + part) * kItemRows + r * kTQ + rin] = make_float4(b1[r], b2[r], __int_as_float(c1[r]), 0.f);
+                s_pub[(pb * kParts + part) * kItemRows + r * kTQ + rin] = loc3_pack(loc[r]);
             __syncwarp();
             if (lane == 0) mbar_arrive(&pub_full[pb]);
         }
@@ -530,10 +670,22 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
     }
     tc_fence_before();
     __syncthreads();
+#ifdef F3D_TC_PROF
+    if (tid == 0 && blockIdx.x < 148) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); g_tcprof[blockIdx.x * 16 + 15] = (long long)g_; }
+#endif
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, kRT * kTNc); }
 }
 
 // ---- finalize: certify, re-evaluate exactly, reduce the loss -----------------------------------------------------------
+#ifdef F3D_TC_PROF
+__device__ unsigned long long g_finprof[8192 * 8];
+__device__ unsigned long long g_cleanprof[4096 * 4];
+#define CPROF(k) do { if (threadIdx.x == 0 && blockIdx.x < 4096) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); g_cleanprof[blockIdx.x * 4 + (k)] = g_; } } while (0)
+#define FPROF(k) do { if (threadIdx.x == 0 && blockIdx.x < 8192) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); g_finprof[blockIdx.x * 8 + (k)] = g_; } } while (0)
+#else
+#define FPROF(k)
+#define CPROF(k)
+#endif
 struct TcFinParams {
     const float* A;
     const float* Bp;
@@ -546,7 +698,13 @@ struct TcFinParams {
     const int* done;
     int32_t* nnA;
     int32_t* nnB;
-    double* partial;        // [nblocks]
+    double* partial;        // [nfin] certified rows of every finalize block
+    int* ambcnt;            // [nfin]        ambiguous rows of every finalize block ...
+    int* ambq;              // [nfin][kFinT] ... their row numbers, in row order ...
+    float* amblim;          // [nfin][kFinT] ... and their windows' upper ends
+    int* amblist;           // [rows]        (finalize block << 6 | position) of every ambiguous row, in arrival order: the cleanup's work list
+    float* ambd;            // [nfin][kFinT] the exact distances the cleanup finds, at the rows' fixed positions
+    int nfin;
     int* hdr;               // kHdr*
     float w1, w2;
     double denomA, denomB;
@@ -555,212 +713,292 @@ struct TcFinParams {
     ChamferPeerSum peer;
 };
 
-__global__ void __launch_bounds__(kFinT, 7) chamfer_tc_finalize_kernel(TcFinParams p) {
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+
+// Finalize, part 1 (co-resident with the sweep): thread <-> row; certify, re-evaluate the located 32 candidates exactly.  Kept
+// lean on purpose — 64 threads, <= 40 registers, 25 KB of shared memory, no block-wide loops — so that several blocks fit
+// beside a sweep CTA and keep pace with it; rows that cannot be certified are only LISTED here (in row order, at fixed
+// positions: the result stays bitwise repeatable) and rescanned by chamfer_tc_cleanup_kernel.
+__global__ void __launch_bounds__(kFinT, 24) chamfer_tc_finalize_kernel(TcFinParams p) {
+    // phase 2 staging: a row's 32-candidate chunk (384 B) is fetched with 24 cp.async of 16 bytes into the thread's own
+    // shared-memory row — all of a block's fetches in flight together instead of four dependent load batches per thread
+    extern __shared__ __align__(16) unsigned char fin_smem[];
     __shared__ double s_red[kFinT / 32];
-    __shared__ bool s_last;
-    constexpr int kMaxSel = 32;
-    __shared__ int s_sel[kMaxSel], s_nsel;
-    __shared__ unsigned s_amb[kFinT / 32], s_wd[kFinT / 32];
-    __shared__ int s_wj[kFinT / 32], s_iq[kFinT];
-    __shared__ float s_ilim[kFinT];
+    __shared__ int s_cnt[kFinT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // block <-> row tile: (item, r) in the sweep's order, so that blocks become ready in the order they are resident
+    FPROF(0);
+    // block <-> 64 rows of a row tile: (item, r, half) in the sweep's order, so that blocks become ready in the order they are resident
+    constexpr int kPerTile = kTQ / kFinT;
     const int ipe = p.rbA + p.rbB;
-    const int item = (int)blockIdx.x / kRT, r = (int)blockIdx.x - item * kRT;
+    const int rt = (int)blockIdx.x / kPerTile, sub = (int)blockIdx.x - rt * kPerTile;   // row tile = item * kRT + r
+    const int item = rt / kRT, r = rt - item * kRT;
     const int b = item / ipe, k = item - b * ipe;
     const bool dir = k >= p.rbA;                       // false: rows of A search B; true: rows of B search A
     const int rb = dir ? k - p.rbA : k;
     const int Q = dir ? p.M : p.N, R = dir ? p.N : p.M;        // queries / searched points per element
     const int npq = dir ? p.NpB : p.NpA;
-    const int nst = dir ? p.nstA : p.nstB;                      // supertiles of the searched cloud
     const float* gQ = (dir ? p.Bp : p.A) + (size_t)b * Q * 3;
     const float* gP = (dir ? p.A : p.Bp) + (size_t)b * R * 3;
-    const int q = rb * kItemRows + r * kTQ + tid;
+    const int q = rb * kItemRows + r * kTQ + sub * kFinT + tid;
     const bool valid = q < Q;
     double mine = 0.0;
 
     if (tid == 0) {
-        const int* flag = p.done + (size_t)item * kRT + r;
+        const int* flag = p.done + rt;
         while (ld_acquire_i32(flag) < 4) __nanosleep(200);
     }
     __syncthreads();
+    FPROF(1);
 
-    // ---- phase 1: certified or ambiguous --------------------------------------------------------------------------------
+    // ---- phase 1: certified (one chunk), certified (two chunks) or ambiguous ---------------------------------------------
     float qx = 0.f, qy = 0.f, qz = 0.f, best = 0.f, win = 0.f, errlim = 0.f;
-    int loc = 0;
-    bool amb = false;
+    int loc = 0, loc2 = 0;
+    bool amb = false, two = false;
     if (valid) {
-        const float4 e = __ldcg(p.rowfin + (size_t)b * (p.NpA + p.NpB) + (dir ? p.NpA : 0) + q);
+        const Loc3 e = loc3_unpack(__ldcg(p.rowfin + (size_t)b * (p.NpA + p.NpB) + (dir ? p.NpA : 0) + q));
         const float nq = __ldcg(&((dir ? p.PB : p.PA) + (size_t)b * npq + q)->w);
         const float other = __uint_as_float(__ldcg(p.maxn + (size_t)(dir ? 0 : 1) * p.B + b));
         qx = __ldg(gQ + 3 * (size_t)q); qy = __ldg(gQ + 3 * (size_t)q + 1); qz = __ldg(gQ + 3 * (size_t)q + 2);
-        best = fmaxf(e.x, 0.0f);
-        const float second = fmaxf(e.y, 0.0f);
-        loc = __float_as_int(e.z);
+        best = fmaxf(e.b1, 0.0f);
+        loc = e.c1; loc2 = e.c2;
         win = fmaf(kTcWinRel, best, kTcWinAbs * (nq + other));
         errlim = kTcErrAbs * (nq + other);
         // written so that NaN / inf / out-of-range norms can only make the row ambiguous, never certified
-        amb = !(nq <= kTcNormLimit && other <= kTcNormLimit && nq + other >= kTcNormFloor && second > best + win);
+        const bool sane = nq <= kTcNormLimit && other <= kTcNormLimit && nq + other >= kTcNormFloor;
+        const bool one = sane && fmaxf(e.b2, 0.0f) > best + win;
+        two = sane && !one && fmaxf(e.b3, 0.0f) > best + win;
+        amb = !(one || two);
     }
-
-    // ---- phase 2: certified rows — the 32 candidates of the located chunk, in the reference arithmetic -------------------
-    if (valid && !amb) {
+    FPROF(2);
+    // ---- phase 2: certified rows — the 32 candidates of the located chunk (of both located chunks), in the reference arithmetic ----
+    {
+        const bool cert = valid && !amb;
+        unsigned char* mychunk = fin_smem + tid * kFinPitch;
         float d = INFINITY;
         int j = 0x7fffffff;
-        const int j0 = loc * kTcChunk, j1 = min(j0 + kTcChunk, R);
-        const float* pp = gP + 3 * (size_t)j0;
-        if (j0 + kTcChunk <= R && (reinterpret_cast<uintptr_t>(pp) & 15u) == 0) {
+        // one pass per located chunk; the second pass runs only in warps that hold a two-chunk row (about one warp in nine)
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool mine_pass = cert && (pass == 0 || two);
+            if (pass == 1 && !__any_sync(0xffffffffu, mine_pass)) break;
+            const int j0 = (pass == 0 ? loc : loc2) * kTcChunk, j1 = min(j0 + kTcChunk, R);
+            const float* pp = gP + 3 * (size_t)j0;
+            const bool staged = mine_pass && j0 + kTcChunk <= R && (reinterpret_cast<uintptr_t>(pp) & 15u) == 0;
+            if (staged) {
 #pragma unroll
-            for (int h = 0; h < kTcChunk / 8; ++h) {  // 8 candidates = six 16-byte loads per trip
-                float4 v[6];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(pp) + h * 6 + i);
-                const float c[24] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w, v[2].x, v[2].y, v[2].z, v[2].w,
-                                     v[3].x, v[3].y, v[3].z, v[3].w, v[4].x, v[4].y, v[4].z, v[4].w, v[5].x, v[5].y, v[5].z, v[5].w};
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    // operand order of the reference: (a - b) with a from the first cloud
-                    const float dd = dir ? sqdist3<false>(c[3 * u], c[3 * u + 1], c[3 * u + 2], qx, qy, qz)
-                                         : sqdist3<false>(qx, qy, qz, c[3 * u], c[3 * u + 1], c[3 * u + 2]);
-                    if (dd < d) { d = dd; j = j0 + h * 8 + u; }  // ascending candidates: '<' keeps the lowest index
-                }
+                for (int i = 0; i < kTcChunk * 12 / 16; ++i) cp_async16(mychunk + 16 * i, reinterpret_cast<const unsigned char*>(pp) + 16 * i);
             }
-        } else {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (mine_pass && !staged) {   // ragged end of the cloud or a cloud that is not 16-byte aligned there: direct loads
 #pragma unroll 4
-            for (int jj = j0; jj < j1; ++jj) {
-                const float px = __ldg(gP + 3 * (size_t)jj), py = __ldg(gP + 3 * (size_t)jj + 1), pz = __ldg(gP + 3 * (size_t)jj + 2);
-                const float dd = dir ? sqdist3<false>(px, py, pz, qx, qy, qz) : sqdist3<false>(qx, qy, qz, px, py, pz);
-                if (dd < d) { d = dd; j = jj; }
-            }
-        }
-        // self-check of the error bound at the located minimum
-        if (!(fabsf(d - best) <= fmaf(kTcErrRel, d, errlim))) {
-            amb = true;
-            atomicAdd(p.hdr + kHdrViol, 1);
-        } else {
-            int32_t* nn = dir ? p.nnB : p.nnA;
-            if (nn) nn[(size_t)b * Q + q] = j;
-            mine += (double)d;
-        }
-    }
-
-    // ---- phase 3: ambiguous rows, one at a time, by the whole block: exact scan of every supertile within the window ---------
-    {
-        const unsigned ambmask = __ballot_sync(0xffffffffu, valid && amb);
-        if (lane == 0) s_amb[warp] = ambmask;
-        if (valid && amb) { s_iq[tid] = q; s_ilim[tid] = best + win; }
-        __syncthreads();
-        const float* tmb = p.tilemin + (size_t)kParts * ((size_t)b * ((size_t)p.nstB * p.NpA + (size_t)p.nstA * p.NpB) + (dir ? (size_t)p.nstB * p.NpA : 0));
-        for (int w = 0; w < kFinT / 32; ++w) {
-            const unsigned wmask = s_amb[w];
-            if (wmask && tid == 0) atomicAdd(p.hdr + kHdrAmb, __popc(wmask));
-            for (unsigned rem = wmask; rem; rem &= rem - 1) {
-                const int src = w * 32 + __ffs(rem) - 1;
-                const int qq = s_iq[src];
-                const float lim = s_ilim[src];  // NaN / inf -> scan everything (comparison below)
-                const float ax = __ldg(gQ + 3 * (size_t)qq), ay = __ldg(gQ + 3 * (size_t)qq + 1), az = __ldg(gQ + 3 * (size_t)qq + 2);
-                float d = INFINITY;
-                int j = 0x7fffffff;
-                if (tid == 0) s_nsel = 0;
-                __syncthreads();
-                for (int t0 = 0; t0 < nst; t0 += kFinT) {
-                    const int t = t0 + tid;
-                    if (t < nst) {
-                        float e1 = __ldcg(tmb + (size_t)t * kParts * npq + qq);   // the supertile's minimum: one partial per read-out group
-#pragma unroll
-                        for (int q4 = 1; q4 < kParts; ++q4) e1 = fminf(e1, __ldcg(tmb + ((size_t)t * kParts + q4) * npq + qq));
-                        if (!(fmaxf(e1, 0.0f) > lim)) {
-                            const int pos = atomicAdd(&s_nsel, 1);
-                            if (pos < kMaxSel) s_sel[pos] = t;
-                        }
-                    }
+                for (int jj = j0; jj < j1; ++jj) {
+                    const float px = __ldg(gP + 3 * (size_t)jj), py = __ldg(gP + 3 * (size_t)jj + 1), pz = __ldg(gP + 3 * (size_t)jj + 2);
+                    const float dd = dir ? sqdist3<false>(px, py, pz, qx, qy, qz) : sqdist3<false>(qx, qy, qz, px, py, pz);
+                    if (dd < d || (dd == d && jj < j)) { d = dd; j = jj; }
                 }
-                __syncthreads();
-                const int nsel = s_nsel;
-                const bool all = nsel > kMaxSel;   // tie-heavy input: more supertiles within the window than the list holds
-                const int total = all ? ((R + 3) & ~3) : nsel * kSuper;
-                for (int idx = 4 * tid; idx < total; idx += 4 * kFinT) {
-                    const int sidx = idx / kSuper, jb = all ? idx : s_sel[sidx] * kSuper + (idx - sidx * kSuper);
-                    if (jb >= R) continue;
-                    const float* pp = gP + 3 * (size_t)jb;
-                    float c[12];
-                    if (jb + 4 <= R && (reinterpret_cast<uintptr_t>(pp) & 15u) == 0) {
-                        const float4 v0 = __ldg(reinterpret_cast<const float4*>(pp));
-                        const float4 v1 = __ldg(reinterpret_cast<const float4*>(pp) + 1);
-                        const float4 v2 = __ldg(reinterpret_cast<const float4*>(pp) + 2);
-                        c[0] = v0.x; c[1] = v0.y; c[2] = v0.z; c[3] = v0.w; c[4] = v1.x; c[5] = v1.y;
-                        c[6] = v1.z; c[7] = v1.w; c[8] = v2.x; c[9] = v2.y; c[10] = v2.z; c[11] = v2.w;
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int jj = min(jb + u, R - 1);  // clamped duplicates are harmless (same value, same index)
-                            c[3 * u] = __ldg(gP + 3 * (size_t)jj); c[3 * u + 1] = __ldg(gP + 3 * (size_t)jj + 1); c[3 * u + 2] = __ldg(gP + 3 * (size_t)jj + 2);
-                        }
-                    }
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");   // a thread only reads the bytes it fetched itself: no barrier needed
+            if (staged) {
+                // row pitch 400 B = 25 x 16 B: the eight lanes of a quarter-warp hit eight different 16-byte bank groups
+#pragma unroll 2
+                for (int h = 0; h < kTcChunk / 4; ++h) {  // 4 candidates = three 16-byte shared-memory loads per trip
+                    const float4 v0 = *reinterpret_cast<const float4*>(mychunk + h * 48);
+                    const float4 v1 = *reinterpret_cast<const float4*>(mychunk + h * 48 + 16);
+                    const float4 v2 = *reinterpret_cast<const float4*>(mychunk + h * 48 + 32);
+                    const float c[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const float dd = dir ? sqdist3<false>(c[3 * u], c[3 * u + 1], c[3 * u + 2], ax, ay, az)
-                                             : sqdist3<false>(ax, ay, az, c[3 * u], c[3 * u + 1], c[3 * u + 2]);
-                        const int jj = min(jb + u, R - 1);
-                        if (dd < d || (dd == d && jj < j)) { d = dd; j = jj; }
+                        // operand order of the reference: (a - b) with a from the first cloud
+                        const float dd = dir ? sqdist3<false>(c[3 * u], c[3 * u + 1], c[3 * u + 2], qx, qy, qz)
+                                             : sqdist3<false>(qx, qy, qz, c[3 * u], c[3 * u + 1], c[3 * u + 2]);
+                        const int jj = j0 + h * 4 + u;
+                        if (dd < d || (dd == d && jj < j)) { d = dd; j = jj; }   // lowest index on ties, also across the two chunks
                     }
                 }
-                // (d, j) minimum over the block, lowest j on ties (d >= 0 or +inf: bit order == value order)
-                const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(d));
-                const int jm = __reduce_min_sync(0xffffffffu, (__float_as_uint(d) == mb) ? j : 0x7fffffff);
-                if (lane == 0) { s_wd[warp] = mb; s_wj[warp] = jm; }
-                __syncthreads();
-                if (tid == src) {
-                    unsigned bd = s_wd[0];
-                    int bj = s_wj[0];
-#pragma unroll
-                    for (int u = 1; u < kFinT / 32; ++u) {
-                        const unsigned od = s_wd[u];
-                        const int oj = s_wj[u];
-                        if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
-                    }
-                    int32_t* nn = dir ? p.nnB : p.nnA;
-                    if (nn) nn[(size_t)b * Q + qq] = bj;
-                    mine += (double)__uint_as_float(bd);
-                }
-                __syncthreads();  // s_wd / s_wj / s_nsel are reused by the next row
+            }
+        }
+        if (cert) {
+            // self-check of the error bound at the located minimum
+            if (!(fabsf(d - best) <= fmaf(kTcErrRel, d, errlim))) {
+                amb = true;
+                atomicAdd(p.hdr + kHdrViol, 1);
+            } else {
+                int32_t* nn = dir ? p.nnB : p.nnA;
+                if (nn) nn[(size_t)b * Q + q] = j;
+                mine += (double)d;
             }
         }
     }
-
-    // ---- block partial sum -> the last block reduces in a fixed order (bitwise repeatable) ---------------------------------
+    FPROF(3);
+    // ---- ambiguous rows: listed in row order for the cleanup kernel; block partial sum of the certified rows -------------
+    const unsigned ambmask = __ballot_sync(0xffffffffu, valid && amb);
     mine = warp_sum(mine);
-    if (lane == 0) s_red[warp] = mine;
+    if (lane == 0) { s_cnt[warp] = __popc(ambmask); s_red[warp] = mine; }
     __syncthreads();
+    int lbase = 0;
+    if (lane == 0 && ambmask) lbase = atomicAdd(p.hdr + kHdrAmb, __popc(ambmask));   // the work list's order is arbitrary; results go to fixed slots
+    lbase = __shfl_sync(0xffffffffu, lbase, 0);
+    if (valid && amb) {
+        const int wpos = __popc(ambmask & ((1u << lane) - 1u));
+        int pos = wpos;
+        for (int w = 0; w < warp; ++w) pos += s_cnt[w];
+        p.ambq[(size_t)blockIdx.x * kFinT + pos] = q;
+        p.amblim[(size_t)blockIdx.x * kFinT + pos] = best + win;
+        p.amblist[lbase + wpos] = (int)(blockIdx.x * kFinT + pos);
+    }
     if (tid == 0) {
-        double s = 0.0;
-        for (int w = 0; w < kFinT / 32; ++w) s += s_red[w];
-        p.partial[blockIdx.x] = s;
+        double s2 = 0.0;
+        int c = 0;
+        for (int w = 0; w < kFinT / 32; ++w) { s2 += s_red[w]; c += s_cnt[w]; }
+        p.partial[blockIdx.x] = s2;
+        p.ambcnt[blockIdx.x] = c;
+    }
+    FPROF(4);
+}
+
+// Finalize, part 2 (after part 1): the rows part 1 could not certify (~0.4 % on uniform clouds; every row of tie-heavy inputs)
+// are rescanned by a whole block each, taken from the work list: every supertile whose filter minimum lies within the row's
+// window is scanned in the reference arithmetic; the distance found goes to the row's FIXED slot.  The last block then adds
+// up the finalize blocks' partial sums and those slots in a fixed order (bitwise repeatable).
+constexpr int kCleanT = 256;
+__global__ void __launch_bounds__(kCleanT, 4) chamfer_tc_cleanup_kernel(TcFinParams p) {
+    __shared__ bool s_last;
+    constexpr int kMaxSel = 32;
+    __shared__ int s_sel[kMaxSel], s_nsel;
+    __shared__ unsigned s_wd[kCleanT / 32];
+    __shared__ int s_wj[kCleanT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kFinPerItem = kItemRows / kFinT;
+    const int ipe = p.rbA + p.rbB;
+    CPROF(0);
+    const int total_amb = __ldcg(p.hdr + kHdrAmb);
+    for (int e = blockIdx.x; e < total_amb; e += gridDim.x) {
+        const int slot = __ldcg(p.amblist + e);
+        const int fb = slot / kFinT;
+        const int item = fb / kFinPerItem;
+        const int b = item / ipe, k = item - b * ipe;
+        const bool dir = k >= p.rbA;
+        const int Q = dir ? p.M : p.N, R = dir ? p.N : p.M;
+        const int npq = dir ? p.NpB : p.NpA;
+        const int nst = dir ? p.nstA : p.nstB;                      // supertiles of the searched cloud
+        const float* gQ = (dir ? p.Bp : p.A) + (size_t)b * Q * 3;
+        const float* gP = (dir ? p.A : p.Bp) + (size_t)b * R * 3;
+        const float* tmb = p.tilemin + (size_t)kParts * ((size_t)b * ((size_t)p.nstB * p.NpA + (size_t)p.nstA * p.NpB) + (dir ? (size_t)p.nstB * p.NpA : 0));
+        const int qq = __ldcg(p.ambq + slot);
+        const float lim = __ldcg(p.amblim + slot);  // NaN / inf -> scan everything (comparison below)
+        const float ax = __ldg(gQ + 3 * (size_t)qq), ay = __ldg(gQ + 3 * (size_t)qq + 1), az = __ldg(gQ + 3 * (size_t)qq + 2);
+        float d = INFINITY;
+        int j = 0x7fffffff;
+        if (tid == 0) s_nsel = 0;
+        __syncthreads();
+        for (int t0 = 0; t0 < nst; t0 += kCleanT) {
+            const int t = t0 + tid;
+            if (t < nst) {
+                float e1 = __ldcg(tmb + (size_t)t * kParts * npq + qq);   // the supertile's minimum: one partial per column quarter
+#pragma unroll
+                for (int q4 = 1; q4 < kParts; ++q4) e1 = fminf(e1, __ldcg(tmb + ((size_t)t * kParts + q4) * npq + qq));
+                if (!(fmaxf(e1, 0.0f) > lim)) {
+                    const int pos = atomicAdd(&s_nsel, 1);
+                    if (pos < kMaxSel) s_sel[pos] = t;
+                }
+            }
+        }
+        __syncthreads();
+        const int nsel = s_nsel;
+        const bool all = nsel > kMaxSel;   // tie-heavy input: more supertiles within the window than the list holds
+        const int total = all ? ((R + 3) & ~3) : nsel * kSuper;
+        for (int idx = 4 * tid; idx < total; idx += 4 * kCleanT) {
+            const int sidx = idx / kSuper, jb = all ? idx : s_sel[sidx] * kSuper + (idx - sidx * kSuper);
+            if (jb >= R) continue;
+            const float* pp = gP + 3 * (size_t)jb;
+            float c[12];
+            if (jb + 4 <= R && (reinterpret_cast<uintptr_t>(pp) & 15u) == 0) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(pp));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(pp) + 1);
+                const float4 v2 = __ldg(reinterpret_cast<const float4*>(pp) + 2);
+                c[0] = v0.x; c[1] = v0.y; c[2] = v0.z; c[3] = v0.w; c[4] = v1.x; c[5] = v1.y;
+                c[6] = v1.z; c[7] = v1.w; c[8] = v2.x; c[9] = v2.y; c[10] = v2.z; c[11] = v2.w;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int jj = min(jb + u, R - 1);  // clamped duplicates are harmless (same value, same index)
+                    c[3 * u] = __ldg(gP + 3 * (size_t)jj); c[3 * u + 1] = __ldg(gP + 3 * (size_t)jj + 1); c[3 * u + 2] = __ldg(gP + 3 * (size_t)jj + 2);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float dd = dir ? sqdist3<false>(c[3 * u], c[3 * u + 1], c[3 * u + 2], ax, ay, az)
+                                     : sqdist3<false>(ax, ay, az, c[3 * u], c[3 * u + 1], c[3 * u + 2]);
+                const int jj = min(jb + u, R - 1);
+                if (dd < d || (dd == d && jj < j)) { d = dd; j = jj; }
+            }
+        }
+        // (d, j) minimum over the block, lowest j on ties (d >= 0 or +inf: bit order == value order)
+        const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(d));
+        const int jm = __reduce_min_sync(0xffffffffu, (__float_as_uint(d) == mb) ? j : 0x7fffffff);
+        if (lane == 0) { s_wd[warp] = mb; s_wj[warp] = jm; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned bd = s_wd[0];
+            int bj = s_wj[0];
+#pragma unroll
+            for (int u = 1; u < kCleanT / 32; ++u) {
+                const unsigned od = s_wd[u];
+                const int oj = s_wj[u];
+                if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+            }
+            int32_t* nn = dir ? p.nnB : p.nnA;
+            if (nn) nn[(size_t)b * Q + qq] = bj;
+            p.ambd[slot] = __uint_as_float(bd);
+        }
+        __syncthreads();  // s_wd / s_wj / s_nsel are reused by the next row
+    }
+    // ---- the last block adds up every partial sum in a fixed order (bitwise repeatable) -----------------------------------
+    CPROF(1);
+    if (tid == 0) {
         __threadfence();
         s_last = (atomicAdd(p.hdr + kHdrDone, 1) == (int)gridDim.x - 1);
     }
     __syncthreads();
+    CPROF(2);
     if (!s_last) return;
     __threadfence();
     double sa = 0.0, sb = 0.0;
-    for (int kk = tid; kk < (int)gridDim.x; kk += kFinT) {
-        const double v = __ldcg(p.partial + kk);
-        if ((kk / kRT) % ipe < p.rbA) sa += v; else sb += v;
+    for (int k0 = 0; k0 < p.nfin; k0 += 8 * kCleanT) {   // per finalize block: eight of them in flight per thread
+        double v[8];
+        int cn[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int kk = k0 + u * kCleanT + tid;
+            v[u] = kk < p.nfin ? __ldcg(p.partial + kk) : 0.0;
+            cn[u] = kk < p.nfin ? __ldcg(p.ambcnt + kk) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int kk = k0 + u * kCleanT + tid;
+            if (kk < p.nfin) {
+                double t = v[u];
+                for (int e = 0; e < cn[u]; ++e) t += (double)__ldcg(p.ambd + (size_t)kk * kFinT + e);   // the block's ambiguous rows, in row order
+                if ((kk / kFinPerItem) % ipe < p.rbA) sa += t; else sb += t;
+            }
+        }
     }
     sa = warp_sum(sa);
     sb = warp_sum(sb);
-    __shared__ double s_a2[kFinT / 32], s_b2[kFinT / 32];
+    __shared__ double s_a2[kCleanT / 32], s_b2[kCleanT / 32];
     if (lane == 0) { s_a2[warp] = sa; s_b2[warp] = sb; }
     __syncthreads();
     if (tid == 0) {
         double ta = 0.0, tb = 0.0;
-        for (int w = 0; w < kFinT / 32; ++w) { ta += s_a2[w]; tb += s_b2[w]; }
+        for (int w = 0; w < kCleanT / 32; ++w) { ta += s_a2[w]; tb += s_b2[w]; }
         const float dAB = (float)(ta / p.denomA), dBA = (float)(tb / p.denomB);  // pcloud.jl:47-48
         if (p.terms) { p.terms[0] = dAB; p.terms[1] = dBA; }
         const float l = __fadd_rn(__fmul_rn(p.w1, dAB), __fmul_rn(p.w2, dBA));   // pcloud.jl:50
         if (p.peer.nranks <= 1) p.loss[0] = l;
         s_a2[0] = (double)l;
     }
+    CPROF(3);
     if (p.peer.nranks <= 1) return;
     // the one exchange of the sharded path, fused (see chamfer.cu: chamfer_filter_finalize_kernel)
     __shared__ float s_v[kMaxPeerRanks];
@@ -775,8 +1013,8 @@ __global__ void __launch_bounds__(kFinT, 7) chamfer_tc_finalize_kernel(TcFinPara
 }
 
 struct TcPlan {
-    int NpA, NpB, rbA, rbB, nstA, nstB, nblocks;
-    size_t off_PA, off_PB, off_rowfin, off_tilemin, off_partial, zero_from, off_hdr, off_maxn, off_done, zero_bytes, total;
+    int NpA, NpB, rbA, rbB, nstA, nstB, nblocks, nfin, nitems;
+    size_t off_PA, off_PB, off_rowfin, off_tilemin, off_partial, off_ambcnt, off_ambq, off_amblim, off_amblist, off_ambd, zero_from, off_hdr, off_maxn, off_done, off_arrived, zero_bytes, total;
 };
 
 TcPlan make_tc_plan(int B, int N, int M) {
@@ -787,18 +1025,26 @@ TcPlan make_tc_plan(int B, int N, int M) {
     pl.rbB = pl.NpB / kItemRows;
     pl.nstA = (pl.NpA + kSuper - 1) / kSuper;
     pl.nstB = (pl.NpB + kSuper - 1) / kSuper;
-    pl.nblocks = B * (pl.rbA + pl.rbB) * kRT;
+    pl.nitems = B * (pl.rbA + pl.rbB);
+    pl.nblocks = pl.nitems * kRT;                 // row tiles
+    pl.nfin = pl.nblocks * (kTQ / kFinT);         // finalize blocks
     size_t o = 0;
     pl.off_hdr = o;     o = align_up(o + sizeof(int) * kHdrInts, 256);   // diagnostics first: a caller can find them
     pl.off_maxn = o;    o = align_up(o + sizeof(unsigned) * 2 * (size_t)B, 256);
     pl.off_done = o;    o = align_up(o + sizeof(int) * (size_t)pl.nblocks, 256);
+    pl.off_arrived = o; o = align_up(o + sizeof(int) * 2 * (size_t)B, 256);   // upload mode: arrived [B], prepared [B]
     pl.zero_from = 0;
     pl.zero_bytes = o;  // header, norm maxima and completion counters are zeroed by ONE memset per call
     pl.off_PA = o;      o = align_up(o + sizeof(float4) * (size_t)B * pl.NpA, 256);
     pl.off_PB = o;      o = align_up(o + sizeof(float4) * (size_t)B * pl.NpB, 256);
     pl.off_rowfin = o;  o = align_up(o + sizeof(float4) * (size_t)B * (pl.NpA + pl.NpB), 256);
     pl.off_tilemin = o; o = align_up(o + sizeof(float) * kParts * (size_t)B * ((size_t)pl.nstB * pl.NpA + (size_t)pl.nstA * pl.NpB), 256);
-    pl.off_partial = o; o = align_up(o + sizeof(double) * (size_t)pl.nblocks, 256);
+    pl.off_partial = o; o = align_up(o + sizeof(double) * (size_t)pl.nfin, 256);
+    pl.off_ambcnt = o;  o = align_up(o + sizeof(int) * (size_t)pl.nfin, 256);
+    pl.off_ambq = o;    o = align_up(o + sizeof(int) * (size_t)pl.nfin * kFinT, 256);
+    pl.off_amblim = o;  o = align_up(o + sizeof(float) * (size_t)pl.nfin * kFinT, 256);
+    pl.off_amblist = o; o = align_up(o + sizeof(int) * (size_t)pl.nfin * kFinT, 256);
+    pl.off_ambd = o;    o = align_up(o + sizeof(float) * (size_t)pl.nfin * kFinT, 256);
     pl.total = o;
     return pl;
 }
@@ -810,20 +1056,27 @@ constexpr size_t kTcSmem = 2 * kRT * kTQ * kRowB + kStages * kTNc * kRowB + kCSt
 size_t chamfer_tc_workspace_bytes(int B, int N, int M) { return make_tc_plan(B, N, M).total; }
 #ifdef F3D_TC_PROF
 extern "C" __attribute__((visibility("default"))) int f3d_debug_read_tc(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, g_tcprof, nbytes); }
+extern "C" __attribute__((visibility("default"))) int f3d_debug_read_fin(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, g_finprof, nbytes); }
+extern "C" __attribute__((visibility("default"))) int f3d_debug_read_clean(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, g_cleanprof, nbytes); }
 #endif
 
 // The tensor-core sweep wants enough 256-row work items to keep every SM's pipeline full for a few items; smaller problems
 // stay on the CUDA-core sweep of chamfer.cu (one tile per CTA fills the machine from 592 tiles of 256 x 1024 pairs on).
-bool chamfer_tc_supported(int B, int N, int M) {
+bool chamfer_tc_possible(int B, int N, int M) {
     if (B <= 0 || N < 1 || M < 1) return false;
     const TcPlan pl = make_tc_plan(B, N, M);
-    if ((long long)B * (pl.rbA + pl.rbB) * kRT > 0x3fffffffLL) return false;
+    if ((long long)B * (pl.rbA + pl.rbB) * kRT * (kTQ / kFinT) > 0x3fffffffLL) return false;
+    return std::max(pl.NpA, pl.NpB) / kTcChunk <= 0xffff;   // chunk ids travel as 16 bits
+}
+bool chamfer_tc_supported(int B, int N, int M) {
+    if (!chamfer_tc_possible(B, N, M)) return false;
+    const TcPlan pl = make_tc_plan(B, N, M);
     return (long long)B * (pl.rbA + pl.rbB) >= 2 * 148 && std::min(N, M) >= 512;
 }
 
 int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M, float w1, float w2, int32_t B_total,
                           float* loss_dev, float* terms_dev, int32_t* nnA_dev, int32_t* nnB_dev, void* ws, size_t ws_bytes, int32_t flags,
-                          cudaStream_t stream, const ChamferPeerSum* peer) {
+                          cudaStream_t stream, const ChamferUpload* upload, const ChamferPeerSum* peer) {
     const TcPlan pl = make_tc_plan(B, N, M);
     if (!ws || ws_bytes < pl.total) return fail(F3D_ERR_WORKSPACE, "f3d_chamfer_fwd: workspace %zu < required %zu bytes", ws_bytes, pl.total);
     unsigned char* w = static_cast<unsigned char*>(ws);
@@ -837,6 +1090,8 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
         // 130 KB) no finalize block (2.5 KB of shared memory) finds room, and the whole finalize runs after the sweep
         F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinT * kFinPitch));
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_cleanup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         int sms = 0;
         F3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (dev >= 0 && dev < 256) { sm_count[dev] = sms; attr_done[dev] = 1; }
@@ -849,8 +1104,24 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
     pp.PA = reinterpret_cast<float4*>(w + pl.off_PA);
     pp.PB = reinterpret_cast<float4*>(w + pl.off_PB);
     pp.maxn = reinterpret_cast<unsigned*>(w + pl.off_maxn);
-    chamfer_tc_prepare_kernel<<<dim3((std::max(pl.NpA, pl.NpB) + kPrepT - 1) / kPrepT, B, 2), kPrepT, 0, stream>>>(pp);
-    F3D_CHECK_LAUNCH("chamfer_tc_prepare_kernel");
+    int prepared_target = 0;
+    if (upload) {
+        // host arrays: A / Bp are staging buffers; one grid uploads and prepares, element by element, beside the sweep
+        TcUploadParams up;
+        up.pp = pp;
+        up.hA = upload->A_host_dev; up.hB = upload->B_host_dev;
+        up.dA = const_cast<float*>(A); up.dB = const_cast<float*>(Bp);
+        up.B = B; up.U = std::max(1, std::min(upload->uploaders, 128)); up.P = 16;
+        up.arrived = reinterpret_cast<unsigned*>(w + pl.off_arrived);
+        up.prepared = reinterpret_cast<int*>(w + pl.off_arrived) + B;
+        up.hdr = reinterpret_cast<int*>(w + pl.off_hdr);
+        prepared_target = up.P;
+        chamfer_tc_upload_prepare_kernel<<<up.U + up.P, kUpT, 0, stream>>>(up);
+        F3D_CHECK_LAUNCH("chamfer_tc_upload_prepare_kernel");
+    } else {
+        chamfer_tc_prepare_kernel<<<dim3((std::max(pl.NpA, pl.NpB) + kPrepT - 1) / kPrepT, B, 2), kPrepT, 0, stream>>>(pp);
+        F3D_CHECK_LAUNCH("chamfer_tc_prepare_kernel");
+    }
 
     TcSweepParams sp;
     sp.PA = pp.PA; sp.PB = pp.PB; sp.B = B; sp.NpA = pl.NpA; sp.NpB = pl.NpB; sp.rbA = pl.rbA; sp.rbB = pl.rbB;
@@ -858,7 +1129,9 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
     sp.tilemin = reinterpret_cast<float*>(w + pl.off_tilemin);
     sp.nstA = pl.nstA; sp.nstB = pl.nstB;
     sp.done = reinterpret_cast<int*>(w + pl.off_done);
-    sp.wait_prepare = 1;
+    sp.wait_prepare = upload ? 0 : 1;
+    sp.prepared = upload ? reinterpret_cast<const int*>(w + pl.off_arrived) + B : nullptr;
+    sp.prepared_target = prepared_target;
     const int nitems = B * (pl.rbA + pl.rbB);
     {
         cudaLaunchConfig_t cfg = {};
@@ -878,6 +1151,12 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
     fp.rowfin = sp.rowfin; fp.tilemin = sp.tilemin; fp.maxn = pp.maxn; fp.done = sp.done;
     fp.nnA = nnA_dev; fp.nnB = nnB_dev;
     fp.partial = reinterpret_cast<double*>(w + pl.off_partial);
+    fp.ambcnt = reinterpret_cast<int*>(w + pl.off_ambcnt);
+    fp.ambq = reinterpret_cast<int*>(w + pl.off_ambq);
+    fp.amblim = reinterpret_cast<float*>(w + pl.off_amblim);
+    fp.amblist = reinterpret_cast<int*>(w + pl.off_amblist);
+    fp.ambd = reinterpret_cast<float*>(w + pl.off_ambd);
+    fp.nfin = pl.nfin;
     fp.hdr = reinterpret_cast<int*>(w + pl.off_hdr);
     fp.w1 = w1; fp.w2 = w2;
     fp.denomA = (double)N * (double)B_total;
@@ -887,7 +1166,7 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
     else { fp.peer.mailboxes = nullptr; fp.peer.nranks = 0; fp.peer.rank = 0; fp.peer.seq = 0; fp.peer.timeout_ns = 0; fp.peer.fault = nullptr; }
     {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(pl.nblocks); cfg.blockDim = dim3(kFinT); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cfg.gridDim = dim3(pl.nfin); cfg.blockDim = dim3(kFinT); cfg.dynamicSmemBytes = kFinT * kFinPitch; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -898,6 +1177,8 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
         F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_tc_finalize_kernel, fp));
     }
     F3D_CHECK_LAUNCH("chamfer_tc_finalize_kernel");
+    chamfer_tc_cleanup_kernel<<<std::min(pl.nfin, 8 * sms), kCleanT, 0, stream>>>(fp);
+    F3D_CHECK_LAUNCH("chamfer_tc_cleanup_kernel");
     return F3D_OK;
 }
 

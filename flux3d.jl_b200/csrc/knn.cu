@@ -386,6 +386,52 @@ bool knn_tc_supported(int N, int F, int K);
 int32_t knn_tc_launch(const float* X, int B, int N, int F, int K, int32_t* idx, float* dist, float* gathered, float* edge, unsigned* stats, cudaStream_t stream);
 }  // namespace f3d
 
+
+namespace f3d {
+namespace {
+// Edge features straight in the layout EdgeConv's 1x1-conv MLP consumes (src/models/dgcnn.jl:46-52): the reference builds
+// cat(X, KNNGraph - X; dims=1) as (2F, K, N, B), then PermutedDimsArray(.., (2,3,1,4)) and reshape to (K*N, 2F, B) — a full
+// permuting copy (336 MB at cfg3, F = 64).  Here E[b][c][n][k] (C order == Julia (K*N, 2F, B)) is written once:
+//   c <  F: x_n[c]                    c >= F: x_{idx[n][k]}[c - F] - x_n[c - F]
+// CTA = kEmitPts points of one cloud x a slice of 8 features: thread <-> (point, neighbour) pair gathers 32 bytes of the
+// neighbour's row (one sector), the (slice x pairs) tile is transposed through shared memory, and every output channel row
+// of the tile — kEmitPts*K consecutive floats — leaves with coalesced stores.
+constexpr int kEmitPts = 32, kEmitFS = 8, kEmitThreads = 256;
+__global__ void __launch_bounds__(kEmitThreads) knn_edge_mlp_kernel(const float* __restrict__ X, const int32_t* __restrict__ idx, int N, int F, int K,
+                                                                    float* __restrict__ E) {
+    extern __shared__ float s_t[];                       // [2][kEmitFS][NK]: centre halves, difference halves
+    const int b = blockIdx.y, n0 = blockIdx.x * kEmitPts;
+    const int np = min(kEmitPts, N - n0), NK = np * K, NKp = kEmitPts * K;
+    const float* Xb = X + (size_t)b * N * F;
+    const int32_t* ib = idx + ((size_t)b * N + n0) * K;
+    for (int c0 = 0; c0 < F; c0 += kEmitFS) {
+        const int fs = min(kEmitFS, F - c0);
+        for (int pr = threadIdx.x; pr < NK; pr += kEmitThreads) {
+            const int n = pr / K;
+            const float* xi = Xb + (size_t)(n0 + n) * F + c0;
+            const float* xj = Xb + (size_t)__ldg(ib + pr) * F + c0;
+#pragma unroll
+            for (int c = 0; c < kEmitFS; ++c) {
+                if (c < fs) {
+                    const float a = __ldg(xi + c);
+                    s_t[c * NKp + pr] = a;
+                    s_t[(kEmitFS + c) * NKp + pr] = __fsub_rn(__ldg(xj + c), a);   // KNNGraph - X  (dgcnn.jl:45)
+                }
+            }
+        }
+        __syncthreads();
+        for (int h = 0; h < 2; ++h)
+            for (int c = 0; c < fs; ++c) {
+                float* dst = E + (((size_t)b * 2 * F + (size_t)h * F + c0 + c) * N + n0) * K;
+                const float* src = s_t + (h * kEmitFS + c) * NKp;
+                for (int pr = threadIdx.x; pr < NK; pr += kEmitThreads) dst[pr] = src[pr];
+            }
+        __syncthreads();
+    }
+}
+}  // namespace
+}  // namespace f3d
+
 extern "C" size_t f3d_knn_graph_workspace_bytes(int32_t, int32_t, int32_t, int32_t) { return 256; }
 
 extern "C" int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F, int32_t K, int32_t* idx,
@@ -398,8 +444,19 @@ extern "C" int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F
     if (K > 63) return fail(F3D_ERR_INVALID, "f3d_knn_graph: K must be <= 63 (got %d)", K);
     if (F > 256) return fail(F3D_ERR_INVALID, "f3d_knn_graph: F must be <= 256 (got %d)", F);
     if (B > 65535) return fail(F3D_ERR_INVALID, "f3d_knn_graph: B must be <= 65535 per call");
-    if (flags & ~(F3D_FLAG_EXACT_SWEEP | F3D_FLAG_TENSOR)) return fail(F3D_ERR_INVALID, "f3d_knn_graph: only F3D_FLAG_EXACT_SWEEP / F3D_FLAG_TENSOR are defined for this call");
+    if (flags & ~(F3D_FLAG_EXACT_SWEEP | F3D_FLAG_TENSOR | F3D_FLAG_EDGE_MLP_LAYOUT))
+        return fail(F3D_ERR_INVALID, "f3d_knn_graph: only F3D_FLAG_EXACT_SWEEP / F3D_FLAG_TENSOR / F3D_FLAG_EDGE_MLP_LAYOUT are defined for this call");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if ((flags & F3D_FLAG_EDGE_MLP_LAYOUT) && edge_feat) {
+        // neighbour search without the (2F,K,N,B) edge tensor, then the edge features once, in the MLP's layout
+        const int32_t rc = f3d_knn_graph(X, B, N, F, K, idx, dist, gathered, nullptr, ws, ws_bytes, flags & ~F3D_FLAG_EDGE_MLP_LAYOUT, stream_);
+        if (rc != F3D_OK) return rc;
+        const size_t smem = sizeof(float) * 2 * kEmitFS * kEmitPts * (size_t)K;
+        F3D_CUDA(cudaFuncSetAttribute(knn_edge_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_edge_mlp_kernel<<<dim3((N + kEmitPts - 1) / kEmitPts, B), kEmitThreads, smem, stream>>>(X, idx, N, F, K, edge_feat);
+        F3D_CHECK_LAUNCH("knn_edge_mlp_kernel");
+        return F3D_OK;
+    }
     // default for wide features (F >= 16, where evaluating the distances dominates): Gram matrix on the tensor cores
     // as a filter + exact re-evaluation (bit-identical results); narrow features are selection-bound and stay on the CUDA cores;
     // F3D_FLAG_EXACT_SWEEP or shapes outside that path: every pair in the reference arithmetic on the CUDA cores

@@ -7,8 +7,9 @@
 //
 // The tensor cores see TF32 (10-bit mantissa), so the Gram matrix is only a FILTER — exactly the certify-and-
 // re-evaluate scheme of the chamfer sweep:
-//   d~_ij = |x_i|² + |x_j|² - 2 G~_ij,   |d~ - d| <= E_i := 2^-7.5 |x_i| max_j|x_j|        (truncation to TF32 costs at
-//   most 2^-10 relative per operand; FP32 accumulation of <= 64 exact products adds < 2^-17)
+//   d~_ij = |x_i|² + |x_j|² - 2 G~_ij,   |d~ - d| <= E_i := 2^-7.5 |x_i| max_j|x_j| + 2 (F+4) u (|x_i|² + max_j|x_j|²)
+//   (truncation to TF32 costs at most 2^-10 relative per operand; FP32 accumulation of <= 64 exact products adds < 2^-17;
+//   the second term covers the FP32 roundings of the norms and of the final fma, which do not vanish with |x_i|)
 // FOUR THREADS own one query (its TMEM lane; thread = (lane quadrant warp%4, column quarter warp/4) of a 16-warp CTA):
 //   pass 1  stream the row of d~ out of TMEM, 32 columns of every 128-column tile per thread; keep the two smallest of
 //           every 32-column group; the 64 local minima of a query are exchanged through shared memory and a
@@ -333,7 +334,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(KnnTcParams p) {
 #pragma unroll
                 for (int i = 1; i < 64; ++i) Tsel = (i == p.K) ? gm[i] : Tsel;  // (K+1)-th smallest, K < 64
                 // collect threshold: T~ + 2 E (E bounds |d~ - d|); not finite => collect everything (and overflow to the exact scan)
-                thr = Tsel + 2.0f * kErrRel * sqrtf(nq) * sqrtf(__uint_as_float(s_maxnc));
+                // ... plus an ABSOLUTE term for the filter's own FP32 roundings, which do not shrink with |x_i|: the norms are
+                // summed in another order than the exact distance (<= F u each, relative), the add nq + n and the fma round once
+                // more — <= (F + 3) u (nq + max n), doubled for slack.  Without it a query of zero / tiny norm (zero-padded
+                // points, dead ReLU features) got thr == Tsel and a near-tied true neighbour could be filtered out.
+                const float maxnc = __uint_as_float(s_maxnc);
+                thr = Tsel + 2.0f * (kErrRel * sqrtf(nq) * sqrtf(maxnc) + 2.0f * (float)(p.F + 4) * 5.9604645e-8f * (nq + maxnc));
             }
         }
     }

@@ -86,6 +86,46 @@ def allreduce_loss_(loss: torch.Tensor, comm=None) -> torch.Tensor:
     return loss
 
 
+class _ShardedChamferFn(torch.autograd.Function):
+    """chamfer_distance of a batch sharded over ranks, differentiable with respect to this rank's shard: the loss every rank
+    holds is the whole batch's, so d loss / d shard is the single-GPU pullback (src/metrics/pcloud.jl:47-50) evaluated with
+    the global N*B_total / M*B_total — f3d_chamfer_bwd with batch_total; no further exchange is needed."""
+
+    @staticmethod
+    def forward(ctx, A, B, w1, w2, batch_total, comm, flags):
+        L = _lib.lib()
+        Bn, N, M = A.shape[0], A.shape[1], B.shape[1]
+        dev = A.device
+        nnA = torch.empty((Bn, N), dtype=torch.int32, device=dev)
+        nnB = torch.empty((Bn, M), dtype=torch.int32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        Ad, Bd = A.detach().contiguous(), B.detach().contiguous()
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(("chamfer", Bn, N, M), L.f3d_chamfer_workspace_bytes(Bn, N, M), dev)
+            if comm is not None and getattr(comm, "p2p", False) and not flags:
+                _lib.check(L.f3d_chamfer_fwd_allreduce(comm._h, _lib.ptr(Ad), _lib.ptr(Bd), Bn, N, M, w1, w2, batch_total, _lib.ptr(loss),
+                                                       _lib.ptr(nnA), _lib.ptr(nnB), _lib.ptr(ws), ws.numel(), 0, _lib.stream_ptr(dev)))
+            else:
+                _lib.check(L.f3d_chamfer_fwd(_lib.ptr(Ad), _lib.ptr(Bd), Bn, N, M, w1, w2, batch_total, _lib.ptr(loss), None,
+                                             _lib.ptr(nnA), _lib.ptr(nnB), _lib.ptr(ws), ws.numel(), flags, _lib.stream_ptr(dev)))
+                allreduce_loss_(loss, comm)
+        ctx.save_for_backward(Ad, Bd, nnA, nnB)
+        ctx.cfg = (w1, w2, batch_total)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        A, B, nnA, nnB = ctx.saved_tensors
+        w1, w2, batch_total = ctx.cfg
+        L = _lib.lib()
+        gA, gB = torch.empty_like(A), torch.empty_like(B)
+        g = gout.to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(A.device):
+            _lib.check(L.f3d_chamfer_bwd(_lib.ptr(A), _lib.ptr(B), A.shape[0], A.shape[1], B.shape[1], w1, w2, batch_total,
+                                         _lib.ptr(nnA), _lib.ptr(nnB), _lib.ptr(g), _lib.ptr(gA), _lib.ptr(gB), _lib.stream_ptr(A.device)))
+        return gA, gB, None, None, None, None, None
+
+
 def chamfer_distance_sharded(A_shard, B_shard, batch_total: int, *, w1: float = 1.0, w2: float = 1.0, comm=None,
                              flags: int = 0, to_host: bool = False) -> torch.Tensor:
     """chamfer_distance over a batch split across ranks: every rank passes its shard (b_local, N, 3) /
@@ -93,6 +133,10 @@ def chamfer_distance_sharded(A_shard, B_shard, batch_total: int, *, w1: float = 
     N*B_total / M*B_total) are summed with one all-reduce, so every rank returns the reference's value for
     the whole batch.  A rank with an empty shard contributes 0."""
     from .metrics import chamfer_forward_host, chamfer_forward_raw
+    if isinstance(A_shard, torch.Tensor) and isinstance(B_shard, torch.Tensor) and A_shard.is_cuda and (A_shard.requires_grad or B_shard.requires_grad) \
+            and torch.is_grad_enabled():
+        # differentiable: the forward keeps the argmin indices, the pullback is f3d_chamfer_bwd with the GLOBAL denominators
+        return _ShardedChamferFn.apply(A_shard, B_shard, float(w1), float(w2), int(batch_total), comm, int(flags))
     if comm is not None and getattr(comm, "p2p", False) and not flags:
         # fused exchange: the finalize kernel's last block trades the shard losses with its peers through mailboxes
         # mapped over NVLink — no NCCL call, no extra launch.  Every rank must take part, so shards may not be empty.

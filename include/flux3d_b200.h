@@ -68,7 +68,11 @@ enum {
     /* f3d_chamfer_fwd: keep the filter sweep on the CUDA cores (packed-FP32 FFMA2 expanded form, chamfer.cu) also for
        problems large enough for the tensor-core sweep (tcgen05 split-TF32 filter, chamfer_tc.cu), which is the default
        from 296 work items of 256 query rows on.  Results are bit-identical either way. */
-    F3D_FLAG_CUDA_CORES = 16
+    F3D_FLAG_CUDA_CORES = 16,
+    /* f3d_knn_graph: write edge_feat in the layout EdgeConv's 1x1-convolution MLP consumes — C [B][2F][N][K], i.e. the Julia
+       (K*N, 2F, B) array of src/models/dgcnn.jl:46-52 — instead of [B][N][K][2F] == Julia (2F, K, N, B) (:45): the reference's
+       PermutedDimsArray + reshape copy of the whole edge tensor disappears. */
+    F3D_FLAG_EDGE_MLP_LAYOUT = 32
 };
 
 enum {
@@ -136,7 +140,8 @@ F3D_API int32_t f3d_chamfer_bwd(const float* A, const float* Bp, int32_t B, int3
  *   sorted ascending by (squared distance, index).  1 <= K < N, K <= 63, F <= 256.
  *   idx [B][N][K] (required); dist [B][N][K] (optional squared distances);
  *   gathered [B][N][K][F] (optional; == the Julia (F,K,N,B) KNNGraph tensor of :36);
- *   edge_feat [B][N][K][2F] (optional; == cat(X, KNNGraph - X; dims=1) of :45).
+ *   edge_feat [B][N][K][2F] (optional; == cat(X, KNNGraph - X; dims=1) of :45); with F3D_FLAG_EDGE_MLP_LAYOUT it is written
+ *     as [B][2F][N][K] == the (K*N, 2F, B) input of the MLP (:46-52) instead.
  *   N <= 1024, 16 <= F <= 64, K <= 31 run the Gram matrix on the tensor cores (tcgen05, TF32) as a filter and re-evaluate the
  *   surviving candidates in the reference arithmetic — results are bit-identical to the all-exact CUDA-core kernel,
  *   which F3D_FLAG_EXACT_SWEEP (or any larger shape) selects.  ws is optional: when >= 8 bytes are given, two

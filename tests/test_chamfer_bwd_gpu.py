@@ -49,3 +49,32 @@ def test_pointcloud_front_end(f3d, oracle):
     assert np.array_equal(nnA.cpu().numpy(), oA) and np.array_equal(nnB.cpu().numpy(), oB)
     with pytest.raises(ValueError):
         f3d.chamfer_distance(np.zeros((2, 5, 3), np.float32), np.zeros((3, 5, 3), np.float32))
+
+
+def test_backward_is_bitwise_repeatable_and_covers_both_paths(f3d, oracle):
+    """Clouds of up to 8192 points take the sorted-gather pullback (one launch, no atomics): bitwise identical reruns, also with
+    many sources pulling on one target.  Larger clouds take the RED.ADD fallback: still within float32 round-off of the oracle."""
+    rng = np.random.default_rng(11)
+    A = rng.random((3, 5000, 3), dtype=np.float32)
+    Bc = rng.random((3, 40, 3), dtype=np.float32)          # every point of B is the target of ~125 points of A
+    grads = []
+    for _ in range(3):
+        tA = torch.from_numpy(A).cuda().requires_grad_(True)
+        tB = torch.from_numpy(Bc).cuda().requires_grad_(True)
+        f3d.chamfer_distance(tA, tB, w1=0.5, w2=2.0).backward()
+        grads.append((tA.grad.clone(), tB.grad.clone()))
+    assert all(torch.equal(g[0], grads[0][0]) and torch.equal(g[1], grads[0][1]) for g in grads[1:])
+    _, nA, nB, _ = oracle.chamfer_distance(A, Bc, 0.5, 2.0, return_all=True)
+    gA, gB = oracle.chamfer_backward(A, Bc, nA, nB, 0.5, 2.0)
+    assert np.allclose(grads[0][0].cpu().numpy(), gA, rtol=1e-4, atol=1e-10)
+    assert np.allclose(grads[0][1].cpu().numpy(), gB, rtol=2e-4, atol=1e-10)
+    # beyond 8192 points per cloud: the two-launch path
+    A2 = rng.random((1, 9000, 3), dtype=np.float32)
+    B2 = rng.random((1, 300, 3), dtype=np.float32)
+    tA = torch.from_numpy(A2).cuda().requires_grad_(True)
+    tB = torch.from_numpy(B2).cuda().requires_grad_(True)
+    f3d.chamfer_distance(tA, tB).backward()
+    _, nA, nB, _ = oracle.chamfer_distance(A2, B2, return_all=True)
+    gA, gB = oracle.chamfer_backward(A2, B2, nA, nB)
+    assert np.allclose(tA.grad.cpu().numpy(), gA, rtol=1e-4, atol=1e-10)
+    assert np.allclose(tB.grad.cpu().numpy(), gB, rtol=2e-4, atol=1e-10)

@@ -260,6 +260,11 @@ def test_host_pipeline_parity(f3d, oracle, B, N, M, chunks):
     # the same kernels on the same bytes: identical to the resident-input call, wherever the host bytes live and
     # however the upload was cut
     assert lh.item() == ld and lh2.item() == ld and lh3.item() == ld and lx.item() == ld
+    # the tensor-core sweep with the upload + prepare grid running beside it (what large host batches take by default)
+    lt = f3d.chamfer_forward_host(pA, pB, 0.7, 1.3, uploaders=chunks, to_host=True, flags=f3d.FLAG_TENSOR)
+    lt2 = f3d.chamfer_forward_host(A, Bc, 0.7, 1.3, uploaders=chunks, flags=f3d.FLAG_TENSOR)   # pageable: copied first
+    torch.cuda.synchronize()
+    assert abs(lt.item() - ld) <= 1e-6 * ld and lt2.item() == lt.item()
 
 
 def test_host_pipeline_repeated_and_interleaved(f3d, oracle):
@@ -320,3 +325,15 @@ def test_host_pipeline_errors(f3d):
     assert L.f3d_chamfer_pipe_run(h, P(A), P(A), 2, 8, 8, 1.0, 1.0, 0, None, host, P(ws), ws.numel(), 0, None, s) == 0
     assert host[0] == 0.0  # loss_host given: copied back and synchronised inside the call
     assert L.f3d_chamfer_pipe_destroy(h) == 0
+
+
+def test_host_pipeline_tensor_path_full_size(f3d, oracle):
+    """cfg2 from page-locked host arrays: the default path is the tensor-core sweep fed by the in-grid upload (batch elements are
+    swept while later ones still cross PCIe) — same loss as on resident inputs, bit for bit, repeatedly."""
+    A = np.random.default_rng(201).random((32, 4096, 3), dtype=np.float32)
+    B = np.random.default_rng(202).random((32, 4096, 3), dtype=np.float32)
+    pA, pB = torch.from_numpy(A).pin_memory(), torch.from_numpy(B).pin_memory()
+    ld, *_ = _run(f3d, A, B)
+    for _ in range(3):
+        assert f3d.chamfer_forward_host(pA, pB, to_host=True).item() == ld
+    assert abs(ld - 0.0028460352) <= 1e-5 * 0.0028460352

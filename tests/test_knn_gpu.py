@@ -101,3 +101,55 @@ def test_knn_tensor_path_is_a_real_filter(f3d):
         queries = 8 * 1024
         assert st[0] == 0, (F, K, st)                          # nobody overflows to the exact scan on random clouds
         assert (K + 1) * queries <= st[1] <= 4 * (K + 1) * queries, (F, K, st)
+
+
+@pytest.mark.parametrize("B,N,F,K", [(2, 300, 3, 20), (3, 257, 64, 10), (1, 100, 5, 7), (2, 1024, 16, 31)])
+def test_edge_features_mlp_layout(f3d, oracle, B, N, F, K):
+    """F3D_FLAG_EDGE_MLP_LAYOUT: the edge features arrive as (B, 2F, N, K) == the Julia (K*N, 2F, B) array that
+    PermutedDimsArray(X, (2,3,1,4)) + reshape produce at src/models/dgcnn.jl:46-52 — bit-identical to the oracle's
+    cat(X, KNNGraph - X) permuted that way."""
+    X = np.random.default_rng(300 + F).standard_normal((B, N, F)).astype(np.float32)
+    out = f3d.knn_graph(torch.from_numpy(X).cuda(), K, want_edge=True, mlp_layout=True)
+    idx = oracle.knn_graph(X, K)
+    assert np.array_equal(out["idx"].cpu().numpy(), idx)
+    want = np.ascontiguousarray(oracle.edge_features(X, idx).transpose(0, 3, 1, 2))     # (B,N,K,2F) -> (B,2F,N,K)
+    assert out["edge"].shape == (B, 2 * F, N, K)
+    assert np.array_equal(out["edge"].cpu().numpy(), want)
+
+
+def test_edge_features_are_differentiable_in_x(f3d):
+    """Only CreateSingleKNNGraph is @nograd in the reference (dgcnn.jl:9); X flows through cat(X, KNNGraph - X) (dgcnn.jl:39-45):
+    the gradient must equal that of the same expression built from torch gathers with the indices held constant."""
+    X = torch.randn(2, 200, 6, device="cuda", dtype=torch.float32)
+    K = 8
+    for mlp_layout in (False, True):
+        Xa = X.clone().requires_grad_(True)
+        E = f3d.edgeconv_features(Xa, K, mlp_layout=mlp_layout)
+        w = torch.randn_like(E)
+        (E * w).sum().backward()
+        idx = f3d.knn_graph(X, K)["idx"].long()
+        Xb = X.clone().double().requires_grad_(True)
+        nb = torch.gather(Xb.unsqueeze(1).expand(-1, 200, -1, -1), 2, idx.unsqueeze(-1).expand(-1, -1, -1, 6))   # (B,N,K,F)
+        ref = torch.cat([Xb.unsqueeze(2).expand(-1, -1, K, -1), nb - Xb.unsqueeze(2)], dim=-1)
+        if mlp_layout:
+            ref = ref.permute(0, 3, 1, 2)
+        assert torch.equal(E.detach(), ref.detach().float())
+        (ref * w.double()).sum().backward()
+        assert torch.allclose(Xa.grad.double(), Xb.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_knn_tensor_path_zero_norm_queries(f3d, oracle):
+    """Zero / tiny-norm queries (zero-padded points, dead ReLU features): the TF32 filter's window must not collapse to the
+    selection threshold — near-tied neighbours of such a query have to survive into the exact re-evaluation."""
+    rng = np.random.default_rng(77)
+    N, F, K = 512, 32, 20
+    X = rng.standard_normal((2, N, F)).astype(np.float32)
+    X[:, :8] = 0.0                                     # all-zero rows (exact duplicates of each other)
+    X[:, 8:16] *= np.float32(1e-6)                     # tiny norms
+    # a shell of near-tied neighbours around the origin: |x| = 1 up to a few ulps
+    shell = rng.standard_normal((2, 64, F)).astype(np.float32)
+    shell /= np.linalg.norm(shell, axis=-1, keepdims=True)
+    X[:, 16:80] = shell * (1.0 + rng.integers(-3, 4, (2, 64, 1)) * np.float32(2.0 ** -23))
+    for flags in (0, f3d.FLAG_TENSOR):
+        out = f3d.knn_graph(torch.from_numpy(X).cuda(), K, want_dist=True, flags=flags)
+        assert np.array_equal(out["idx"].cpu().numpy(), oracle.knn_graph(X, K))
