@@ -117,6 +117,10 @@ extern "C" int32_t f3d_chamfer_pipe_run(void* pipe, const float* A_host, const f
         up.B_host_dev = up.A_host_dev ? device_view(B_host) : nullptr;
     }
     const bool in_grid = up.A_host_dev && up.B_host_dev;
+    // In-grid upload: the CUDA-core sweep is the default carrier — its uploaders are CTAs of the sweep grid itself and the
+    // whole call is a memset + two launches (cfg2, host arrays -> host scalar: 204 us against 221 us for the tensor-core sweep
+    // with its separate upload + prepare grid, profiles/r02h_e2e_paths.txt).  F3D_FLAG_TENSOR selects the latter.
+    if (in_grid && !(flags & F3D_FLAG_TENSOR)) flags |= F3D_FLAG_CUDA_CORES;
     if (!in_grid) {
         F3D_CUDA(cudaMemcpyAsync(dA, A_host, sizeof(float) * 3 * (size_t)B * N, cudaMemcpyHostToDevice, stream));
         F3D_CUDA(cudaMemcpyAsync(dB, B_host, sizeof(float) * 3 * (size_t)B * M, cudaMemcpyHostToDevice, stream));

@@ -65,7 +65,13 @@ constexpr int kTcThreads = (kEpiWarps + kConvWarps + 4) * 32;   // 768: six warp
 // Registers: the CTA is launched with kLaunchRegs per thread; the four read-out warpgroups then grow to kEpiRegs — both
 // tcgen05.ld of an accumulator quarter are in flight at once, 64 registers of data — and the other two shrink to kAuxRegs
 // (setmaxnreg).  768 x 72 = 512 x 88 + 256 x 40, and 10 240 registers stay free for a co-resident finalize block.
-constexpr int kLaunchRegs = 72, kEpiRegs = F3D_TC_EPI_REGS, kAuxRegs = 40;
+#ifndef F3D_TC_LAUNCH_REGS
+#define F3D_TC_LAUNCH_REGS 72
+#endif
+#ifndef F3D_TC_AUX_REGS
+#define F3D_TC_AUX_REGS 40
+#endif
+constexpr int kLaunchRegs = F3D_TC_LAUNCH_REGS, kEpiRegs = F3D_TC_EPI_REGS, kAuxRegs = F3D_TC_AUX_REGS;
 static_assert(kTcThreads * kLaunchRegs >= kEpiWarps * 32 * kEpiRegs + (kTcThreads - kEpiWarps * 32) * kAuxRegs, "register budget");
 static_assert(kItemRows == kTNc, "the query rows of an item travel as one 256-point compact tile");
 constexpr int kFinT = 64;                   // finalize block = half a row tile
@@ -301,50 +307,59 @@ __device__ __forceinline__ float ld_host_f1(const float* p) {
     asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
 }
-// floats [s, e) of src -> dst (same index space, both bases 16-byte aligned): scalar head / tail, 16-byte body, four loads in flight
-__device__ __forceinline__ void upload_span(const float* __restrict__ src, float* __restrict__ dst, size_t s, size_t e, int u, int U, int tid, int nthreads) {
-    size_t s4 = (s + 3) & ~(size_t)3, e4 = e & ~(size_t)3;
+// floats [s, e) of src -> dst (same index space, both bases 16-byte aligned) by ONE WARP of W cooperating warps (this one is
+// warp w): scalar head / tail, 16-byte body, four loads per lane in flight
+__device__ __forceinline__ void upload_span_warp(const float* __restrict__ src, float* __restrict__ dst, unsigned s, unsigned e, int w, int W, int lane) {
+    // (32-bit float offsets and two loads per lane in flight: the whole kernel has to live in 32 registers — see below)
+    unsigned s4 = (s + 3u) & ~3u, e4 = e & ~3u;
     if (s4 > e4) s4 = e4 = e;  // fewer than one aligned quad: everything is "head"
-    if (u == 0) {
-        if (s + tid < s4) dst[s + tid] = ld_host_f1(src + s + tid);    // < 4 floats each
-        if (e4 + tid < e && e4 >= s4) dst[e4 + tid] = ld_host_f1(src + e4 + tid);
+    if (w == 0) {
+        if (s + lane < s4) dst[s + lane] = ld_host_f1(src + s + lane);    // < 4 floats each
+        if (e4 + lane < e && e4 >= s4) dst[e4 + lane] = ld_host_f1(src + e4 + lane);
     }
-    const size_t n4 = (e4 - s4) >> 2, stride = (size_t)U * nthreads;
-    for (size_t i = (size_t)u * nthreads + tid; i < n4; i += 4 * stride) {
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (i + k * stride < n4) v[k] = ld_host_f4(src + s4 + 4 * (i + k * stride));
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (i + k * stride < n4) __stcg(reinterpret_cast<float4*>(dst + s4) + i + k * stride, v[k]);
+    const unsigned n4 = (e4 - s4) >> 2, stride = (unsigned)W * 32u;
+    const float4* s16 = reinterpret_cast<const float4*>(src + s4);
+    float4* d16 = reinterpret_cast<float4*>(dst + s4);
+    for (unsigned i = (unsigned)w * 32u + lane; i < n4; i += 2 * stride) {
+        const bool two = i + stride < n4;
+        const float4 v0 = ld_host_f4(reinterpret_cast<const float*>(s16 + i));
+        float4 v1 = v0;
+        if (two) v1 = ld_host_f4(reinterpret_cast<const float*>(s16 + i + stride));
+        __stcg(d16 + i, v0);
+        if (two) __stcg(d16 + i + stride, v1);
     }
 }
 constexpr int kUpT = 256;
-__global__ void __launch_bounds__(kUpT) chamfer_tc_upload_prepare_kernel(TcUploadParams p) {
+// <= 32 registers: an upload / prepare CTA must fit BESIDE a sweep CTA (55 296 of the SM's 65 536 registers), or the sweep
+// CTAs of a third of the SMs would only start once the whole batch has crossed PCIe
+__global__ void __launch_bounds__(kUpT, 8) chamfer_tc_upload_prepare_kernel(TcUploadParams p) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the sweep becomes resident beside this grid; its producer waits per element
     __shared__ int s_ticket;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_ticket = atomicAdd(p.hdr + kHdrStarted, 1);
     __syncthreads();
     const int ticket = s_ticket;
     const TcPrepParams& q = p.pp;
     if (ticket < p.U) {
-        const size_t ea = (size_t)q.N * 3, eb = (size_t)q.M * 3;
+        // uploaders: every WARP moves its share of every element and counts it on its own — no block-wide barrier, so the warps
+        // of the grid spread over two or three elements and keep the PCIe read queue full
+        const unsigned ea = (unsigned)q.N * 3u, eb = (unsigned)q.M * 3u;   // (the host side checks B*N*3, B*M*3 < 2^31)
+        const int W = p.U * (kUpT / 32), w = ticket * (kUpT / 32) + warp;
         for (int b = 0; b < p.B; ++b) {
-            upload_span(p.hA, p.dA, b * ea, (b + 1) * ea, ticket, p.U, tid, kUpT);
-            upload_span(p.hB, p.dB, b * eb, (b + 1) * eb, ticket, p.U, tid, kUpT);
-            __threadfence();   // this thread's stores are visible device-wide ...
-            __syncthreads();   // ... for every thread of the CTA ...
-            if (tid == 0) atomicAdd(p.arrived + b, 1u);  // ... before the element counts as delivered by this CTA
+            upload_span_warp(p.hA, p.dA, b * ea, (b + 1) * ea, w, W, lane);
+            upload_span_warp(p.hB, p.dB, b * eb, (b + 1) * eb, w, W, lane);
+            __threadfence();   // this lane's stores are visible device-wide ...
+            __syncwarp();      // ... for every lane of the warp ...
+            if (lane == 0) atomicAdd(p.arrived + b, 1u);  // ... before the element counts as delivered by this warp
         }
         return;
     }
     const int v = ticket - p.U;
+    const int arrive_target = p.U * (kUpT / 32);
     for (int b = 0; b < p.B; ++b) {
         if (tid == 0) {
             const int* f = reinterpret_cast<const int*>(p.arrived) + b;
-            while (ld_acquire_i32(f) < p.U) __nanosleep(100);
+            while (ld_acquire_i32(f) < arrive_target) __nanosleep(100);
         }
         __syncthreads();
         const float* gA = q.A + (size_t)b * q.N * 3;
@@ -637,6 +652,11 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
                     tmem_ld32_issue(base + 32, v[1]);
                     tmem_ld_wait(v[0]);
                     tmem_ld_wait(v[1]);
+                    // the accumulator quarter is in registers: hand the accumulator back NOW — the next MMAs into it run while
+                    // the minima below are taken (the accumulator is busy for one TMEM round trip, not for the whole read-out)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[r]);
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const float m = min32(v[q]);
@@ -644,9 +664,6 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
                         loc3_insert(loc[r], m, chunk);
                         stmin[r] = fminf(stmin[r], m);
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[r]);
                     PROF(1);
                 }
                 if ((t & (kTilesPerSuper - 1)) == kTilesPerSuper - 1 || t == ntiles - 1) {
@@ -861,8 +878,8 @@ __global__ void __launch_bounds__(kFinT, 24) chamfer_tc_finalize_kernel(TcFinPar
 // are rescanned by a whole block each, taken from the work list: every supertile whose filter minimum lies within the row's
 // window is scanned in the reference arithmetic; the distance found goes to the row's FIXED slot.  The last block then adds
 // up the finalize blocks' partial sums and those slots in a fixed order (bitwise repeatable).
-constexpr int kCleanT = 256;
-__global__ void __launch_bounds__(kCleanT, 4) chamfer_tc_cleanup_kernel(TcFinParams p) {
+constexpr int kCleanT = 1024;   // wide blocks: the last one adds up thousands of partial sums in one round trip
+__global__ void __launch_bounds__(kCleanT, 1) chamfer_tc_cleanup_kernel(TcFinParams p) {
     __shared__ bool s_last;
     constexpr int kMaxSel = 32;
     __shared__ int s_sel[kMaxSel], s_nsel;
@@ -965,17 +982,17 @@ __global__ void __launch_bounds__(kCleanT, 4) chamfer_tc_cleanup_kernel(TcFinPar
     if (!s_last) return;
     __threadfence();
     double sa = 0.0, sb = 0.0;
-    for (int k0 = 0; k0 < p.nfin; k0 += 8 * kCleanT) {   // per finalize block: eight of them in flight per thread
-        double v[8];
-        int cn[8];
+    for (int k0 = 0; k0 < p.nfin; k0 += 4 * kCleanT) {   // per finalize block: four of them in flight per thread
+        double v[4];
+        int cn[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
             const int kk = k0 + u * kCleanT + tid;
             v[u] = kk < p.nfin ? __ldcg(p.partial + kk) : 0.0;
             cn[u] = kk < p.nfin ? __ldcg(p.ambcnt + kk) : 0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
             const int kk = k0 + u * kCleanT + tid;
             if (kk < p.nfin) {
                 double t = v[u];
@@ -1092,6 +1109,10 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
         F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinT * kFinPitch));
         F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_cleanup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        // ... and the grids that run BEFORE / BESIDE the sweep must leave the SMs in that same configuration: an SM that an
+        // upload CTA has configured for a large L1 cannot take a sweep CTA (130 KB of shared memory) until it drains
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_upload_prepare_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_prepare_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         int sms = 0;
         F3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (dev >= 0 && dev < 256) { sm_count[dev] = sms; attr_done[dev] = 1; }
@@ -1105,6 +1126,8 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
     pp.PB = reinterpret_cast<float4*>(w + pl.off_PB);
     pp.maxn = reinterpret_cast<unsigned*>(w + pl.off_maxn);
     int prepared_target = 0;
+    if (upload && ((long long)B * N * 3 >= 0x7fffffffLL || (long long)B * M * 3 >= 0x7fffffffLL))
+        return fail(F3D_ERR_INVALID, "chamfer_tc_launch: batch too large for the in-grid upload");
     if (upload) {
         // host arrays: A / Bp are staging buffers; one grid uploads and prepares, element by element, beside the sweep
         TcUploadParams up;
@@ -1177,7 +1200,7 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
         F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_tc_finalize_kernel, fp));
     }
     F3D_CHECK_LAUNCH("chamfer_tc_finalize_kernel");
-    chamfer_tc_cleanup_kernel<<<std::min(pl.nfin, 8 * sms), kCleanT, 0, stream>>>(fp);
+    chamfer_tc_cleanup_kernel<<<std::min(pl.nfin, 2 * sms), kCleanT, 0, stream>>>(fp);
     F3D_CHECK_LAUNCH("chamfer_tc_cleanup_kernel");
     return F3D_OK;
 }

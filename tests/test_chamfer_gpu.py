@@ -328,12 +328,14 @@ def test_host_pipeline_errors(f3d):
 
 
 def test_host_pipeline_tensor_path_full_size(f3d, oracle):
-    """cfg2 from page-locked host arrays: the default path is the tensor-core sweep fed by the in-grid upload (batch elements are
-    swept while later ones still cross PCIe) — same loss as on resident inputs, bit for bit, repeatedly."""
+    """cfg2 from page-locked host arrays through the tensor-core sweep fed by the upload + prepare grid (batch elements are swept
+    while later ones still cross PCIe) — same loss as on resident inputs, bit for bit, repeatedly."""
     A = np.random.default_rng(201).random((32, 4096, 3), dtype=np.float32)
     B = np.random.default_rng(202).random((32, 4096, 3), dtype=np.float32)
     pA, pB = torch.from_numpy(A).pin_memory(), torch.from_numpy(B).pin_memory()
     ld, *_ = _run(f3d, A, B)
     for _ in range(3):
-        assert f3d.chamfer_forward_host(pA, pB, to_host=True).item() == ld
+        assert f3d.chamfer_forward_host(pA, pB, to_host=True, flags=f3d.FLAG_TENSOR).item() == ld
+    # the default carrier of the in-grid upload (CUDA-core sweep): same rows, another summation order
+    assert abs(f3d.chamfer_forward_host(pA, pB, to_host=True).item() - ld) <= 1e-6 * ld
     assert abs(ld - 0.0028460352) <= 1e-5 * 0.0028460352

@@ -128,12 +128,14 @@ def test_edge_features_are_differentiable_in_x(f3d):
         w = torch.randn_like(E)
         (E * w).sum().backward()
         idx = f3d.knn_graph(X, K)["idx"].long()
+
+        def build(Xv):
+            nb = torch.gather(Xv.unsqueeze(1).expand(-1, 200, -1, -1), 2, idx.unsqueeze(-1).expand(-1, -1, -1, 6))   # (B,N,K,F)
+            out = torch.cat([Xv.unsqueeze(2).expand(-1, -1, K, -1), nb - Xv.unsqueeze(2)], dim=-1)
+            return out.permute(0, 3, 1, 2) if mlp_layout else out
+        assert torch.equal(E.detach(), build(X))          # float32 subtraction, rounded once — like the kernel
         Xb = X.clone().double().requires_grad_(True)
-        nb = torch.gather(Xb.unsqueeze(1).expand(-1, 200, -1, -1), 2, idx.unsqueeze(-1).expand(-1, -1, -1, 6))   # (B,N,K,F)
-        ref = torch.cat([Xb.unsqueeze(2).expand(-1, -1, K, -1), nb - Xb.unsqueeze(2)], dim=-1)
-        if mlp_layout:
-            ref = ref.permute(0, 3, 1, 2)
-        assert torch.equal(E.detach(), ref.detach().float())
+        ref = build(Xb)
         (ref * w.double()).sum().backward()
         assert torch.allclose(Xa.grad.double(), Xb.grad, rtol=1e-5, atol=1e-6)
 
