@@ -203,10 +203,15 @@ __device__ __forceinline__ unsigned long long umma_desc64(unsigned smem_addr) {
 constexpr unsigned kIdescTc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kTNc >> 3) << 17) | ((unsigned)(kTQ >> 4) << 24);
 
 // x = h + l + e with h, l representable in TF32 (11 significant bits) and |e| <= 2^-22 |x|
-__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// Veltkamp splitting with 2^13 + 1: three FP32 operations on the (idle) FMA pipe give x rounded to 11 significant bits — the
+// ALU pipe, which the read-out's FMNMX work saturates (ncu: 79 % active), is left alone.  No contraction: -fmad=false.
+__device__ __forceinline__ float rn_tf32(float x) {
+    const float c = __fmul_rn(x, 8193.0f);
+    return __fsub_rn(c, __fsub_rn(c, x));
+}
 __device__ __forceinline__ void split_tf32(float x, float& h, float& l) {
     h = rn_tf32(x);
-    l = rn_tf32(__fsub_rn(x, h));
+    l = rn_tf32(__fsub_rn(x, h));   // x - h is exact
 }
 
 // The locator record of a query row: the two smallest chunk minima with their chunk ids and the third smallest value.
@@ -217,6 +222,23 @@ struct Loc3 {
     float b1, b2, b3;
     int c1, c2;
 };
+// Inside the sweep the chunk id travels IN the value: the low `idbits` mantissa bits of a chunk minimum are replaced by the
+// thread's running chunk number (2 x tile + chunk of its quarter), so that three FMNMX keep the two smallest chunk minima
+// together with where they came from — no compares, no selects (5 ALU instructions less per chunk on the pipe that binds).
+// The values move by at most 2^(idbits-23) relative; the certificate's relative term carries that (tc_win_rel below).
+struct Loc3v {
+    float b1, b2, b3;   // b1 <= b2 <= b3, ids in the low bits
+};
+__device__ __forceinline__ void loc3v_insert(Loc3v& l, float m) {
+    l.b3 = fminf(l.b3, fmaxf(l.b2, m));
+    l.b2 = fminf(l.b2, fmaxf(l.b1, m));
+    l.b1 = fminf(l.b1, m);
+}
+__host__ __device__ __forceinline__ int tc_idbits(int ntiles) {   // bits for 2 * ntiles chunk numbers
+    int b = 1;
+    while ((1 << b) < 2 * ntiles) ++b;
+    return b;
+}
 __device__ __forceinline__ void loc3_insert(Loc3& l, float m, int chunk) {   // strict '<': the EARLIEST chunk reaching a value keeps it
     const bool lt1 = m < l.b1, lt2 = m < l.b2;
     l.b3 = fminf(l.b3, fmaxf(l.b2, m));
@@ -588,19 +610,24 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             const bool dir = k >= p.rbA;
             const int rb = dir ? k - p.rbA : k;
             const unsigned pb = it & 1;
+            const unsigned idmask = (1u << tc_idbits((dir ? p.NpA : p.NpB) / kTNc)) - 1u;
             mbar_wait(&pub_full[pb], (it >> 1) & 1);
             float4* out = p.rowfin + (size_t)b * (p.NpA + p.NpB) + (dir ? p.NpA : 0) + (size_t)rb * kItemRows;
             const float4* src = s_pub + pb * kParts * kItemRows;
 #pragma unroll 2
             for (int rin = lane; rin < kItemRows; rin += 32) {
-                Loc3 e = loc3_unpack(src[rin]);
+                // quarter q's record: values with the quarter's running chunk number (2 * tile + chunk) in their low bits ->
+                // global chunk id = tile * 8 + q * 2 + chunk.  Quarters hold disjoint chunk sets: insert the two located minima;
+                // the third value can only be third or later
+                Loc3 e;
+                e.b1 = INFINITY; e.b2 = INFINITY; e.b3 = INFINITY; e.c1 = 0; e.c2 = 0;
 #pragma unroll
-                for (int q = 1; q < kParts; ++q) {
-                    // disjoint chunk sets: insert the quarter's two located chunk minima; its third value can only be third or later
-                    const Loc3 o = loc3_unpack(src[q * kItemRows + rin]);
-                    loc3_insert(e, o.b1, o.c1);
-                    loc3_insert(e, o.b2, o.c2);
-                    e.b3 = fminf(e.b3, o.b3);
+                for (int q = 0; q < kParts; ++q) {
+                    const float4 o = src[q * kItemRows + rin];
+                    const unsigned i1 = __float_as_uint(o.x) & idmask, i2 = __float_as_uint(o.y) & idmask;
+                    loc3_insert(e, o.x, (int)((i1 >> 1) * (kTNc / kTcChunk) + q * (kTNc / kParts / kTcChunk) + (i1 & 1u)));
+                    loc3_insert(e, o.y, (int)((i2 >> 1) * (kTNc / kTcChunk) + q * (kTNc / kParts / kTcChunk) + (i2 & 1u)));
+                    e.b3 = fminf(e.b3, o.z);
                 }
                 out[rin] = loc3_pack(e);
             }
@@ -634,10 +661,11 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             const int rin = quad * 32 + lane;               // row within its row tile
             float* tm = p.tilemin + (size_t)kParts * ((size_t)b * ((size_t)p.nstB * p.NpA + (size_t)p.nstA * p.NpB) + (dir ? (size_t)p.nstB * p.NpA : 0)) +
                         (size_t)rb * kItemRows + rin;
-            Loc3 loc[kRT];
+            Loc3v loc[kRT];
             float stmin[kRT];
 #pragma unroll
-            for (int r = 0; r < kRT; ++r) { loc[r].b1 = INFINITY; loc[r].b2 = INFINITY; loc[r].b3 = INFINITY; loc[r].c1 = 0; loc[r].c2 = 0; stmin[r] = INFINITY; }
+            for (int r = 0; r < kRT; ++r) { loc[r].b1 = INFINITY; loc[r].b2 = INFINITY; loc[r].b3 = INFINITY; stmin[r] = INFINITY; }
+            const unsigned idmask = (1u << tc_idbits(ntiles)) - 1u;
             for (int t = 0; t < ntiles; ++t, ++g) {
 #pragma unroll
                 for (int r = 0; r < kRT; ++r) {
@@ -660,8 +688,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const float m = min32(v[q]);
-                        const int chunk = t * (kTNc / kTcChunk) + part * (kTNc / kParts / kTcChunk) + q;
-                        loc3_insert(loc[r], m, chunk);
+                        loc3v_insert(loc[r], __uint_as_float((__float_as_uint(m) & ~idmask) | (unsigned)(2 * t + q)));
                         stmin[r] = fminf(stmin[r], m);
                     }
                     PROF(1);
@@ -679,7 +706,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             mbar_wait(&pub_empty[pb], ((it >> 1) & 1) ^ 1);
 #pragma unroll
             for (int r = 0; r < kRT; ++r)
-                s_pub[(pb * kParts + part) * kItemRows + r * kTQ + rin] = loc3_pack(loc[r]);
+                s_pub[(pb * kParts + part) * kItemRows + r * kTQ + rin] = make_float4(loc[r].b1, loc[r].b2, loc[r].b3, 0.f);
             __syncwarp();
             if (lane == 0) mbar_arrive(&pub_full[pb]);
         }
@@ -780,8 +807,10 @@ __global__ void __launch_bounds__(kFinT, 24) chamfer_tc_finalize_kernel(TcFinPar
         qx = __ldg(gQ + 3 * (size_t)q); qy = __ldg(gQ + 3 * (size_t)q + 1); qz = __ldg(gQ + 3 * (size_t)q + 2);
         best = fmaxf(e.b1, 0.0f);
         loc = e.c1; loc2 = e.c2;
-        win = fmaf(kTcWinRel, best, kTcWinAbs * (nq + other));
-        errlim = kTcErrAbs * (nq + other);
+        // the chunk numbers embedded in the located values moved them by up to 2^(idbits-23) relative
+        const float idrel = ldexpf(1.0f, tc_idbits((dir ? p.NpA : p.NpB) / kTNc) - 23);
+        win = fmaf(kTcWinRel + 2.0f * idrel, best, kTcWinAbs * (nq + other));
+        errlim = fmaf(idrel, best, kTcErrAbs * (nq + other));
         // written so that NaN / inf / out-of-range norms can only make the row ambiguous, never certified
         const bool sane = nq <= kTcNormLimit && other <= kTcNormLimit && nq + other >= kTcNormFloor;
         const bool one = sane && fmaxf(e.b2, 0.0f) > best + win;
@@ -1083,7 +1112,7 @@ bool chamfer_tc_possible(int B, int N, int M) {
     if (B <= 0 || N < 1 || M < 1) return false;
     const TcPlan pl = make_tc_plan(B, N, M);
     if ((long long)B * (pl.rbA + pl.rbB) * kRT * (kTQ / kFinT) > 0x3fffffffLL) return false;
-    return std::max(pl.NpA, pl.NpB) / kTcChunk <= 0xffff;   // chunk ids travel as 16 bits
+    return std::max(pl.NpA, pl.NpB) <= 131072;   // running chunk numbers travel in <= 10 mantissa bits, global chunk ids as 16 bits
 }
 bool chamfer_tc_supported(int B, int N, int M) {
     if (!chamfer_tc_possible(B, N, M)) return false;
