@@ -6,17 +6,17 @@
 //   gB_j = cB (B_j - A_nnB(j))  -  Σ_{i : nnA(i) = j} cA (A_i - B_j),   cB = 2 w2 g / (M B_total)
 // HBM-bound (reads 2 clouds + 2 index arrays, writes 2 gradients: 32 B per point).
 //
-// Default (clouds of up to 8 192 points): ONE launch, no atomics, bitwise repeatable.  CTA = (batch element, which
-// gradient).  The scatter term is turned into a gather: the CTA sorts the (target, source) pairs of its element by
-// target with a stable block radix sort (cub::BlockRadixSort — sources of one target stay in ascending order), then every
-// target point finds its segment with a binary search in shared memory and subtracts its sources' contributions from
-// the direct term in that fixed order; every gradient entry is written exactly once.
+// Default (clouds of up to 24 576 points): ONE launch, no global atomics, bitwise repeatable.  The scatter term is turned into a
+// gather by a counting sort in shared memory: CTA = (batch element, which gradient, slice of the targets) counts the sources
+// that pull on each of its targets (shared-memory atomics: counts do not depend on the order), turns the counts into segment
+// offsets (block scan), drops every source into its target's segment, and every target then subtracts its sources'
+// contributions from the direct term in ASCENDING source order (segments hold one or two sources on real clouds: a selection
+// over the segment; targets with more than 32 sources — degenerate inputs — are summed by the whole block in a fixed order).
+// Every gradient entry is written exactly once.
 // Larger clouds: two launches — the direct terms overwrite the outputs, then the scatter terms are added with
 // RED.ADD.F32 (order not fixed: the last bit of an entry that receives several contributions may vary run to run; the
 // reference pins this to atol 1e-2 / rtol 1e-3, test/metrics.jl:112-114).
 #include <algorithm>
-
-#include <cub/block/block_radix_sort.cuh>
 
 #include "f3d_common.cuh"
 
@@ -66,18 +66,24 @@ __global__ void __launch_bounds__(kBT) chamfer_bwd_kernel(BwdParams p) {
     }
 }
 
-// ---- sorted gather: grid (B, 2); y = 0 computes gA (targets: points of A, sources: points of B through nnB), y = 1 gB ----
-template <int kItems>
-__global__ void __launch_bounds__(kBT) chamfer_bwd_sorted_kernel(BwdParams p) {
-    using Sort = cub::BlockRadixSort<int, kBT, kItems, int>;
-    constexpr int kCap = kBT * kItems;
-    extern __shared__ __align__(16) unsigned char bwd_smem[];
-    typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(bwd_smem);
-    int* sk = reinterpret_cast<int*>(bwd_smem);   // the sorted keys / values take the sort's scratch over afterwards
-    int* sv = sk + kCap;
-    const int b = blockIdx.x, tid = threadIdx.x;
+// ---- gather: grid (B, 2, S); y = 0 computes gA (targets: points of A, sources: points of B through nnB), y = 1 gB; z = slice of
+// the targets.  Dynamic shared memory: cnt[nt + 1], list[nS], heavy[nS / 33 + 1] ----
+constexpr int kGT = 1024;
+constexpr int kHeavy = 32;     // a target with more sources than this is summed by the whole block
+constexpr int kGatherMaxPts = 24576;
+
+__global__ void __launch_bounds__(kGT) chamfer_bwd_gather_kernel(BwdParams p) {
+    extern __shared__ __align__(16) int bwd_smem[];
+    __shared__ int s_warp[kGT / 32];
+    __shared__ int s_nheavy;
+    __shared__ float s_hx[kGT / 32], s_hy[kGT / 32], s_hz[kGT / 32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool forA = blockIdx.y == 0;
     const int nT = forA ? p.N : p.M, nS = forA ? p.M : p.N;               // targets / sources of this element
+    const int t0 = (int)((long)nT * blockIdx.z / gridDim.z), t1 = (int)((long)nT * (blockIdx.z + 1) / gridDim.z), nt = t1 - t0;
+    int* cnt = bwd_smem;               // [nt + 1]
+    int* list = cnt + nt + 1;          // [nS]
+    int* heavy = list + nS;            // [nS / (kHeavy + 1) + 1]
     const float* T = (forA ? p.A : p.Bp) + (size_t)b * nT * 3;
     const float* S = (forA ? p.Bp : p.A) + (size_t)b * nS * 3;
     const int32_t* nnT = (forA ? p.nnA : p.nnB) + (size_t)b * nT;         // target -> its nearest source (direct term)
@@ -85,47 +91,101 @@ __global__ void __launch_bounds__(kBT) chamfer_bwd_sorted_kernel(BwdParams p) {
     float* G = (forA ? p.gA : p.gB) + (size_t)b * nT * 3;
     const float g = __ldg(p.gout);
     const float cT = (forA ? p.cA : p.cB) * g, cS = (forA ? p.cB : p.cA) * g;
-    int keys[kItems], vals[kItems];
-#pragma unroll
-    for (int k = 0; k < kItems; ++k) {   // blocked arrangement: thread t holds sources t*kItems .. +kItems-1 (ascending: the sort is stable)
-        const int j = tid * kItems + k;
-        keys[k] = j < nS ? __ldg(nnS + j) : 0x7fffffff;
-        vals[k] = j;
+
+    for (int i = tid; i <= nt; i += kGT) cnt[i] = 0;
+    if (tid == 0) s_nheavy = 0;
+    __syncthreads();
+    for (int j = tid; j < nS; j += kGT) {
+        const unsigned t = (unsigned)(__ldg(nnS + j) - t0);
+        if (t < (unsigned)nt) atomicAdd(&cnt[t], 1);
     }
-    int bits = 1;
-    while ((1 << bits) < nT) ++bits;
-    Sort(tmp).Sort(keys, vals, 0, bits < 31 ? bits + 1 : 31);   // (+1: the padding key 0x7fffffff need not sort last — it is never looked up — but keep real keys exact)
     __syncthreads();
+    // exclusive scan of cnt[0 .. nt): thread <-> a contiguous run of `per` targets
+    {
+        const int per = (nt + kGT - 1) / kGT, lo = min(tid * per, nt), hi = min(lo + per, nt);
+        int sum = 0;
+        for (int i = lo; i < hi; ++i) sum += cnt[i];
+        int incl = sum;
 #pragma unroll
-    for (int k = 0; k < kItems; ++k) { sk[tid * kItems + k] = keys[k]; sv[tid * kItems + k] = vals[k]; }
-    __syncthreads();
-    for (int i = tid; i < nT; i += kBT) {
-        const float tx = __ldg(T + 3 * i), ty = __ldg(T + 3 * i + 1), tz = __ldg(T + 3 * i + 2);
-        const int o = __ldg(nnT + i);
-        float gx = cT * (tx - __ldg(S + 3 * o)), gy = cT * (ty - __ldg(S + 3 * o + 1)), gz = cT * (tz - __ldg(S + 3 * o + 2));
-        int lo = 0, hi = nS;              // first position with key >= i among the nS real entries (padding keys sort after them or are skipped)
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (sk[mid] < i) lo = mid + 1; else hi = mid;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        for (int e = lo; e < nS && sk[e] == i; ++e) {   // ascending source index: a fixed summation order
-            const int j = sv[e];
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += v;
+            }
+            s_warp[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        int run = incl - sum + (warp ? s_warp[warp - 1] : 0);
+        for (int i = lo; i < hi; ++i) { const int c = cnt[i]; cnt[i] = run; run += c; }
+    }
+    __syncthreads();
+    // every source into its target's segment; afterwards cnt[t] = end of segment t = start of segment t + 1
+    for (int j = tid; j < nS; j += kGT) {
+        const unsigned t = (unsigned)(__ldg(nnS + j) - t0);
+        if (t < (unsigned)nt) list[atomicAdd(&cnt[t], 1)] = j;
+    }
+    __syncthreads();
+    for (int i = tid; i < nt; i += kGT) {
+        const int ti = t0 + i;
+        const int start = i ? cnt[i - 1] : 0, end = cnt[i];
+        if (end - start > kHeavy) { heavy[atomicAdd(&s_nheavy, 1)] = i; continue; }
+        const float tx = __ldg(T + 3 * ti), ty = __ldg(T + 3 * ti + 1), tz = __ldg(T + 3 * ti + 2);
+        const int o = __ldg(nnT + ti);
+        float gx = cT * (tx - __ldg(S + 3 * o)), gy = cT * (ty - __ldg(S + 3 * o + 1)), gz = cT * (tz - __ldg(S + 3 * o + 2));
+        int last = -1;
+        for (int e = start; e < end; ++e) {   // ascending source index: a fixed summation order whatever order the segment was filled in
+            int j = 0x7fffffff;
+            for (int k = start; k < end; ++k) {
+                const int v = list[k];
+                if (v > last && v < j) j = v;
+            }
+            last = j;
             gx -= cS * (__ldg(S + 3 * j) - tx);
             gy -= cS * (__ldg(S + 3 * j + 1) - ty);
             gz -= cS * (__ldg(S + 3 * j + 2) - tz);
         }
-        G[3 * i] = gx; G[3 * i + 1] = gy; G[3 * i + 2] = gz;
+        G[3 * ti] = gx; G[3 * ti + 1] = gy; G[3 * ti + 2] = gz;
     }
-}
-
-template <int kItems>
-int32_t launch_sorted(const BwdParams& p, int B, cudaStream_t stream) {
-    using Sort = cub::BlockRadixSort<int, kBT, kItems, int>;
-    const size_t smem = std::max(sizeof(typename Sort::TempStorage), sizeof(int) * 2 * (size_t)kBT * kItems);
-    F3D_CUDA(cudaFuncSetAttribute(chamfer_bwd_sorted_kernel<kItems>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chamfer_bwd_sorted_kernel<kItems><<<dim3(B, 2), kBT, smem, stream>>>(p);
-    F3D_CHECK_LAUNCH("chamfer_bwd_sorted_kernel");
-    return F3D_OK;
+    __syncthreads();
+    // targets that many sources pull on (degenerate inputs): the block sums each one's sources — thread <-> a strided subset in
+    // ascending order, then a fixed tree
+    const int nheavy = s_nheavy;
+    for (int hI = 0; hI < nheavy; ++hI) {
+        const int ti = t0 + heavy[hI];
+        const float tx = __ldg(T + 3 * ti), ty = __ldg(T + 3 * ti + 1), tz = __ldg(T + 3 * ti + 2);
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int j = tid; j < nS; j += kGT)
+            if (__ldg(nnS + j) == ti) {
+                sx += cS * (__ldg(S + 3 * j) - tx);
+                sy += cS * (__ldg(S + 3 * j + 1) - ty);
+                sz += cS * (__ldg(S + 3 * j + 2) - tz);
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+            sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        }
+        if (lane == 0) { s_hx[warp] = sx; s_hy[warp] = sy; s_hz[warp] = sz; }
+        __syncthreads();
+        if (tid == 0) {
+            float ax = 0.f, ay = 0.f, az = 0.f;
+            for (int w = 0; w < kGT / 32; ++w) { ax += s_hx[w]; ay += s_hy[w]; az += s_hz[w]; }
+            const int o = __ldg(nnT + ti);
+            G[3 * ti] = cT * (tx - __ldg(S + 3 * o)) - ax;
+            G[3 * ti + 1] = cT * (ty - __ldg(S + 3 * o + 1)) - ay;
+            G[3 * ti + 2] = cT * (tz - __ldg(S + 3 * o + 2)) - az;
+        }
+        __syncthreads();
+    }
 }
 
 }  // namespace
@@ -147,10 +207,24 @@ extern "C" int32_t f3d_chamfer_bwd(const float* A, const float* Bp, int32_t B, i
     p.gA = gA; p.gB = gB;
     p.totA = (long)B * N; p.totB = (long)B * M;
     const int big = std::max(N, M);
-    if (B <= 65535 && big <= kBT * 32) {   // sorted gather: one launch, no atomics, bitwise repeatable
-        if (big <= kBT * 4) return launch_sorted<4>(p, B, stream);
-        if (big <= kBT * 16) return launch_sorted<16>(p, B, stream);
-        return launch_sorted<32>(p, B, stream);
+    if (B <= 65535 && big <= kGatherMaxPts) {   // counting-sort gather: one launch, no global atomics, bitwise repeatable
+        int dev = 0, sms = 148;
+        F3D_CUDA(cudaGetDevice(&dev));
+        static int sm_count[256];
+        if (dev >= 0 && dev < 256) {
+            if (!sm_count[dev]) {
+                F3D_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+                F3D_CUDA(cudaFuncSetAttribute(chamfer_bwd_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(sizeof(int) * (2 * (size_t)kGatherMaxPts + kGatherMaxPts / (kHeavy + 1) + 4))));
+            }
+            sms = sm_count[dev];
+        }
+        // slices of the targets so that the grid covers the machine (every slice still reads all of the sources' indices)
+        const int slices = std::max(1, std::min({8, (sms + 2 * B - 1) / (2 * B), std::min(N, M)}));
+        const size_t smem = sizeof(int) * ((size_t)(big + slices - 1) / slices + 2 + (size_t)big + (size_t)big / (kHeavy + 1) + 1);
+        chamfer_bwd_gather_kernel<<<dim3(B, 2, slices), kGT, smem, stream>>>(p);
+        F3D_CHECK_LAUNCH("chamfer_bwd_gather_kernel");
+        return F3D_OK;
     }
     const long tot = p.totA + p.totB;
     const unsigned grid = (unsigned)((tot + kBT - 1) / kBT);

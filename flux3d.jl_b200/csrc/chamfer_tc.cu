@@ -15,22 +15,29 @@
 // chamfer.cu; the certificate below assumes 35 u.
 //
 // Work item = 256 query rows of one batch element and direction (two 128-row UMMA tiles) against ALL candidates of the
-// other cloud, streamed as 128-candidate tiles.  One persistent CTA per SM, 14 warps with fixed roles:
-//     producer (1 thread)   TMA bulk copies (cp.async.bulk -> UBLKCP) of compact operands {x', y', z', |p'|²} (16 B / point,
-//                           written once by chamfer_tc_prepare_kernel) into a 4-slot ring
-//     converters (4 warps)  thread <-> point: split the four values into TF32 pieces and write the 64-byte K-major
-//                           SWIZZLE_64B operand row (the 64 B/point image is never in HBM or L2: at 256 rows per candidate
-//                           tile a pre-expanded image would need ~9 TB/s of L2 -> SM traffic at the rate the MMAs run)
-//     MMA issuer (1 thread) four tcgen05.mma.kind::tf32 (2 row tiles x 2 K-steps, M = 128, N = 128) per candidate tile into
-//                           double-buffered TMEM accumulators (4 x 128 columns = all 512)
-//     read-out (8 warps)    thread <-> query row (TMEM lane): tcgen05.ld 32 columns at a time, FMNMX3 tree, and the locator
-//                           triple of chamfer.cu — b1 = row minimum, c1 = the 32-candidate chunk where it was first reached,
-//                           b2 = the minimum over all other chunks — plus one minimum per 1024-candidate supertile.
-// chamfer_tc_finalize_kernel (launched programmatically, co-resident with the sweep: it runs on the FP32 pipe the sweep
-// leaves idle) certifies every row — b2 > b1 + window proves the exact argmin, lowest index on ties, lies in chunk c1 —
-// re-evaluates those 32 candidates in the reference arithmetic, and rescans the supertiles within the window for the rare
-// ambiguous rows.  The loss is reduced in a fixed order (bitwise repeatable); for a sharded batch the sum over ranks is
-// fused into its last block (peer mailboxes over NVLink, as in chamfer.cu).
+// other cloud, streamed as 256-candidate tiles.  One persistent CTA per SM, 32 warps with fixed roles (setmaxnreg moves the
+// registers to where they are needed: 88 per read-out thread, 40 for everybody else — the whole register file):
+//     producer (1 thread)    TMA bulk copies (cp.async.bulk -> UBLKCP) of compact operands {x', y', z', |p'|²} (16 B / point,
+//                            written once by chamfer_tc_prepare_kernel) into a 4-slot ring
+//     converters (4 warps)   thread <-> point: split the four values into TF32 pieces and write the 64-byte K-major
+//                            SWIZZLE_64B operand row (the 64 B/point image is never in HBM or L2: at 256 rows per candidate
+//                            tile a pre-expanded image would need ~9 TB/s of L2 -> SM traffic at the rate the MMAs run)
+//     MMA issuer (1 thread)  four tcgen05.mma.kind::tf32 (2 row tiles x 2 K-steps, M = 128, N = 256) per candidate tile into
+//                            one 256-column TMEM accumulator per row tile (all 512 columns; the pair is the double buffer)
+//     read-out (16 warps)    thread <-> query row (TMEM lane) and column quarter: two tcgen05.ld of 32 columns in flight, an
+//                            FMNMX3 tree per 32-candidate chunk, and the locator record — the two smallest chunk minima with
+//                            their chunk numbers (carried in the low mantissa bits) and the third smallest value — plus one
+//                            minimum per 2048-candidate supertile
+//     certifiers (8 warps)   the item that has just left the read-out, while the tensor cores work on the next one:
+//                            lane <-> row merges the four column quarters' records and decides — b2 > b1 + window proves that
+//                            the exact argmin (lowest index on ties) lies in chunk c1; else b3 > b1 + window: in c1 or c2; else
+//                            the row is ambiguous — then fetches the located 32 candidates (384 contiguous bytes of the
+//                            ORIGINAL cloud) with one TMA bulk copy per row into its own shared-memory row and re-evaluates
+//                            them in the reference arithmetic: index, distance, and the item's partial sum of the loss.
+// No locator record, flag or completion counter goes through global memory; the step is three launches (prepare, sweep,
+// cleanup).  chamfer_tc_cleanup_kernel (launched programmatically; its blocks take the SMs as the sweep's CTAs leave) rescans
+// the supertiles within the window for the rare ambiguous rows and reduces the loss in a fixed order (bitwise repeatable);
+// for a sharded batch the sum over ranks is fused into its last block (peer mailboxes over NVLink, as in chamfer.cu).
 #include <algorithm>
 #include <cstdlib>
 
@@ -60,22 +67,24 @@ constexpr int kCStages = F3D_TC_CSTAGES;    // compact ring (4 KB per slot)
 constexpr int kParts = 4;                   // a row's 256 accumulator columns are read by four warps, 64 columns each
 constexpr int kEpiWarps = 4 * kParts;       // read-out warps: warp w reads lane quadrant w & 3, column quarter w >> 2 of BOTH row tiles' accumulators
 constexpr int kConvWarps = 4;               // converters: thread <-> two points of a 256-point tile
-constexpr int kWarpProducer = kEpiWarps + kConvWarps, kWarpMma = kWarpProducer + 1, kWarpPublisher = kWarpMma + 1;
-constexpr int kTcThreads = (kEpiWarps + kConvWarps + 4) * 32;   // 768: six warpgroups (the last one: producer, MMA issuer, publisher, one idle warp)
+constexpr int kWarpProducer = kEpiWarps + kConvWarps, kWarpMma = kWarpProducer + 1;
+constexpr int kCertWarps = 8;               // certifiers: warp <-> 32 rows of the item that has just left the read-out
+constexpr int kWarpCert = kWarpProducer + 4;
+constexpr int kTcThreads = (kWarpCert + kCertWarps) * 32;   // 1024: eight warpgroups (4 read-out, converters, {producer, MMA issuer, two idle warps}, 2 certifier)
 // Registers: the CTA is launched with kLaunchRegs per thread; the four read-out warpgroups then grow to kEpiRegs — both
-// tcgen05.ld of an accumulator quarter are in flight at once, 64 registers of data — and the other two shrink to kAuxRegs
-// (setmaxnreg).  768 x 72 = 512 x 88 + 256 x 40, and 10 240 registers stay free for a co-resident finalize block.
+// tcgen05.ld of an accumulator quarter are in flight at once, 64 registers of data — and the other four shrink to kAuxRegs
+// (setmaxnreg).  1024 x 64 = 512 x 88 + 512 x 40: the whole register file.
 #ifndef F3D_TC_LAUNCH_REGS
-#define F3D_TC_LAUNCH_REGS 72
+#define F3D_TC_LAUNCH_REGS 64
 #endif
 #ifndef F3D_TC_AUX_REGS
 #define F3D_TC_AUX_REGS 40
 #endif
 constexpr int kLaunchRegs = F3D_TC_LAUNCH_REGS, kEpiRegs = F3D_TC_EPI_REGS, kAuxRegs = F3D_TC_AUX_REGS;
 static_assert(kTcThreads * kLaunchRegs >= kEpiWarps * 32 * kEpiRegs + (kTcThreads - kEpiWarps * 32) * kAuxRegs, "register budget");
+static_assert(kTcThreads * kLaunchRegs <= 65536 && kCertWarps * 32 == kItemRows, "one CTA per SM; certifier lane <-> row of the item");
 static_assert(kItemRows == kTNc, "the query rows of an item travel as one 256-point compact tile");
-constexpr int kFinT = 64;                   // finalize block = half a row tile
-constexpr int kFinPitch = 400;              // bytes per staged chunk in the finalize (384 B of data)
+constexpr int kChunkPitch = 400;            // bytes per staged chunk of the certifiers (384 B of data; 25 x 16 B: conflict-free 16-byte rows)
 constexpr float kPadN = 1.0e30f;            // |p'|² of padded points: never a minimum for in-contract inputs
 constexpr float kTcNormLimit = 1.0e29f, kTcNormFloor = 1.0e-30f;  // outside: certify nothing (overflow / underflow of the pieces)
 // Certificate: |f - d| <= kErrAbs (nq + nc) + 5.001 u d  (u = 2^-24; d = the reference-arithmetic distance).  35 u =
@@ -425,6 +434,7 @@ __global__ void __launch_bounds__(kUpT, 8) chamfer_tc_upload_prepare_kernel(TcUp
 #ifdef F3D_TC_PROF
 // development: cycles every role spends waiting / working, per CTA (read back with f3d_debug_read_tc)
 __device__ long long g_tcprof[148 * 16];
+__device__ long long g_certprof[148 * 8];
 #define PROF_DECL long long pf_[6] = {0, 0, 0, 0, 0, 0}; long long pt_ = clock64()
 #define PROF(k) do { const long long n_ = clock64(); pf_[k] += n_ - pt_; pt_ = n_; } while (0)
 #define PROF_OUT(base, n) do { if (blockIdx.x < 148) for (int i_ = 0; i_ < (n); ++i_) g_tcprof[blockIdx.x * 16 + (base) + i_] = pf_[i_]; } while (0)
@@ -433,18 +443,44 @@ __device__ long long g_tcprof[148 * 16];
 #define PROF(k)
 #define PROF_OUT(base, n)
 #endif
+// What the certifier warps of the sweep and the cleanup kernel share.  "Slot" = item * 256 + position: the ambiguous rows of an
+// item are listed in row order at fixed positions, so that the loss stays bitwise repeatable whatever order they are handled in.
+struct TcFinParams {
+    const float* A;
+    const float* Bp;
+    const float4* PA;
+    const float4* PB;
+    int B, N, M, NpA, NpB, rbA, rbB, nstA, nstB;
+    const float* tilemin;
+    const unsigned* maxn;   // [2][B]
+    int32_t* nnA;
+    int32_t* nnB;
+    double* partial;        // [nitems]       sum of the certified rows' distances of every item
+    int* ambcnt;            // [nitems]       ambiguous rows of every item ...
+    int* ambq;              // [nitems][256]  ... their row numbers, in row order ...
+    float* amblim;          // [nitems][256]  ... and their windows' upper ends
+    int* amblist;           // [rows]         slots of all ambiguous rows, in arrival order: the cleanup's work list
+    float* ambd;            // [nitems][256]  the exact distances the cleanup finds, at the rows' slots
+    int nitems;
+    int* hdr;               // kHdr*
+    float w1, w2;
+    double denomA, denomB;
+    float* loss;
+    float* terms;
+    ChamferPeerSum peer;
+};
+
 struct TcSweepParams {
     const float4* PA;
     const float4* PB;
     int B, NpA, NpB;       // padded cloud sizes (multiples of 256)
     int rbA, rbB;          // 256-row blocks per batch element: NpA / 256, NpB / 256
-    float4* rowfin;        // [B][NpA + NpB]  {b1, b2, b3, c1 | c2 << 16}: rows of A (searching B), then rows of B (searching A)
     float* tilemin;        // [B][ (nstB*NpA + nstA*NpB) * kParts ]  per supertile of the searched cloud, read-out group and row
     int nstA, nstB;        // supertiles of cloud A / B
-    int* done;             // [B*(rbA+rbB)*kRT]  read-out warps that have published a row tile (target 4)
     int wait_prepare;      // launched programmatically behind the prepare grid
     const int* prepared;   // upload mode: [B] preparer CTAs that have written an element's operands (target prepared_target); else null
     int prepared_target;
+    TcFinParams f;         // the certifier warps' inputs and outputs
 };
 
 __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p) {
@@ -453,19 +489,28 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
     unsigned char* s_a = smem;                                            // [2][kRT][128][64 B]   query operand tiles, double-buffered per item
     unsigned char* s_b = s_a + 2 * kRT * kTQ * kRowB;                     // [kStages][256][64 B]  candidate operand ring
     float4* s_c = reinterpret_cast<float4*>(s_b + kStages * kTNc * kRowB);  // [kCStages][256]      compact ring
-    float4* s_pub = s_c + kCStages * kTNc;                                // [2][kParts][256]     locator triples per column quarter, per item parity
-    __shared__ unsigned long long cfull[kCStages], cempty[kCStages], full_b[kStages], empty_b[kStages], tfull[kRT], tempty[kRT], a_full[2], a_empty[2],
-        pub_full[2], pub_empty[2];
+    float4* s_pub = s_c + kCStages * kTNc;                                // [kParts][256]        locator triples per column quarter
+    unsigned char* s_chunk = reinterpret_cast<unsigned char*>(s_pub + kParts * kItemRows);   // [256][400 B] the certifiers' located chunks
+    __shared__ unsigned long long cert_bar[kCertWarps], cfull[kCStages], cempty[kCStages], full_b[kStages], empty_b[kStages], tfull[kRT], tempty[kRT], a_full[2],
+        a_empty[2], pub_full, pub_empty;
     __shared__ unsigned s_tmem;
 
+    __shared__ double s_part[2][kCertWarps];
+    __shared__ int s_cnt[2][kCertWarps];
+
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // the finalize grid may become resident beside this one right away: its blocks wait for `done`
+#ifdef F3D_TC_PROF
+    if (tid == 0 && blockIdx.x < 148) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); g_certprof[blockIdx.x * 8 + 5] = (long long)g_; }  // CTA start
+#endif
+    // the cleanup grid may be set up right away: its blocks take the SMs as the CTAs of this grid leave and wait for the grid's end
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         for (int s = 0; s < kCStages; ++s) { mbar_init(&cfull[s], 1); mbar_init(&cempty[s], kConvWarps); }
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_b[s], kConvWarps); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < kRT; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiWarps); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], kConvWarps); mbar_init(&a_empty[s], 1); mbar_init(&pub_full[s], kEpiWarps); mbar_init(&pub_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], kConvWarps); mbar_init(&a_empty[s], 1); }
+        mbar_init(&pub_full, kEpiWarps); mbar_init(&pub_empty, kCertWarps);
+        for (int s = 0; s < kCertWarps; ++s) mbar_init(&cert_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&s_tmem, kRT * kTNc);  // all 512 columns: one 256-column accumulator per row tile
@@ -477,7 +522,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
     const int ipe = p.rbA + p.rbB, nitems = p.B * ipe;   // items per batch element: row blocks of A, then of B
     // every role walks the same item sequence; tile / slot counters run on across items so the pipelines never drain
     if (warp >= kEpiWarps) {
-      // the two auxiliary warpgroups (converters; producer / MMA issuer / publisher / one idle warp) hand registers back
+      // the four auxiliary warpgroups (converters; producer / MMA issuer / two idle warps; certifiers) hand registers back
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAuxRegs));
       if (warp == kWarpProducer) {
         if (lane == 0) {
@@ -601,47 +646,186 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             }
         }
         if (warp == kEpiWarps && lane == 0) PROF_OUT(5, 3);
-      } else if (warp == kWarpPublisher) {
-        // ---- publisher: merges the four column quarters of every row, stores the row's locator triple, and raises the row
-        // tiles' completion flags — the device-wide fence and the atomics stay off the read-out warps' critical path --------
-        unsigned it = 0;
+      } else if (warp >= kWarpCert) {
+        // ---- certifiers: the item that has just left the read-out is certified and re-evaluated in the reference arithmetic
+        // while the tensor cores work on the next one.  Phase 1, lane <-> row: merge the four column quarters' locator records
+        // and decide — b2 > b1 + window: the exact argmin lies in chunk c1; else b3 > b1 + window: in c1 or c2; else ambiguous
+        // (listed for the cleanup kernel).  Phase 2, warp <-> row, lane <-> candidate of the located 32-candidate chunk: three
+        // coalesced loads, one distance, REDUX.MIN + ballot for (minimum, lowest index) — four rows in flight.
+        const TcFinParams& f = p.f;
+        const int cw = warp - kWarpCert;
+        const unsigned full = 0xffffffffu;
+        if (p.wait_prepare) asm volatile("griddepcontrol.wait;" ::: "memory");   // norms and norm maxima come from the prepare grid
+        unsigned it = 0, cphase = 0;
+        // this warp's barrier, as an address of its own: folded into another shared-memory base as "[R + -0xc0]" the operand is
+        // mis-tracked by compute-sanitizer's synccheck ("missing init" on an initialised barrier)
+        unsigned long long* cbar = &cert_bar[cw];
+        asm volatile("" : "+l"(cbar));
+        PROF_DECL;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
             const int b = item / ipe, k = item - b * ipe;
-            const bool dir = k >= p.rbA;
+            const bool dir = k >= p.rbA;                       // false: rows of A search B; true: rows of B search A
             const int rb = dir ? k - p.rbA : k;
+            const int Q = dir ? f.M : f.N, R = dir ? f.N : f.M;        // queries / searched points per element
+            const float* gQ = (dir ? f.Bp : f.A) + (size_t)b * Q * 3;
+            const float* gP = (dir ? f.A : f.Bp) + (size_t)b * R * 3;
             const unsigned pb = it & 1;
-            const unsigned idmask = (1u << tc_idbits((dir ? p.NpA : p.NpB) / kTNc)) - 1u;
-            mbar_wait(&pub_full[pb], (it >> 1) & 1);
-            float4* out = p.rowfin + (size_t)b * (p.NpA + p.NpB) + (dir ? p.NpA : 0) + (size_t)rb * kItemRows;
-            const float4* src = s_pub + pb * kParts * kItemRows;
-#pragma unroll 2
-            for (int rin = lane; rin < kItemRows; rin += 32) {
-                // quarter q's record: values with the quarter's running chunk number (2 * tile + chunk) in their low bits ->
-                // global chunk id = tile * 8 + q * 2 + chunk.  Quarters hold disjoint chunk sets: insert the two located minima;
+            const int idbits = tc_idbits((dir ? p.NpA : p.NpB) / kTNc);
+            const unsigned idmask = (1u << idbits) - 1u;
+            const int rin = cw * 32 + lane;
+            const int q = rb * kItemRows + rin;
+            const bool valid = q < Q;
+            // what does not depend on the sweep is fetched before the wait (device-resident inputs; in upload mode the element
+            // may still be crossing PCIe — its points are only known to have arrived once the item's records are here)
+            float qx = 0.f, qy = 0.f, qz = 0.f, nq = 0.f, other = 0.f;
+            const bool early = p.prepared == nullptr;
+            if (valid && early) {
+                nq = __ldcg(&((dir ? p.PB : p.PA) + (size_t)b * (dir ? p.NpB : p.NpA) + q)->w);
+                other = __uint_as_float(__ldcg(f.maxn + (size_t)(dir ? 0 : 1) * p.B + b));
+                qx = __ldcg(gQ + 3 * (size_t)q); qy = __ldcg(gQ + 3 * (size_t)q + 1); qz = __ldcg(gQ + 3 * (size_t)q + 2);
+            }
+            PROF(4);
+            mbar_wait(&pub_full, it & 1);
+            PROF(0);
+            Loc3 e;
+            e.b1 = INFINITY; e.b2 = INFINITY; e.b3 = INFINITY; e.c1 = 0; e.c2 = 0;
+            {
+                // quarter q4's record: values with the quarter's running chunk number (2 * tile + chunk) in their low bits ->
+                // global chunk id = tile * 8 + q4 * 2 + chunk.  Quarters hold disjoint chunk sets: insert the two located minima;
                 // the third value can only be third or later
-                Loc3 e;
-                e.b1 = INFINITY; e.b2 = INFINITY; e.b3 = INFINITY; e.c1 = 0; e.c2 = 0;
+                const float4* src = s_pub + rin;
 #pragma unroll
-                for (int q = 0; q < kParts; ++q) {
-                    const float4 o = src[q * kItemRows + rin];
+                for (int q4 = 0; q4 < kParts; ++q4) {
+                    const float4 o = src[q4 * kItemRows];
                     const unsigned i1 = __float_as_uint(o.x) & idmask, i2 = __float_as_uint(o.y) & idmask;
-                    loc3_insert(e, o.x, (int)((i1 >> 1) * (kTNc / kTcChunk) + q * (kTNc / kParts / kTcChunk) + (i1 & 1u)));
-                    loc3_insert(e, o.y, (int)((i2 >> 1) * (kTNc / kTcChunk) + q * (kTNc / kParts / kTcChunk) + (i2 & 1u)));
+                    loc3_insert(e, o.x, (int)((i1 >> 1) * (kTNc / kTcChunk) + q4 * (kTNc / kParts / kTcChunk) + (i1 & 1u)));
+                    loc3_insert(e, o.y, (int)((i2 >> 1) * (kTNc / kTcChunk) + q4 * (kTNc / kParts / kTcChunk) + (i2 & 1u)));
                     e.b3 = fminf(e.b3, o.z);
                 }
-                out[rin] = loc3_pack(e);
             }
+            // (released after the merge has consumed the loads: an arrive does not wait for an LDS in flight)
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&pub_empty[pb]);
-                // the read-out warps' supertile minima were stored before they arrived on pub_full (release / acquire at CTA
-                // scope); this fence is cumulative: they and this warp's rows are visible device-wide before the flags move
-                __threadfence();
-                atomicExch(p.done + (size_t)item * kRT, 4);
-                atomicExch(p.done + (size_t)item * kRT + 1, 4);
+            if (lane == 0) mbar_arrive(&pub_empty);
+            // ---- phase 1 ----
+            float best = 0.f, win = 0.f, errlim = 0.f;
+            int loc1 = -1, loc2 = -1;      // chunks to re-evaluate (-1: none)
+            bool amb = false;
+            if (valid) {
+                if (!early) {   // (the producer saw `prepared` before this item's first tile; L2 loads)
+                    nq = __ldcg(&((dir ? p.PB : p.PA) + (size_t)b * (dir ? p.NpB : p.NpA) + q)->w);
+                    other = __uint_as_float(__ldcg(f.maxn + (size_t)(dir ? 0 : 1) * p.B + b));
+                    qx = __ldcg(gQ + 3 * (size_t)q); qy = __ldcg(gQ + 3 * (size_t)q + 1); qz = __ldcg(gQ + 3 * (size_t)q + 2);
+                }
+                best = fmaxf(e.b1, 0.0f);
+                // the chunk numbers embedded in the located values moved them by up to 2^(idbits-23) relative
+                const float idrel = ldexpf(1.0f, idbits - 23);
+                win = fmaf(kTcWinRel + 2.0f * idrel, best, kTcWinAbs * (nq + other));
+                errlim = fmaf(idrel, best, kTcErrAbs * (nq + other));
+                // written so that NaN / inf / out-of-range norms can only make the row ambiguous, never certified
+                const bool sane = nq <= kTcNormLimit && other <= kTcNormLimit && nq + other >= kTcNormFloor;
+                const bool one = sane && fmaxf(e.b2, 0.0f) > best + win;
+                const bool two = sane && !one && fmaxf(e.b3, 0.0f) > best + win;
+                amb = !(one || two);
+                if (!amb) loc1 = e.c1;
+                if (two) loc2 = e.c2;
             }
-            __syncwarp();
+            PROF(1);
+            // ---- phase 2: the located chunk (both located chunks) in the reference arithmetic.  Every row fetches its chunk —
+            // 32 candidates = 384 contiguous bytes — with ONE bulk copy (TMA) into its own shared-memory row: a gather of 256
+            // chunks per item that costs the SM eight instructions; the scan then runs thread <-> row out of shared memory ----
+            float d = INFINITY;
+            int j = 0x7fffffff;
+            unsigned char* myrow = s_chunk + rin * kChunkPitch;
+            if (p.prepared) asm volatile("fence.proxy.async;" ::: "memory");   // upload mode: the points were written with generic stores by the upload grid
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c = pass == 0 ? loc1 : loc2;
+                if (pass == 1 && !__any_sync(full, c >= 0)) break;   // (about one warp in nine holds a two-chunk row)
+                const int j0 = c * kTcChunk;
+                const float* pp = gP + 3 * (size_t)(c < 0 ? 0 : j0);
+                const bool staged = c >= 0 && j0 + kTcChunk <= R && (reinterpret_cast<uintptr_t>(pp) & 15u) == 0;
+                // one arrival per warp and pass, carrying the bytes of all its rows' copies
+                const unsigned nstaged = __popc(__ballot_sync(full, staged));
+                if (lane == 0) mbar_expect_tx(cbar, nstaged * (kTcChunk * 12));
+                __syncwarp();
+                if (staged) {
+                    tma_bulk_g2s(myrow, pp, kTcChunk * 12, cbar);
+                } else {
+                    if (c >= 0) {   // ragged end of the cloud, or a cloud that is not 16-byte aligned there: direct loads
+                        const int j1 = min(j0 + kTcChunk, R);
+#pragma unroll 4
+                        for (int jj = j0; jj < j1; ++jj) {
+                            const float dd = sqdist3<false>(qx, qy, qz, __ldcg(gP + 3 * (size_t)jj), __ldcg(gP + 3 * (size_t)jj + 1), __ldcg(gP + 3 * (size_t)jj + 2));
+                            if (dd < d || (dd == d && jj < j)) { d = dd; j = jj; }
+                        }
+                    }
+                }
+                mbar_wait(cbar, cphase);
+                cphase ^= 1u;
+                if (staged) {
+                    // (a - b)² is the same bits as (b - a)²: one operand order serves both directions of the reference's A .- B
+#pragma unroll 2
+                    for (int h = 0; h < kTcChunk / 4; ++h) {  // 4 candidates = three 16-byte shared-memory loads per trip
+                        const float4 v0 = *reinterpret_cast<const float4*>(myrow + h * 48);
+                        const float4 v1 = *reinterpret_cast<const float4*>(myrow + h * 48 + 16);
+                        const float4 v2 = *reinterpret_cast<const float4*>(myrow + h * 48 + 32);
+                        const float cc[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float dd = sqdist3<false>(qx, qy, qz, cc[3 * u], cc[3 * u + 1], cc[3 * u + 2]);
+                            const int jj = j0 + h * 4 + u;
+                            if (dd < d || (dd == d && jj < j)) { d = dd; j = jj; }   // lowest index on ties, also across the two chunks
+                        }
+                    }
+                }
+                __syncwarp();
+                PROF(2 + pass);
+            }
+            double mine = 0.0;
+            if (valid && !amb) {
+                // self-check of the error bound at the located minimum
+                if (!(fabsf(d - best) <= fmaf(kTcErrRel, d, errlim))) {
+                    amb = true;
+                    atomicAdd(f.hdr + kHdrViol, 1);
+                } else {
+                    int32_t* nn = dir ? f.nnB : f.nnA;
+                    if (nn) nn[(size_t)b * Q + q] = j;
+                    mine = (double)d;
+                }
+            }
+            // ---- the item's partial sum (fixed order) and its ambiguous rows, listed in row order at fixed slots ----
+            const unsigned ambmask = __ballot_sync(full, valid && amb);
+            mine = warp_sum(mine);
+            if (lane == 0) { s_part[pb][cw] = mine; s_cnt[pb][cw] = __popc(ambmask); }
+            named_bar_sync(1, kCertWarps * 32);   // (s_part / s_cnt are double-buffered by item parity: one barrier per item is enough)
+            if (ambmask) {
+                int lbase = 0;
+                if (lane == 0) lbase = atomicAdd(f.hdr + kHdrAmb, __popc(ambmask));   // the work list's order is arbitrary; results go to fixed slots
+                lbase = __shfl_sync(full, lbase, 0);
+                if (valid && amb) {
+                    const int wpos = __popc(ambmask & ((1u << lane) - 1u));
+                    int pos = wpos;
+                    for (int w = 0; w < cw; ++w) pos += s_cnt[pb][w];
+                    const size_t slot = (size_t)item * kItemRows + pos;
+                    f.ambq[slot] = q;
+                    f.amblim[slot] = best + win;
+                    f.amblist[lbase + wpos] = (int)slot;
+                }
+            }
+            if (cw == 0 && lane == 0) {
+                double s2 = 0.0;
+                int c = 0;
+#pragma unroll
+                for (int w = 0; w < kCertWarps; ++w) { s2 += s_part[pb][w]; c += s_cnt[pb][w]; }
+                f.partial[item] = s2;
+                f.ambcnt[item] = c;
+            }
         }
+#ifdef F3D_TC_PROF
+        if (cw == 0 && lane == 0 && blockIdx.x < 148) {
+            for (int i_ = 0; i_ < 5; ++i_) g_certprof[blockIdx.x * 8 + i_] = pf_[i_];
+            unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); g_certprof[blockIdx.x * 8 + 6] = (long long)g_;   // certifier end
+        }
+#endif
       }
     } else {
         // the four read-out warpgroups take them: both tcgen05.ld of an accumulator quarter in flight = 64 registers of data
@@ -701,16 +885,19 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
                     }
                 }
             }
-            // hand the two rows' triples to the publisher (double-buffered by item parity)
-            const unsigned pb = it & 1;
-            mbar_wait(&pub_empty[pb], ((it >> 1) & 1) ^ 1);
+            // hand the two rows' triples to the certifier warps (double-buffered by item parity)
+            // (single buffer: the certifiers merge an item's records as soon as they are complete, an item's time before the next write)
+            mbar_wait(&pub_empty, (it & 1) ^ 1);
 #pragma unroll
             for (int r = 0; r < kRT; ++r)
-                s_pub[(pb * kParts + part) * kItemRows + r * kTQ + rin] = make_float4(loc[r].b1, loc[r].b2, loc[r].b3, 0.f);
+                s_pub[part * kItemRows + r * kTQ + rin] = make_float4(loc[r].b1, loc[r].b2, loc[r].b3, 0.f);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&pub_full[pb]);
+            if (lane == 0) mbar_arrive(&pub_full);
         }
         if ((warp == 0 || warp == 8) && lane == 0) PROF_OUT(8 + (warp >> 3) * 3, 3);
+#ifdef F3D_TC_PROF
+        if (tid == 0 && blockIdx.x < 148) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); g_tcprof[blockIdx.x * 16 + 14] = (long long)g_; }  // the read-out's end
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -722,207 +909,30 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
 
 // ---- finalize: certify, re-evaluate exactly, reduce the loss -----------------------------------------------------------
 #ifdef F3D_TC_PROF
-__device__ unsigned long long g_finprof[8192 * 8];
 __device__ unsigned long long g_cleanprof[4096 * 4];
 #define CPROF(k) do { if (threadIdx.x == 0 && blockIdx.x < 4096) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); g_cleanprof[blockIdx.x * 4 + (k)] = g_; } } while (0)
-#define FPROF(k) do { if (threadIdx.x == 0 && blockIdx.x < 8192) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); g_finprof[blockIdx.x * 8 + (k)] = g_; } } while (0)
 #else
-#define FPROF(k)
 #define CPROF(k)
 #endif
-struct TcFinParams {
-    const float* A;
-    const float* Bp;
-    const float4* PA;
-    const float4* PB;
-    int B, N, M, NpA, NpB, rbA, rbB, nstA, nstB;
-    const float4* rowfin;
-    const float* tilemin;
-    const unsigned* maxn;   // [2][B]
-    const int* done;
-    int32_t* nnA;
-    int32_t* nnB;
-    double* partial;        // [nfin] certified rows of every finalize block
-    int* ambcnt;            // [nfin]        ambiguous rows of every finalize block ...
-    int* ambq;              // [nfin][kFinT] ... their row numbers, in row order ...
-    float* amblim;          // [nfin][kFinT] ... and their windows' upper ends
-    int* amblist;           // [rows]        (finalize block << 6 | position) of every ambiguous row, in arrival order: the cleanup's work list
-    float* ambd;            // [nfin][kFinT] the exact distances the cleanup finds, at the rows' fixed positions
-    int nfin;
-    int* hdr;               // kHdr*
-    float w1, w2;
-    double denomA, denomB;
-    float* loss;
-    float* terms;
-    ChamferPeerSum peer;
-};
 
-__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
-}
-
-// Finalize, part 1 (co-resident with the sweep): thread <-> row; certify, re-evaluate the located 32 candidates exactly.  Kept
-// lean on purpose — 64 threads, <= 40 registers, 25 KB of shared memory, no block-wide loops — so that several blocks fit
-// beside a sweep CTA and keep pace with it; rows that cannot be certified are only LISTED here (in row order, at fixed
-// positions: the result stays bitwise repeatable) and rescanned by chamfer_tc_cleanup_kernel.
-__global__ void __launch_bounds__(kFinT, 24) chamfer_tc_finalize_kernel(TcFinParams p) {
-    // phase 2 staging: a row's 32-candidate chunk (384 B) is fetched with 24 cp.async of 16 bytes into the thread's own
-    // shared-memory row — all of a block's fetches in flight together instead of four dependent load batches per thread
-    extern __shared__ __align__(16) unsigned char fin_smem[];
-    __shared__ double s_red[kFinT / 32];
-    __shared__ int s_cnt[kFinT / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    FPROF(0);
-    // block <-> 64 rows of a row tile: (item, r, half) in the sweep's order, so that blocks become ready in the order they are resident
-    constexpr int kPerTile = kTQ / kFinT;
-    const int ipe = p.rbA + p.rbB;
-    const int rt = (int)blockIdx.x / kPerTile, sub = (int)blockIdx.x - rt * kPerTile;   // row tile = item * kRT + r
-    const int item = rt / kRT, r = rt - item * kRT;
-    const int b = item / ipe, k = item - b * ipe;
-    const bool dir = k >= p.rbA;                       // false: rows of A search B; true: rows of B search A
-    const int rb = dir ? k - p.rbA : k;
-    const int Q = dir ? p.M : p.N, R = dir ? p.N : p.M;        // queries / searched points per element
-    const int npq = dir ? p.NpB : p.NpA;
-    const float* gQ = (dir ? p.Bp : p.A) + (size_t)b * Q * 3;
-    const float* gP = (dir ? p.A : p.Bp) + (size_t)b * R * 3;
-    const int q = rb * kItemRows + r * kTQ + sub * kFinT + tid;
-    const bool valid = q < Q;
-    double mine = 0.0;
-
-    if (tid == 0) {
-        const int* flag = p.done + rt;
-        while (ld_acquire_i32(flag) < 4) __nanosleep(200);
-    }
-    __syncthreads();
-    FPROF(1);
-
-    // ---- phase 1: certified (one chunk), certified (two chunks) or ambiguous ---------------------------------------------
-    float qx = 0.f, qy = 0.f, qz = 0.f, best = 0.f, win = 0.f, errlim = 0.f;
-    int loc = 0, loc2 = 0;
-    bool amb = false, two = false;
-    if (valid) {
-        const Loc3 e = loc3_unpack(__ldcg(p.rowfin + (size_t)b * (p.NpA + p.NpB) + (dir ? p.NpA : 0) + q));
-        const float nq = __ldcg(&((dir ? p.PB : p.PA) + (size_t)b * npq + q)->w);
-        const float other = __uint_as_float(__ldcg(p.maxn + (size_t)(dir ? 0 : 1) * p.B + b));
-        qx = __ldg(gQ + 3 * (size_t)q); qy = __ldg(gQ + 3 * (size_t)q + 1); qz = __ldg(gQ + 3 * (size_t)q + 2);
-        best = fmaxf(e.b1, 0.0f);
-        loc = e.c1; loc2 = e.c2;
-        // the chunk numbers embedded in the located values moved them by up to 2^(idbits-23) relative
-        const float idrel = ldexpf(1.0f, tc_idbits((dir ? p.NpA : p.NpB) / kTNc) - 23);
-        win = fmaf(kTcWinRel + 2.0f * idrel, best, kTcWinAbs * (nq + other));
-        errlim = fmaf(idrel, best, kTcErrAbs * (nq + other));
-        // written so that NaN / inf / out-of-range norms can only make the row ambiguous, never certified
-        const bool sane = nq <= kTcNormLimit && other <= kTcNormLimit && nq + other >= kTcNormFloor;
-        const bool one = sane && fmaxf(e.b2, 0.0f) > best + win;
-        two = sane && !one && fmaxf(e.b3, 0.0f) > best + win;
-        amb = !(one || two);
-    }
-    FPROF(2);
-    // ---- phase 2: certified rows — the 32 candidates of the located chunk (of both located chunks), in the reference arithmetic ----
-    {
-        const bool cert = valid && !amb;
-        unsigned char* mychunk = fin_smem + tid * kFinPitch;
-        float d = INFINITY;
-        int j = 0x7fffffff;
-        // one pass per located chunk; the second pass runs only in warps that hold a two-chunk row (about one warp in nine)
-        for (int pass = 0; pass < 2; ++pass) {
-            const bool mine_pass = cert && (pass == 0 || two);
-            if (pass == 1 && !__any_sync(0xffffffffu, mine_pass)) break;
-            const int j0 = (pass == 0 ? loc : loc2) * kTcChunk, j1 = min(j0 + kTcChunk, R);
-            const float* pp = gP + 3 * (size_t)j0;
-            const bool staged = mine_pass && j0 + kTcChunk <= R && (reinterpret_cast<uintptr_t>(pp) & 15u) == 0;
-            if (staged) {
-#pragma unroll
-                for (int i = 0; i < kTcChunk * 12 / 16; ++i) cp_async16(mychunk + 16 * i, reinterpret_cast<const unsigned char*>(pp) + 16 * i);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            if (mine_pass && !staged) {   // ragged end of the cloud or a cloud that is not 16-byte aligned there: direct loads
-#pragma unroll 4
-                for (int jj = j0; jj < j1; ++jj) {
-                    const float px = __ldg(gP + 3 * (size_t)jj), py = __ldg(gP + 3 * (size_t)jj + 1), pz = __ldg(gP + 3 * (size_t)jj + 2);
-                    const float dd = dir ? sqdist3<false>(px, py, pz, qx, qy, qz) : sqdist3<false>(qx, qy, qz, px, py, pz);
-                    if (dd < d || (dd == d && jj < j)) { d = dd; j = jj; }
-                }
-            }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");   // a thread only reads the bytes it fetched itself: no barrier needed
-            if (staged) {
-                // row pitch 400 B = 25 x 16 B: the eight lanes of a quarter-warp hit eight different 16-byte bank groups
-#pragma unroll 2
-                for (int h = 0; h < kTcChunk / 4; ++h) {  // 4 candidates = three 16-byte shared-memory loads per trip
-                    const float4 v0 = *reinterpret_cast<const float4*>(mychunk + h * 48);
-                    const float4 v1 = *reinterpret_cast<const float4*>(mychunk + h * 48 + 16);
-                    const float4 v2 = *reinterpret_cast<const float4*>(mychunk + h * 48 + 32);
-                    const float c[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        // operand order of the reference: (a - b) with a from the first cloud
-                        const float dd = dir ? sqdist3<false>(c[3 * u], c[3 * u + 1], c[3 * u + 2], qx, qy, qz)
-                                             : sqdist3<false>(qx, qy, qz, c[3 * u], c[3 * u + 1], c[3 * u + 2]);
-                        const int jj = j0 + h * 4 + u;
-                        if (dd < d || (dd == d && jj < j)) { d = dd; j = jj; }   // lowest index on ties, also across the two chunks
-                    }
-                }
-            }
-        }
-        if (cert) {
-            // self-check of the error bound at the located minimum
-            if (!(fabsf(d - best) <= fmaf(kTcErrRel, d, errlim))) {
-                amb = true;
-                atomicAdd(p.hdr + kHdrViol, 1);
-            } else {
-                int32_t* nn = dir ? p.nnB : p.nnA;
-                if (nn) nn[(size_t)b * Q + q] = j;
-                mine += (double)d;
-            }
-        }
-    }
-    FPROF(3);
-    // ---- ambiguous rows: listed in row order for the cleanup kernel; block partial sum of the certified rows -------------
-    const unsigned ambmask = __ballot_sync(0xffffffffu, valid && amb);
-    mine = warp_sum(mine);
-    if (lane == 0) { s_cnt[warp] = __popc(ambmask); s_red[warp] = mine; }
-    __syncthreads();
-    int lbase = 0;
-    if (lane == 0 && ambmask) lbase = atomicAdd(p.hdr + kHdrAmb, __popc(ambmask));   // the work list's order is arbitrary; results go to fixed slots
-    lbase = __shfl_sync(0xffffffffu, lbase, 0);
-    if (valid && amb) {
-        const int wpos = __popc(ambmask & ((1u << lane) - 1u));
-        int pos = wpos;
-        for (int w = 0; w < warp; ++w) pos += s_cnt[w];
-        p.ambq[(size_t)blockIdx.x * kFinT + pos] = q;
-        p.amblim[(size_t)blockIdx.x * kFinT + pos] = best + win;
-        p.amblist[lbase + wpos] = (int)(blockIdx.x * kFinT + pos);
-    }
-    if (tid == 0) {
-        double s2 = 0.0;
-        int c = 0;
-        for (int w = 0; w < kFinT / 32; ++w) { s2 += s_red[w]; c += s_cnt[w]; }
-        p.partial[blockIdx.x] = s2;
-        p.ambcnt[blockIdx.x] = c;
-    }
-    FPROF(4);
-}
-
-// Finalize, part 2 (after part 1): the rows part 1 could not certify (~0.4 % on uniform clouds; every row of tie-heavy inputs)
-// are rescanned by a whole block each, taken from the work list: every supertile whose filter minimum lies within the row's
-// window is scanned in the reference arithmetic; the distance found goes to the row's FIXED slot.  The last block then adds
-// up the finalize blocks' partial sums and those slots in a fixed order (bitwise repeatable).
+// Cleanup (after the sweep): the rows the certifier warps could not certify (a handful on uniform clouds; every row of
+// tie-heavy inputs) are rescanned by a whole block each, taken from the work list: every supertile whose filter minimum lies
+// within the row's window is scanned in the reference arithmetic; the distance found goes to the row's FIXED slot.  The last
+// block then adds up the items' partial sums and those slots in a fixed order (bitwise repeatable).
 constexpr int kCleanT = 1024;   // wide blocks: the last one adds up thousands of partial sums in one round trip
 __global__ void __launch_bounds__(kCleanT, 1) chamfer_tc_cleanup_kernel(TcFinParams p) {
-    __shared__ bool s_last;
     constexpr int kMaxSel = 32;
     __shared__ int s_sel[kMaxSel], s_nsel;
     __shared__ unsigned s_wd[kCleanT / 32];
     __shared__ int s_wj[kCleanT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int kFinPerItem = kItemRows / kFinT;
     const int ipe = p.rbA + p.rbB;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // launched programmatically: the sweep grid has ended, its stores are visible
     CPROF(0);
     const int total_amb = __ldcg(p.hdr + kHdrAmb);
     for (int e = blockIdx.x; e < total_amb; e += gridDim.x) {
         const int slot = __ldcg(p.amblist + e);
-        const int fb = slot / kFinT;
-        const int item = fb / kFinPerItem;
+        const int item = slot / kItemRows;
         const int b = item / ipe, k = item - b * ipe;
         const bool dir = k >= p.rbA;
         const int Q = dir ? p.M : p.N, R = dir ? p.N : p.M;
@@ -1000,33 +1010,41 @@ __global__ void __launch_bounds__(kCleanT, 1) chamfer_tc_cleanup_kernel(TcFinPar
         }
         __syncthreads();  // s_wd / s_wj / s_nsel are reused by the next row
     }
-    // ---- the last block adds up every partial sum in a fixed order (bitwise repeatable) -----------------------------------
+    // ---- the grid's last block adds up every partial sum in a fixed order (bitwise repeatable).  It is the designated
+    // reducer (the grid is at most one block per SM: all blocks are resident together): the items' sums are in its registers
+    // by the time the other blocks have finished their rows ---------------------------------------------------------------
     CPROF(1);
-    if (tid == 0) {
-        __threadfence();
-        s_last = (atomicAdd(p.hdr + kHdrDone, 1) == (int)gridDim.x - 1);
+    if (blockIdx.x != gridDim.x - 1) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(p.hdr + kHdrDone, 1);
+        }
+        return;
     }
-    __syncthreads();
-    CPROF(2);
-    if (!s_last) return;
-    __threadfence();
     double sa = 0.0, sb = 0.0;
-    for (int k0 = 0; k0 < p.nfin; k0 += 4 * kCleanT) {   // per finalize block: four of them in flight per thread
+    for (int k0 = 0; k0 < p.nitems; k0 += 4 * kCleanT) {   // per item: four of them in flight per thread
         double v[4];
         int cn[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int kk = k0 + u * kCleanT + tid;
-            v[u] = kk < p.nfin ? __ldcg(p.partial + kk) : 0.0;
-            cn[u] = kk < p.nfin ? __ldcg(p.ambcnt + kk) : 0;
+            v[u] = kk < p.nitems ? __ldcg(p.partial + kk) : 0.0;
+            cn[u] = kk < p.nitems ? __ldcg(p.ambcnt + kk) : 0;
+        }
+        if (k0 == 0) {   // the other blocks' distances (ambd) are complete and visible from here on
+            if (tid == 0)
+                while (ld_acquire_i32(p.hdr + kHdrDone) < (int)gridDim.x - 1) __nanosleep(64);
+            __syncthreads();
+            CPROF(2);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int kk = k0 + u * kCleanT + tid;
-            if (kk < p.nfin) {
+            if (kk < p.nitems) {
                 double t = v[u];
-                for (int e = 0; e < cn[u]; ++e) t += (double)__ldcg(p.ambd + (size_t)kk * kFinT + e);   // the block's ambiguous rows, in row order
-                if ((kk / kFinPerItem) % ipe < p.rbA) sa += t; else sb += t;
+                for (int e = 0; e < cn[u]; ++e) t += (double)__ldcg(p.ambd + (size_t)kk * kItemRows + e);   // the item's ambiguous rows, in row order
+                if (kk % ipe < p.rbA) sa += t; else sb += t;
             }
         }
     }
@@ -1059,8 +1077,8 @@ __global__ void __launch_bounds__(kCleanT, 1) chamfer_tc_cleanup_kernel(TcFinPar
 }
 
 struct TcPlan {
-    int NpA, NpB, rbA, rbB, nstA, nstB, nblocks, nfin, nitems;
-    size_t off_PA, off_PB, off_rowfin, off_tilemin, off_partial, off_ambcnt, off_ambq, off_amblim, off_amblist, off_ambd, zero_from, off_hdr, off_maxn, off_done, off_arrived, zero_bytes, total;
+    int NpA, NpB, rbA, rbB, nstA, nstB, nitems;
+    size_t off_PA, off_PB, off_tilemin, off_partial, off_ambcnt, off_ambq, off_amblim, off_amblist, off_ambd, zero_from, off_hdr, off_maxn, off_arrived, zero_bytes, total;
 };
 
 TcPlan make_tc_plan(int B, int N, int M) {
@@ -1072,37 +1090,33 @@ TcPlan make_tc_plan(int B, int N, int M) {
     pl.nstA = (pl.NpA + kSuper - 1) / kSuper;
     pl.nstB = (pl.NpB + kSuper - 1) / kSuper;
     pl.nitems = B * (pl.rbA + pl.rbB);
-    pl.nblocks = pl.nitems * kRT;                 // row tiles
-    pl.nfin = pl.nblocks * (kTQ / kFinT);         // finalize blocks
     size_t o = 0;
     pl.off_hdr = o;     o = align_up(o + sizeof(int) * kHdrInts, 256);   // diagnostics first: a caller can find them
     pl.off_maxn = o;    o = align_up(o + sizeof(unsigned) * 2 * (size_t)B, 256);
-    pl.off_done = o;    o = align_up(o + sizeof(int) * (size_t)pl.nblocks, 256);
     pl.off_arrived = o; o = align_up(o + sizeof(int) * 2 * (size_t)B, 256);   // upload mode: arrived [B], prepared [B]
     pl.zero_from = 0;
-    pl.zero_bytes = o;  // header, norm maxima and completion counters are zeroed by ONE memset per call
+    pl.zero_bytes = o;  // header, norm maxima and arrival counters are zeroed by ONE memset per call
     pl.off_PA = o;      o = align_up(o + sizeof(float4) * (size_t)B * pl.NpA, 256);
     pl.off_PB = o;      o = align_up(o + sizeof(float4) * (size_t)B * pl.NpB, 256);
-    pl.off_rowfin = o;  o = align_up(o + sizeof(float4) * (size_t)B * (pl.NpA + pl.NpB), 256);
     pl.off_tilemin = o; o = align_up(o + sizeof(float) * kParts * (size_t)B * ((size_t)pl.nstB * pl.NpA + (size_t)pl.nstA * pl.NpB), 256);
-    pl.off_partial = o; o = align_up(o + sizeof(double) * (size_t)pl.nfin, 256);
-    pl.off_ambcnt = o;  o = align_up(o + sizeof(int) * (size_t)pl.nfin, 256);
-    pl.off_ambq = o;    o = align_up(o + sizeof(int) * (size_t)pl.nfin * kFinT, 256);
-    pl.off_amblim = o;  o = align_up(o + sizeof(float) * (size_t)pl.nfin * kFinT, 256);
-    pl.off_amblist = o; o = align_up(o + sizeof(int) * (size_t)pl.nfin * kFinT, 256);
-    pl.off_ambd = o;    o = align_up(o + sizeof(float) * (size_t)pl.nfin * kFinT, 256);
+    pl.off_partial = o; o = align_up(o + sizeof(double) * (size_t)pl.nitems, 256);
+    pl.off_ambcnt = o;  o = align_up(o + sizeof(int) * (size_t)pl.nitems, 256);
+    pl.off_ambq = o;    o = align_up(o + sizeof(int) * (size_t)pl.nitems * kItemRows, 256);
+    pl.off_amblim = o;  o = align_up(o + sizeof(float) * (size_t)pl.nitems * kItemRows, 256);
+    pl.off_amblist = o; o = align_up(o + sizeof(int) * (size_t)pl.nitems * kItemRows, 256);
+    pl.off_ambd = o;    o = align_up(o + sizeof(float) * (size_t)pl.nitems * kItemRows, 256);
     pl.total = o;
     return pl;
 }
 
-constexpr size_t kTcSmem = 2 * kRT * kTQ * kRowB + kStages * kTNc * kRowB + kCStages * kTNc * 16 + 2 * kParts * kItemRows * 16 + 1024;  // 129 KB
+constexpr size_t kTcSmem = 2 * kRT * kTQ * kRowB + kStages * kTNc * kRowB + kCStages * kTNc * 16 + kParts * kItemRows * 16 + kItemRows * kChunkPitch + 1024;  // 213 KB
 
 }  // namespace
 
 size_t chamfer_tc_workspace_bytes(int B, int N, int M) { return make_tc_plan(B, N, M).total; }
 #ifdef F3D_TC_PROF
 extern "C" __attribute__((visibility("default"))) int f3d_debug_read_tc(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, g_tcprof, nbytes); }
-extern "C" __attribute__((visibility("default"))) int f3d_debug_read_fin(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, g_finprof, nbytes); }
+extern "C" __attribute__((visibility("default"))) int f3d_debug_read_cert(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, g_certprof, nbytes); }
 extern "C" __attribute__((visibility("default"))) int f3d_debug_read_clean(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, g_cleanprof, nbytes); }
 #endif
 
@@ -1111,7 +1125,7 @@ extern "C" __attribute__((visibility("default"))) int f3d_debug_read_clean(void*
 bool chamfer_tc_possible(int B, int N, int M) {
     if (B <= 0 || N < 1 || M < 1) return false;
     const TcPlan pl = make_tc_plan(B, N, M);
-    if ((long long)B * (pl.rbA + pl.rbB) * kRT * (kTQ / kFinT) > 0x3fffffffLL) return false;
+    if ((long long)B * (pl.rbA + pl.rbB) * kItemRows > 0x3fffffffLL) return false;   // slots are ints
     return std::max(pl.NpA, pl.NpB) <= 131072;   // running chunk numbers travel in <= 10 mantissa bits, global chunk ids as 16 bits
 }
 bool chamfer_tc_supported(int B, int N, int M) {
@@ -1132,14 +1146,9 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
     static int sm_count[256];
     if (dev < 0 || dev >= 256 || !attr_done[dev]) {
         F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-        // the finalize blocks must fit beside a sweep CTA: with the smallest carveout that holds the sweep (132 KB for its
-        // 130 KB) no finalize block (2.5 KB of shared memory) finds room, and the whole finalize runs after the sweep
+        // the grids that run BEFORE / BESIDE the sweep must leave the SMs in the sweep's shared-memory configuration: an SM that
+        // an upload CTA has configured for a large L1 cannot take a sweep CTA (130 KB of shared memory) until it drains
         F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinT * kFinPitch));
-        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_cleanup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        // ... and the grids that run BEFORE / BESIDE the sweep must leave the SMs in that same configuration: an SM that an
-        // upload CTA has configured for a large L1 cannot take a sweep CTA (130 KB of shared memory) until it drains
         F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_upload_prepare_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_prepare_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         int sms = 0;
@@ -1175,32 +1184,10 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
         F3D_CHECK_LAUNCH("chamfer_tc_prepare_kernel");
     }
 
-    TcSweepParams sp;
-    sp.PA = pp.PA; sp.PB = pp.PB; sp.B = B; sp.NpA = pl.NpA; sp.NpB = pl.NpB; sp.rbA = pl.rbA; sp.rbB = pl.rbB;
-    sp.rowfin = reinterpret_cast<float4*>(w + pl.off_rowfin);
-    sp.tilemin = reinterpret_cast<float*>(w + pl.off_tilemin);
-    sp.nstA = pl.nstA; sp.nstB = pl.nstB;
-    sp.done = reinterpret_cast<int*>(w + pl.off_done);
-    sp.wait_prepare = upload ? 0 : 1;
-    sp.prepared = upload ? reinterpret_cast<const int*>(w + pl.off_arrived) + B : nullptr;
-    sp.prepared_target = prepared_target;
-    const int nitems = B * (pl.rbA + pl.rbB);
-    {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(std::min(nitems, sms)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kTcSmem; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_tc_sweep_kernel, sp));
-    }
-    F3D_CHECK_LAUNCH("chamfer_tc_sweep_kernel");
-    if (flags & F3D_FLAG_SWEEP_ONLY) return F3D_OK;
-
     TcFinParams fp;
     fp.A = A; fp.Bp = Bp; fp.PA = pp.PA; fp.PB = pp.PB;
     fp.B = B; fp.N = N; fp.M = M; fp.NpA = pl.NpA; fp.NpB = pl.NpB; fp.rbA = pl.rbA; fp.rbB = pl.rbB; fp.nstA = pl.nstA; fp.nstB = pl.nstB;
-    fp.rowfin = sp.rowfin; fp.tilemin = sp.tilemin; fp.maxn = pp.maxn; fp.done = sp.done;
+    fp.tilemin = reinterpret_cast<float*>(w + pl.off_tilemin); fp.maxn = pp.maxn;
     fp.nnA = nnA_dev; fp.nnB = nnB_dev;
     fp.partial = reinterpret_cast<double*>(w + pl.off_partial);
     fp.ambcnt = reinterpret_cast<int*>(w + pl.off_ambcnt);
@@ -1208,7 +1195,7 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
     fp.amblim = reinterpret_cast<float*>(w + pl.off_amblim);
     fp.amblist = reinterpret_cast<int*>(w + pl.off_amblist);
     fp.ambd = reinterpret_cast<float*>(w + pl.off_ambd);
-    fp.nfin = pl.nfin;
+    fp.nitems = pl.nitems;
     fp.hdr = reinterpret_cast<int*>(w + pl.off_hdr);
     fp.w1 = w1; fp.w2 = w2;
     fp.denomA = (double)N * (double)B_total;
@@ -1216,20 +1203,37 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
     fp.loss = loss_dev; fp.terms = terms_dev;
     if (peer) fp.peer = *peer;
     else { fp.peer.mailboxes = nullptr; fp.peer.nranks = 0; fp.peer.rank = 0; fp.peer.seq = 0; fp.peer.timeout_ns = 0; fp.peer.fault = nullptr; }
+
+    TcSweepParams sp;
+    sp.PA = pp.PA; sp.PB = pp.PB; sp.B = B; sp.NpA = pl.NpA; sp.NpB = pl.NpB; sp.rbA = pl.rbA; sp.rbB = pl.rbB;
+    sp.tilemin = reinterpret_cast<float*>(w + pl.off_tilemin);
+    sp.nstA = pl.nstA; sp.nstB = pl.nstB;
+    sp.wait_prepare = upload ? 0 : 1;
+    sp.prepared = upload ? reinterpret_cast<const int*>(w + pl.off_arrived) + B : nullptr;
+    sp.prepared_target = prepared_target;
+    sp.f = fp;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
     {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(pl.nfin); cfg.blockDim = dim3(kFinT); cfg.dynamicSmemBytes = kFinT * kFinPitch; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.gridDim = dim3(std::min(pl.nitems, sms)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kTcSmem; cfg.stream = stream;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_tc_sweep_kernel, sp));
+    }
+    F3D_CHECK_LAUNCH("chamfer_tc_sweep_kernel");
+    if (flags & F3D_FLAG_SWEEP_ONLY) return F3D_OK;
+    {
+        // programmatic launch: the blocks are set up while the sweep runs and take the SMs as its CTAs leave (griddepcontrol.wait
+        // holds them until the whole sweep grid has ended)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(std::min(pl.nitems, sms)); cfg.blockDim = dim3(kCleanT);   // one wave: the reducer block waits for the others cfg.dynamicSmemBytes = 0; cfg.stream = stream;
 #ifdef F3D_TC_EXP_ENV
-        if (getenv("F3D_TC_NOPDL")) attr[0].val.programmaticStreamSerializationAllowed = 0;  // development: finalize strictly after the sweep
+        if (getenv("F3D_TC_NOPDL")) attr[0].val.programmaticStreamSerializationAllowed = 0;  // development: cleanup launched strictly after the sweep
 #endif
         cfg.attrs = attr; cfg.numAttrs = 1;
-        F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_tc_finalize_kernel, fp));
+        F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_tc_cleanup_kernel, fp));
     }
-    F3D_CHECK_LAUNCH("chamfer_tc_finalize_kernel");
-    chamfer_tc_cleanup_kernel<<<std::min(pl.nfin, 2 * sms), kCleanT, 0, stream>>>(fp);
     F3D_CHECK_LAUNCH("chamfer_tc_cleanup_kernel");
     return F3D_OK;
 }

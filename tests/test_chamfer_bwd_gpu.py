@@ -52,8 +52,9 @@ def test_pointcloud_front_end(f3d, oracle):
 
 
 def test_backward_is_bitwise_repeatable_and_covers_both_paths(f3d, oracle):
-    """Clouds of up to 8192 points take the sorted-gather pullback (one launch, no atomics): bitwise identical reruns, also with
-    many sources pulling on one target.  Larger clouds take the RED.ADD fallback: still within float32 round-off of the oracle."""
+    """Clouds of up to 24576 points take the counting-sort gather pullback (one launch, no global atomics): bitwise identical
+    reruns, also with many sources pulling on one target (> 32: summed by the whole block).  Larger clouds take the RED.ADD
+    fallback: still within float32 round-off of the oracle."""
     rng = np.random.default_rng(11)
     A = rng.random((3, 5000, 3), dtype=np.float32)
     Bc = rng.random((3, 40, 3), dtype=np.float32)          # every point of B is the target of ~125 points of A
@@ -68,13 +69,27 @@ def test_backward_is_bitwise_repeatable_and_covers_both_paths(f3d, oracle):
     gA, gB = oracle.chamfer_backward(A, Bc, nA, nB, 0.5, 2.0)
     assert np.allclose(grads[0][0].cpu().numpy(), gA, rtol=1e-4, atol=1e-10)
     assert np.allclose(grads[0][1].cpu().numpy(), gB, rtol=2e-4, atol=1e-10)
-    # beyond 8192 points per cloud: the two-launch path
-    A2 = rng.random((1, 9000, 3), dtype=np.float32)
-    B2 = rng.random((1, 300, 3), dtype=np.float32)
-    tA = torch.from_numpy(A2).cuda().requires_grad_(True)
-    tB = torch.from_numpy(B2).cuda().requires_grad_(True)
+    # several target slices per element (B = 1), segments of ~30 sources (selection in the segment); then beyond 24576 points
+    # per cloud: the two-launch path
+    for n2, m2, repeatable in ((9000, 300, True), (25000, 300, False)):
+        A2 = rng.random((1, n2, 3), dtype=np.float32)
+        B2 = rng.random((1, m2, 3), dtype=np.float32)
+        got = []
+        for _ in range(2):
+            tA = torch.from_numpy(A2).cuda().requires_grad_(True)
+            tB = torch.from_numpy(B2).cuda().requires_grad_(True)
+            f3d.chamfer_distance(tA, tB).backward()
+            got.append((tA.grad.clone(), tB.grad.clone()))
+        if repeatable:
+            assert torch.equal(got[0][0], got[1][0]) and torch.equal(got[0][1], got[1][1])
+        _, nA, nB, _ = oracle.chamfer_distance(A2, B2, return_all=True)
+        gA, gB = oracle.chamfer_backward(A2, B2, nA, nB)
+        assert np.allclose(got[0][0].cpu().numpy(), gA, rtol=1e-4, atol=1e-10)
+        assert np.allclose(got[0][1].cpu().numpy(), gB, rtol=2e-4, atol=1e-10)
+    # every point on one spot: one target takes every source (lowest index on ties)
+    P = torch.full((2, 700, 3), 0.5, device="cuda")
+    tA = (P + 0.0).requires_grad_(True)
+    tB = (P[:, :300] * 1.0 + 0.25).requires_grad_(True)
     f3d.chamfer_distance(tA, tB).backward()
-    _, nA, nB, _ = oracle.chamfer_distance(A2, B2, return_all=True)
-    gA, gB = oracle.chamfer_backward(A2, B2, nA, nB)
-    assert np.allclose(tA.grad.cpu().numpy(), gA, rtol=1e-4, atol=1e-10)
-    assert np.allclose(tB.grad.cpu().numpy(), gB, rtol=2e-4, atol=1e-10)
+    assert torch.isfinite(tA.grad).all() and torch.isfinite(tB.grad).all()
+    assert torch.allclose(tA.grad.sum(), -tB.grad.sum(), rtol=1e-4)   # the loss only depends on differences
