@@ -384,6 +384,10 @@ size_t knn_smem_bytes(int Fp, bool stage_block) { return sizeof(float) * (size_t
 // knn_tc.cu: the tensor-core (tcgen05) path for N <= 1024, F <= 64
 bool knn_tc_supported(int N, int F, int K);
 int32_t knn_tc_launch(const float* X, int B, int N, int F, int K, int32_t* idx, float* dist, float* gathered, float* edge, unsigned* stats, cudaStream_t stream);
+int32_t knn_emit_launch(const float* X, int B, int N, int F, int K, const int32_t* idx, float* gathered, float* edge, cudaStream_t stream);
+bool knn_gram_supported(int N, int F, int K);
+size_t knn_gram_workspace_bytes(int B, int N, int F);
+int32_t knn_gram_launch(const float* X, int B, int N, int F, int K, int32_t* idx, float* dist, void* ws, size_t ws_bytes, cudaStream_t stream);
 }  // namespace f3d
 
 
@@ -432,7 +436,11 @@ __global__ void __launch_bounds__(kEmitThreads) knn_edge_mlp_kernel(const float*
 }  // namespace
 }  // namespace f3d
 
-extern "C" size_t f3d_knn_graph_workspace_bytes(int32_t, int32_t, int32_t, int32_t) { return 256; }
+// Optional: without (enough of) it f3d_knn_graph stays on the kernels that need none (knn_tc.cu / the CUDA-core sweep)
+extern "C" size_t f3d_knn_graph_workspace_bytes(int32_t B, int32_t N, int32_t F, int32_t K) {
+    if (B > 0 && N > 0 && F > 0 && f3d::knn_gram_supported(N, F, K)) return f3d::knn_gram_workspace_bytes(B, N, F);
+    return 256;
+}
 
 extern "C" int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F, int32_t K, int32_t* idx,
                                  float* dist, float* gathered, float* edge_feat, void* ws, size_t ws_bytes,
@@ -460,6 +468,14 @@ extern "C" int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F
     // default for wide features (F >= 16, where evaluating the distances dominates): Gram matrix on the tensor cores
     // as a filter + exact re-evaluation (bit-identical results); narrow features are selection-bound and stay on the CUDA cores;
     // F3D_FLAG_EXACT_SWEEP or shapes outside that path: every pair in the reference arithmetic on the CUDA cores
+    // (first choice: the TMA-fed Gram filter of knn_gram.cu — point clouds (F <= 4, split-TF32 rows) and wide features — when
+    // the caller has brought its workspace)
+    if (!(flags & F3D_FLAG_EXACT_SWEEP) && (F <= 4 || F >= 16 || (flags & F3D_FLAG_TENSOR)) && knn_gram_supported(N, F, K) && ws &&
+        ws_bytes >= knn_gram_workspace_bytes(B, N, F)) {
+        const int32_t rc = knn_gram_launch(X, B, N, F, K, idx, dist, ws, ws_bytes, stream);
+        if (rc != F3D_OK) return rc;
+        return knn_emit_launch(X, B, N, F, K, idx, gathered, edge_feat, stream);
+    }
     if (!(flags & F3D_FLAG_EXACT_SWEEP) && (F >= 16 || (flags & F3D_FLAG_TENSOR)) && knn_tc_supported(N, F, K)) return knn_tc_launch(X, B, N, F, K, idx, dist, gathered, edge_feat, (ws && ws_bytes >= 8) ? static_cast<unsigned*>(ws) : nullptr, stream);
     KnnParams p;
     p.X = X; p.N = N; p.F = F; p.Fp = (F + 3) / 4 * 4; p.K = K;

@@ -494,6 +494,17 @@ __global__ void __launch_bounds__(256) knn_emit_kernel(const float* __restrict__
 // called from f3d_knn_graph (knn.cu); returns false if the shape is outside this path
 bool knn_tc_supported(int N, int F, int K) { return N <= kMaxTiles * kTN && F <= 64 && K + 1 <= 32 && N >= 2; }
 
+// gathered (F,K,N,B) / edge (2F,K,N,B) tensors from the neighbour indices (also used behind knn_gram.cu)
+int32_t knn_emit_launch(const float* X, int B, int N, int F, int K, const int32_t* idx, float* gathered, float* edge, cudaStream_t stream) {
+    if (gathered || edge) {
+        const bool v4 = (F & 3) == 0 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(gathered) | reinterpret_cast<uintptr_t>(edge)) & 15) == 0;
+        if (v4) knn_emit_kernel<4><<<(unsigned)(B * N), 256, 0, stream>>>(X, idx, N, F, K, gathered, edge);
+        else knn_emit_kernel<1><<<(unsigned)(B * N), 256, 0, stream>>>(X, idx, N, F, K, gathered, edge);
+        F3D_CHECK_LAUNCH("knn_emit_kernel");
+    }
+    return F3D_OK;
+}
+
 int32_t knn_tc_launch(const float* X, int B, int N, int F, int K, int32_t* idx, float* dist, float* gathered, float* edge, unsigned* stats, cudaStream_t stream) {
     KnnTcParams p;
     p.X = X; p.N = N; p.F = F; p.Kp = (F + 31) / 32 * 32; p.K = K; p.idx = idx; p.dist = dist; p.stats = stats;
@@ -506,13 +517,7 @@ int32_t knn_tc_launch(const float* X, int B, int N, int F, int K, int32_t* idx, 
     dim3 grid((N + kTQ - 1) / kTQ, B);
     knn_tc_kernel<<<grid, kTcThreads, smem, stream>>>(p);
     F3D_CHECK_LAUNCH("knn_tc_kernel");
-    if (gathered || edge) {
-        const bool v4 = (F & 3) == 0 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(gathered) | reinterpret_cast<uintptr_t>(edge)) & 15) == 0;
-        if (v4) knn_emit_kernel<4><<<(unsigned)(B * N), 256, 0, stream>>>(X, idx, N, F, K, gathered, edge);
-        else knn_emit_kernel<1><<<(unsigned)(B * N), 256, 0, stream>>>(X, idx, N, F, K, gathered, edge);
-        F3D_CHECK_LAUNCH("knn_emit_kernel");
-    }
-    return F3D_OK;
+    return knn_emit_launch(X, B, N, F, K, idx, gathered, edge, stream);
 }
 
 }  // namespace f3d

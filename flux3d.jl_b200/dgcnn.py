@@ -35,13 +35,17 @@ def knn_graph(X, K: int, *, want_dist: bool = False, want_gathered: bool = False
     edge = torch.empty((B, 2 * F, N, K) if mlp_layout else (B, N, K, 2 * F), dtype=torch.float32, device=dev) if want_edge else None
     if want_edge and mlp_layout:
         flags = int(flags) | FLAG_EDGE_MLP_LAYOUT
-    stats = torch.zeros(16, dtype=torch.int32, device=dev) if want_stats else None
     with torch.cuda.device(dev):
+        # the workspace holds the cloud's tensor-core operand image (knn_gram.cu); its first words are diagnostics
+        nws = int(L.f3d_knn_graph_workspace_bytes(B, N, F, K))
+        ws = _lib.workspace(("knn", B, N, F, K), nws, dev)
+        if want_stats:
+            ws[:64].zero_()
         _lib.check(L.f3d_knn_graph(_lib.ptr(X), B, N, F, K, _lib.ptr(idx), _lib.ptr(dist), _lib.ptr(gat), _lib.ptr(edge),
-                                   _lib.ptr(stats), 64 if want_stats else 0, int(flags), _lib.stream_ptr(dev)))
+                                   _lib.ptr(ws), nws, int(flags), _lib.stream_ptr(dev)))
     out = {"idx": idx}
     if want_stats:
-        out["stats"] = stats  # [queries that fell back to an exact scan, candidates re-evaluated exactly]
+        out["stats"] = ws[:64].view(torch.int32).clone()  # [queries that fell back to an exact scan, candidates re-evaluated exactly]
     if want_dist:
         out["dist"] = dist
     if want_gathered:

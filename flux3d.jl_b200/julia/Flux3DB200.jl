@@ -146,9 +146,12 @@ function knn_graph(X::CuArray{Float32,3}, K::Int; gathered = false, edge = false
     # edge features: (2F, K, N, B) == cat(X, KNNGraph - X; dims=1) (:45), or — mlp_layout — already permuted and reshaped to
     # the (K*N, 2F, B) array the Conv1x1 MLP consumes (:46-52): C [B][2F][N][K]
     E = edge ? (mlp_layout ? CuArray{Float32}(undef, K * N, 2F, Bn) : CuArray{Float32}(undef, 2F, K, N, Bn)) : nothing
+    # the workspace takes the cloud's tensor-core operand image (knn_gram.cu); without it the library stays on slower kernels
+    nbytes = ccall((:f3d_knn_graph_workspace_bytes, LIB), Csize_t, (Int32, Int32, Int32, Int32), Bn, N, F, K)
+    ws = workspace((:knn, Bn, N, F, K), nbytes)
     check(ccall((:f3d_knn_graph, LIB), Int32,
         (Ptr{Float32}, Int32, Int32, Int32, Int32, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Cvoid}, Csize_t, Int32, Ptr{Cvoid}),
-        devptr(X), Bn, N, F, K, devptr(idx), C_NULL, gathered ? devptr(G) : C_NULL, edge ? devptr(E) : C_NULL, C_NULL, 0,
+        devptr(X), Bn, N, F, K, devptr(idx), C_NULL, gathered ? devptr(G) : C_NULL, edge ? devptr(E) : C_NULL, devptr(ws), nbytes,
         (edge && mlp_layout) ? FLAG_EDGE_MLP_LAYOUT : Int32(0), cur_stream()))
     return idx, G, E
 end

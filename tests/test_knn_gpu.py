@@ -155,3 +155,39 @@ def test_knn_tensor_path_zero_norm_queries(f3d, oracle):
     for flags in (0, f3d.FLAG_TENSOR):
         out = f3d.knn_graph(torch.from_numpy(X).cuda(), K, want_dist=True, flags=flags)
         assert np.array_equal(out["idx"].cpu().numpy(), oracle.knn_graph(X, K))
+
+
+@pytest.mark.parametrize("B,N,F,K", [
+    (3, 1024, 3, 20), (2, 1000, 1, 8), (2, 777, 2, 12), (2, 2048, 4, 31), (2, 1300, 3, 20),     # split-TF32 rows (F <= 4), fine / coarse chunks
+    (2, 1024, 64, 20), (2, 900, 33, 16), (1, 2048, 16, 31), (2, 520, 7, 9), (2, 1500, 40, 25),  # plain rows, one and two 32-feature halves
+])
+def test_knn_gram_path(f3d, oracle, B, N, F, K):
+    """knn_gram.cu (TMA-fed Gram filter, exact re-evaluation out of the operand tiles): parity with the oracle, and the
+    diagnostics prove that this path served the call, that (almost) no row fell back to the exact scan and that the filter
+    passed close to K + 1 candidates per query."""
+    rng = np.random.default_rng(900 + N + F + K)
+    X = rng.standard_normal((B, N, F)).astype(np.float32)
+    out = f3d.knn_graph(torch.from_numpy(X).cuda(), K, want_dist=True, want_stats=True, flags=8)
+    idx, dist = oracle.knn_graph(X, K, want_dist=True)
+    assert np.array_equal(out["idx"].cpu().numpy(), idx)
+    assert np.array_equal(out["dist"].cpu().numpy(), dist)
+    st = out["stats"].cpu().numpy()
+    assert st[7] == 2, st
+    assert st[0] <= B * N // 100, st
+    assert (K + 1) * B * N <= st[1] <= 3 * (K + 1) * B * N, st
+
+
+def test_knn_gram_degenerate_inputs(f3d, oracle):
+    """Heavy ties and clustered clouds overflow the candidate slots: those rows are redone by the exact scan (fixup kernel);
+    zero rows and huge offsets must not be certified wrongly."""
+    rng = np.random.default_rng(77)
+    lattice = rng.integers(0, 4, size=(2, 1100, 3)).astype(np.float32)                    # ~17 copies of every point
+    clustered = (rng.integers(0, 3, (2, 1200, 1)) * 50.0 + rng.standard_normal((2, 1200, 64)) * 0.01).astype(np.float32)
+    zeros = np.zeros((1, 1024, 3), np.float32)
+    far = (rng.standard_normal((2, 1024, 3)) + 1000.0).astype(np.float32)
+    for X, K in ((lattice, 20), (clustered, 16), (zeros, 5), (far, 20)):
+        out = f3d.knn_graph(torch.from_numpy(X).cuda(), K, want_dist=True, want_stats=True, flags=8)
+        idx, dist = oracle.knn_graph(X, K, want_dist=True)
+        assert out["stats"].cpu().numpy()[7] == 2
+        assert np.array_equal(out["idx"].cpu().numpy(), idx)
+        assert np.array_equal(out["dist"].cpu().numpy(), dist)

@@ -46,15 +46,18 @@ l1 = f3d.chamfer_forward_host(pA, pB, to_host=True, flags=f3d.FLAG_TENSOR)
 l2 = f3d.chamfer_forward_host(hA, hB, flags=f3d.FLAG_TENSOR)
 torch.cuda.synchronize()
 assert abs(l0.item() - l1.item()) <= 1e-6 * l0.item() and l2.item() == l1.item()
-# chamfer backward: sorted gather and (beyond 8192 points) the RED.ADD path
-for (B, N, M) in ((2, 500, 70), (1, 8300, 64)):
+# chamfer backward: counting-sort gather (also a target with > 32 sources) and (beyond 24576 points) the RED.ADD path
+for (B, N, M) in ((2, 500, 70), (1, 2100, 40), (1, 24600, 64)):
     tA, tB = cloud(B, N, 3).requires_grad_(True), cloud(B, M, 3).requires_grad_(True)
     f3d.chamfer_distance(tA, tB).backward()
 # kNN graph: CUDA-core kernel (narrow / wide), tensor-core kernel, gathered / edge outputs, MLP layout, gradient
-for (B, N, F, K, fl) in ((2, 200, 3, 10, 0), (1, 300, 20, 33, 0), (2, 256, 64, 20, 0), (1, 130, 3, 5, f3d.FLAG_TENSOR)):
+# knn_gram (TMA-fed Gram filter: split rows F <= 4, plain rows; its prepare / fixup kernels: the lattice cloud overflows the slots)
+for (B, N, F, K, fl) in ((2, 200, 3, 10, 0), (1, 300, 20, 33, 0), (2, 256, 64, 20, 0), (1, 130, 3, 5, f3d.FLAG_TENSOR), (2, 600, 3, 10, 0), (1, 520, 40, 9, 0)):
     X = torch.from_numpy(rng.standard_normal((B, N, F)).astype(np.float32)).cuda()
     f3d.knn_graph(X, K, want_dist=True, want_gathered=True, want_edge=True, flags=fl)
     f3d.knn_graph(X, K, want_edge=True, mlp_layout=True, flags=fl)
+Xl = torch.from_numpy(rng.integers(0, 3, size=(1, 600, 3)).astype(np.float32)).cuda()
+assert int(f3d.knn_graph(Xl, 10, want_stats=True)["stats"][7]) == 2
 Xg = torch.randn(1, 150, 6, device="cuda", requires_grad=True)
 f3d.edgeconv_features(Xg, 7, mlp_layout=True).sum().backward()
 # mesh kernels on the reference's teapot fixture
