@@ -251,6 +251,26 @@ def ops_block(steps, flush, pk):
            cpu_time(lambda: O.verts_normals(vpk, fpk, 0)), "oracle, 1 thread")
     us = timed(lambda: f3d.edge_loss(m))
     report("edge_loss cfg4", nE, "edges", us, nV * 12 + nE * 8 + 4)
+    # the fit_mesh step (examples/fit_mesh.jl:78-84) — two sample_points, chamfer distance, laplacian_loss, edge_loss, forward AND
+    # pullbacks — called op by op, and captured once and replayed as ONE CUDA-graph launch (flux3d_b200.capture_step)
+    m2 = f3d.TriMesh([v * np.float32(1.05) for v in vl], fl)
+    delta = torch.zeros((nV, 3), device="cuda", requires_grad=True)
+    delta.grad = torch.zeros_like(delta)
+    c1 = torch.zeros(1, dtype=torch.int64, device="cuda")
+    c2 = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def train_step():
+        delta.grad.zero_()
+        md = f3d.offset(m, delta)
+        a = f3d.sample_points(md, 10000, seed=1, counter=c1)
+        b = f3d.sample_points(m2, 10000, seed=2, counter=c2)
+        loss = f3d.chamfer_distance(a, b) + 0.1 * f3d.laplacian_loss(md) + f3d.edge_loss(md)
+        loss.backward()
+        return loss
+    us_eager = timed(train_step)
+    us = timed(f3d.capture_step(train_step))
+    report("fit_mesh step cfg4 (forward + pullbacks), one CUDA-graph launch", 16 * 10000 * 10000, "pairs", us, 2 * (nV * 12 + nF * 12 + 160000 * 12) + 4 * 160000 * 12)
+    out[-1]["op_by_op_us_per_call"] = round(us_eager, 2)
     A = torch.rand((32, 4096, 3), device="cuda")
     Bc = torch.rand((32, 4096, 3), device="cuda")
     _, _, nnA, nnB = f3d.chamfer_forward_raw(A, Bc, 1.0, 1.0)

@@ -17,8 +17,9 @@ from .mesh import (NORMALS_ACCUMULATE, NORMALS_REFERENCE_CPU, TriMesh, compute_f
 from .sampling import sample_points
 from .dgcnn import create_single_knn_graph, edgeconv_features, knn_graph
 from .distributed import Communicator, allreduce_loss_, chamfer_distance_sharded, shard_range
+from .graph import CapturedStep, capture_step
 
-__all__ = ["PointCloud", "TriMesh", "chamfer_distance", "chamfer_forward_raw", "chamfer_forward_host", "nearest_neighbors", "laplacian_loss",
+__all__ = ["CapturedStep", "capture_step", "PointCloud", "TriMesh", "chamfer_distance", "chamfer_forward_raw", "chamfer_forward_host", "nearest_neighbors", "laplacian_loss",
            "edge_loss", "sample_points", "knn_graph", "create_single_knn_graph", "edgeconv_features",
            "compute_verts_normals_packed", "compute_faces_normals_packed", "compute_faces_areas_packed",
            "get_verts_packed", "get_edges_packed", "get_laplacian_packed", "load_trimesh", "offset", "packed_to_padded",

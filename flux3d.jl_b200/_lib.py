@@ -46,6 +46,9 @@ SIGNATURES = {
     "f3d_sample_points": (C.c_int32, [_f32p, _i32p, _i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_double, C.c_uint64, C.c_uint64, _i32p, _f32p, _f32p, _f32p, _i32p, _f32p,
                                       _vp, C.c_size_t, _vp]),
+    "f3d_sample_points_replayable": (C.c_int32, [_f32p, _i32p, _i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                 C.c_double, C.c_uint64, C.c_uint64, _vp, _i32p, _f32p, _f32p, _f32p, _i32p, _f32p,
+                                                 _vp, C.c_size_t, _vp]),
     "f3d_sample_points_bwd": (C.c_int32, [_f32p, _i32p, _f32p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _vp]),
     "f3d_edge_loss_bwd": (C.c_int32, [_f32p, _i32p, _i32p, C.c_int32, C.c_int32, C.c_float, _f32p, _f32p, _vp]),
     "f3d_comm_unique_id_host": (C.c_int32, [_vp]),

@@ -95,9 +95,13 @@ __global__ void __launch_bounds__(kGT) chamfer_bwd_gather_kernel(BwdParams p) {
     for (int i = tid; i <= nt; i += kGT) cnt[i] = 0;
     if (tid == 0) s_nheavy = 0;
     __syncthreads();
-    for (int j = tid; j < nS; j += kGT) {
-        const unsigned t = (unsigned)(__ldg(nnS + j) - t0);
-        if (t < (unsigned)nt) atomicAdd(&cnt[t], 1);
+    for (int j0 = tid; j0 < nS; j0 += 4 * kGT) {   // four loads in flight per thread, then their atomics
+        unsigned t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = j0 + k * kGT < nS ? (unsigned)(__ldg(nnS + j0 + k * kGT) - t0) : 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (t[k] < (unsigned)nt) atomicAdd(&cnt[t[k]], 1);
     }
     __syncthreads();
     // exclusive scan of cnt[0 .. nt): thread <-> a contiguous run of `per` targets
@@ -128,9 +132,13 @@ __global__ void __launch_bounds__(kGT) chamfer_bwd_gather_kernel(BwdParams p) {
     }
     __syncthreads();
     // every source into its target's segment; afterwards cnt[t] = end of segment t = start of segment t + 1
-    for (int j = tid; j < nS; j += kGT) {
-        const unsigned t = (unsigned)(__ldg(nnS + j) - t0);
-        if (t < (unsigned)nt) list[atomicAdd(&cnt[t], 1)] = j;
+    for (int j0 = tid; j0 < nS; j0 += 4 * kGT) {
+        unsigned t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = j0 + k * kGT < nS ? (unsigned)(__ldg(nnS + j0 + k * kGT) - t0) : 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (t[k] < (unsigned)nt) list[atomicAdd(&cnt[t[k]], 1)] = j0 + k * kGT;
     }
     __syncthreads();
     for (int i = tid; i < nt; i += kGT) {

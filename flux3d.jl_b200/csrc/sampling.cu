@@ -44,6 +44,7 @@ struct SampleParams {
     int Vmax, Fmax, S;
     double eps;
     unsigned long long seed, offset;
+    const unsigned long long* offset_dev;   // optional: added to `offset` at run time (a captured graph draws afresh at every replay)
     const int32_t* inj_face;
     const float* inj_r1;
     const float* inj_r2;
@@ -131,7 +132,8 @@ __device__ __forceinline__ void draw_and_emit(const SampleParams& p, int mesh, i
         r1 = __ldg(p.inj_r1 + o);
         r2 = __ldg(p.inj_r2 + o);
     } else {
-        unsigned c[4] = {(unsigned)s, (unsigned)mesh, (unsigned)p.offset, (unsigned)(p.offset >> 32)};
+        const unsigned long long off = p.offset + (p.offset_dev ? __ldg(p.offset_dev) : 0ull);
+        unsigned c[4] = {(unsigned)s, (unsigned)mesh, (unsigned)off, (unsigned)(off >> 32)};
         philox4x32_10(c, (unsigned)p.seed, (unsigned)(p.seed >> 32));
         const unsigned long long m = (((unsigned long long)c[0] << 32) | c[1]) >> 11;  // 53-bit uniform
         r1 = (float)(c[2] >> 8) * (1.0f / 16777216.0f);
@@ -227,11 +229,27 @@ extern "C" size_t f3d_sample_points_workspace_bytes(int32_t Nmesh, int32_t Fmax)
     return align_up(sizeof(unsigned long long) * (size_t)Nmesh * Fmax, 256);
 }
 
+namespace f3d {
+namespace {
+__global__ void sample_counter_bump_kernel(unsigned long long* ctr) { *ctr += 1ull; }
+}  // namespace
+}  // namespace f3d
+
 extern "C" int32_t f3d_sample_points(const float* verts_padded, const int32_t* faces_padded, const int32_t* verts_len,
                                      const int32_t* faces_len, int32_t Nmesh, int32_t Vmax, int32_t Fmax, int32_t S,
                                      double eps, uint64_t seed, uint64_t offset, const int32_t* inj_face,
                                      const float* inj_r1, const float* inj_r2, float* samples, int32_t* face_idx_out,
                                      float* bary_out, void* ws, size_t ws_bytes, f3d_stream_t stream_) {
+    return f3d_sample_points_replayable(verts_padded, faces_padded, verts_len, faces_len, Nmesh, Vmax, Fmax, S, eps, seed, offset, nullptr,
+                                        inj_face, inj_r1, inj_r2, samples, face_idx_out, bary_out, ws, ws_bytes, stream_);
+}
+
+extern "C" int32_t f3d_sample_points_replayable(const float* verts_padded, const int32_t* faces_padded, const int32_t* verts_len,
+                                                const int32_t* faces_len, int32_t Nmesh, int32_t Vmax, int32_t Fmax, int32_t S,
+                                                double eps, uint64_t seed, uint64_t offset, uint64_t* offset_dev,
+                                                const int32_t* inj_face, const float* inj_r1, const float* inj_r2, float* samples,
+                                                int32_t* face_idx_out, float* bary_out, void* ws, size_t ws_bytes, f3d_stream_t stream_) {
+    using namespace f3d;
     (void)verts_len;  // faces only reference valid vertices; kept in the ABI to mirror verts[:, 1:_verts_len[i], i] (:52)
     if (!verts_padded || !faces_padded || !faces_len || !samples) return fail(F3D_ERR_INVALID, "f3d_sample_points: null pointer");
     if (Nmesh <= 0 || Vmax <= 0 || Fmax <= 0 || S <= 0) return fail(F3D_ERR_INVALID, "f3d_sample_points: Nmesh, Vmax, Fmax, S must be positive (got %d, %d, %d, %d)", Nmesh, Vmax, Fmax, S);
@@ -241,7 +259,7 @@ extern "C" int32_t f3d_sample_points(const float* verts_padded, const int32_t* f
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SampleParams p;
     p.verts = verts_padded; p.faces = faces_padded; p.faces_len = faces_len;
-    p.Vmax = Vmax; p.Fmax = Fmax; p.S = S; p.eps = eps; p.seed = seed; p.offset = offset;
+    p.Vmax = Vmax; p.Fmax = Fmax; p.S = S; p.eps = eps; p.seed = seed; p.offset = offset; p.offset_dev = reinterpret_cast<const unsigned long long*>(offset_dev);
     p.inj_face = inj_face; p.inj_r1 = inj_r1; p.inj_r2 = inj_r2;
     p.samples = samples; p.face_idx_out = face_idx_out; p.bary_out = bary_out; p.cdf_ws = nullptr;
     // one sample per thread: the draw path is a chain of dependent loads (CDF search -> face ids -> vertices), so
@@ -263,6 +281,10 @@ extern "C" int32_t f3d_sample_points(const float* verts_padded, const int32_t* f
         F3D_CHECK_LAUNCH("sample_points_cdf_kernel");
         sample_points_draw_kernel<<<dim3(chunks, Nmesh), kST, 0, stream>>>(p);
         F3D_CHECK_LAUNCH("sample_points_draw_kernel");
+    }
+    if (offset_dev && !inj) {   // the next launch (or the next replay of a captured graph) draws from a fresh counter block
+        sample_counter_bump_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<unsigned long long*>(offset_dev));
+        F3D_CHECK_LAUNCH("sample_counter_bump_kernel");
     }
     return F3D_OK;
 }

@@ -14,7 +14,7 @@ from .mesh import TriMesh
 EPS = 1e-6  # src/transforms/utils.jl:4
 
 
-def _launch(m, verts, num_samples, eps, seed, offset, inj, want_faces, want_bary):
+def _launch(m, verts, num_samples, eps, seed, offset, inj, want_faces, want_bary, counter=None):
     L = _lib.lib()
     dev = m.device
     faces = m.faces_padded_device()
@@ -25,11 +25,11 @@ def _launch(m, verts, num_samples, eps, seed, offset, inj, want_faces, want_bary
     with torch.cuda.device(dev):
         nws = L.f3d_sample_points_workspace_bytes(m.N, m.F)
         ws = _lib.workspace(("sample", m.N, m.F), nws, dev) if nws else None
-        _lib.check(L.f3d_sample_points(_lib.ptr(verts), _lib.ptr(faces), _lib.ptr(m.verts_len_device()),
-                                       _lib.ptr(m.faces_len_device()), m.N, m.V, m.F, num_samples, float(eps),
-                                       int(seed), int(offset), _lib.ptr(inj_face), _lib.ptr(inj_r1), _lib.ptr(inj_r2),
-                                       _lib.ptr(out), _lib.ptr(fidx), _lib.ptr(bary), _lib.ptr(ws),
-                                       ws.numel() if ws is not None else 0, _lib.stream_ptr(dev)))
+        _lib.check(L.f3d_sample_points_replayable(_lib.ptr(verts), _lib.ptr(faces), _lib.ptr(m.verts_len_device()),
+                                                  _lib.ptr(m.faces_len_device()), m.N, m.V, m.F, num_samples, float(eps),
+                                                  int(seed), int(offset), _lib.ptr(counter), _lib.ptr(inj_face), _lib.ptr(inj_r1),
+                                                  _lib.ptr(inj_r2), _lib.ptr(out), _lib.ptr(fidx), _lib.ptr(bary), _lib.ptr(ws),
+                                                  ws.numel() if ws is not None else 0, _lib.stream_ptr(dev)))
     return out, fidx, bary
 
 
@@ -37,8 +37,8 @@ class _SampleFn(torch.autograd.Function):
     """Differentiable w.r.t. the (padded) vertices; the face draws are constants (mesh_func.jl:47 is @ignore)."""
 
     @staticmethod
-    def forward(ctx, verts_padded, m, num_samples, eps, seed, offset, inj):
-        out, fidx, bary = _launch(m, verts_padded, num_samples, eps, seed, offset, inj, True, True)
+    def forward(ctx, verts_padded, m, num_samples, eps, seed, offset, inj, counter=None):
+        out, fidx, bary = _launch(m, verts_padded, num_samples, eps, seed, offset, inj, True, True, counter)
         ctx.save_for_backward(fidx, bary)
         ctx.m, ctx.S = m, num_samples
         ctx.mark_non_differentiable(fidx)
@@ -53,15 +53,16 @@ class _SampleFn(torch.autograd.Function):
         with torch.cuda.device(m.device):
             _lib.check(L.f3d_sample_points_bwd(_lib.ptr(g), _lib.ptr(fidx), _lib.ptr(bary), _lib.ptr(m.faces_padded_device()),
                                                m.N, m.V, m.F, ctx.S, _lib.ptr(gv), _lib.stream_ptr(m.device)))
-        return gv, None, None, None, None, None, None
+        return gv, None, None, None, None, None, None, None
 
 
 def sample_points(m: TriMesh, num_samples: int = 5000, *, eps: float = EPS, seed=None, offset: int = 0,
-                  inj_face=None, inj_r1=None, inj_r2=None, return_faces: bool = False):
+                  inj_face=None, inj_r1=None, inj_r2=None, return_faces: bool = False, counter=None):
     """sample_points(m, num_samples=5000; eps=1e-6) → (N, num_samples, 3) float32 device tensor
     (== Julia (3, num_samples, N)), differentiable w.r.t. the mesh vertices.  inj_face/inj_r1/inj_r2 ((N, S)
     int32 / float32 / float32 device tensors) inject the draws (bit-parity mode); return_faces also returns the
-    sampled face ids (N, S)."""
+    sampled face ids (N, S).  counter: a 1-element int64 device tensor added to ``offset`` on the device and incremented after the
+    draws — inside a captured CUDA graph (graph.capture_step) every replay then draws fresh samples."""
     if num_samples <= 0:
         raise ValueError("num_samples must be positive")
     dev = m.device
@@ -76,7 +77,7 @@ def sample_points(m: TriMesh, num_samples: int = 5000, *, eps: float = EPS, seed
     inj = (inj_face, inj_r1, inj_r2)
     verts = m.get_verts_padded()
     if torch.is_grad_enabled() and verts.requires_grad:
-        out, fidx = _SampleFn.apply(verts.contiguous(), m, num_samples, eps, seed, offset, inj)
+        out, fidx = _SampleFn.apply(verts.contiguous(), m, num_samples, eps, seed, offset, inj, counter)
     else:
-        out, fidx, _ = _launch(m, verts.detach().contiguous(), num_samples, eps, seed, offset, inj, return_faces, False)
+        out, fidx, _ = _launch(m, verts.detach().contiguous(), num_samples, eps, seed, offset, inj, return_faces, False, counter)
     return (out, fidx) if return_faces else out

@@ -238,6 +238,17 @@ F3D_API int32_t f3d_sample_points(const float* verts_padded, const int32_t* face
                           uint64_t offset, const int32_t* inj_face, const float* inj_r1,
                           const float* inj_r2, float* samples, int32_t* face_idx_out, float* bary_out,
                           void* ws, size_t ws_bytes, f3d_stream_t stream);
+/* f3d_sample_points with a run-time draw counter, for CUDA-graph capture (fit_mesh draws fresh samples every iteration,
+ * examples/fit_mesh.jl:78-84; a captured launch would otherwise repeat the draws baked into its parameters):
+ *   offset_dev (device, one 64-bit word; NULL = f3d_sample_points): its value is ADDED to `offset` when the kernel runs, and it is
+ *   incremented by one after the draws (stream-ordered), so every replay of a graph that contains this call uses a new block of
+ *   Philox counters.  Ignored in the injected-draw mode. */
+F3D_API int32_t f3d_sample_points_replayable(const float* verts_padded, const int32_t* faces_padded,
+                          const int32_t* verts_len, const int32_t* faces_len, int32_t Nmesh,
+                          int32_t Vmax, int32_t Fmax, int32_t S, double eps, uint64_t seed,
+                          uint64_t offset, uint64_t* offset_dev, const int32_t* inj_face, const float* inj_r1,
+                          const float* inj_r2, float* samples, int32_t* face_idx_out, float* bary_out,
+                          void* ws, size_t ws_bytes, f3d_stream_t stream);
 /* Pullback of _sample_points (src/transforms/mesh_func.jl:60-73; the face draws are constants, :47 is @ignore):
  *   gverts_padded[mesh][faces[face][k]] += w_k * gsamples[mesh][s]   for the three corners k of every sample.
  * gverts_padded [Nmesh][Vmax][3] is ACCUMULATED into (zero it first); float RED.ADD, so the summation order —

@@ -21,7 +21,7 @@ def _c_class(ctype):
     t = ctype.replace("const", " ").strip()
     t = re.sub(r"\s+", " ", t).replace(" *", "*")
     table = {"int32_t": "i32", "uint32_t": "u32", "uint64_t": "u64", "size_t": "size", "float": "f32", "double": "f64",
-             "float*": "ptr:f32", "int32_t*": "ptr:i32", "void*": "ptr:void", "char*": "ptr:char", "void**": "ptr:ptr",
+             "float*": "ptr:f32", "int32_t*": "ptr:i32", "uint64_t*": "ptr:u64", "void*": "ptr:void", "char*": "ptr:char", "void**": "ptr:ptr",
              "f3d_stream_t": "ptr:void"}
     assert t in table, f"unknown C type {ctype!r}"
     return table[t]
@@ -74,7 +74,7 @@ def _balanced(src, start):
 
 JL = {"Int32": "i32", "UInt32": "u32", "UInt64": "u64", "Csize_t": "size", "Float32": "f32", "Float64": "f64",
       "Ptr{Float32}": "ptr:f32", "Ptr{Int32}": "ptr:i32", "Ptr{Cvoid}": "ptr:void", "Ptr{UInt8}": "ptr:char",
-      "Ptr{Ptr{Cvoid}}": "ptr:ptr"}
+      "Ptr{Ptr{Cvoid}}": "ptr:ptr", "Ptr{UInt64}": "ptr:u64"}
 
 
 def shim_ccalls():
@@ -108,7 +108,7 @@ def _compatible(jl, c):
 
 def test_every_ccall_matches_the_header():
     protos = header_prototypes()
-    assert len(protos) >= 31
+    assert len(protos) >= 32
     calls = shim_ccalls()
     assert len(calls) >= 20
     for name, ret, types, nargs, line in calls:
@@ -133,7 +133,7 @@ def test_shim_binds_what_the_integration_table_lists():
     protos = header_prototypes()
     assert listed <= set(protos), f"INTEGRATION.md names symbols the header does not declare: {sorted(listed - set(protos))}"
     julia_side = listed - {"f3d_version", "f3d_comm_unique_id_host", "f3d_allreduce_sum_f32", "f3d_comm_destroy", "f3d_chamfer_pipe_destroy",
-                           "f3d_knn_graph_workspace_bytes"}
+                           "f3d_sample_points_replayable"}
     assert julia_side <= bound, f"INTEGRATION.md lists bindings the shim does not make: {sorted(julia_side - bound)}"
     for needle in ("Flux3D._chamfer_distance(A::CuArray", "Zygote.@adjoint function Flux3D._chamfer_distance", "Flux3D._nearest_neighbors(x::CuArray",
                    "Flux3D.CreateSingleKNNGraph(X::CuArray", "(m::Flux3D.EdgeConv)(X::CuArray", "Flux3D.laplacian_loss(m::TriMesh{Float32,R,CuArray})",

@@ -129,6 +129,26 @@ def main():
     report("fit_mesh objective forward cfg4 (2x sample_points + chamfer S=10000 + laplacian + edge)", 16 * 10000 * 10000, "pairs", us,
            2 * (nV * 12 + nF * 12 + 160000 * 12) + 2 * 160000 * 12)
 
+    # the whole fit_mesh step — forward AND pullbacks — eager and as ONE CUDA-graph launch (flux3d_b200.capture_step)
+    nVt = sum(len(v) for v in vl)
+    delta = torch.zeros((nVt, 3), device="cuda", requires_grad=True)
+    delta.grad = torch.zeros_like(delta)
+    c1 = torch.zeros(1, dtype=torch.int64, device="cuda"); c2 = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def train_step():
+        delta.grad.zero_()
+        md = f3d.offset(m, delta)
+        a = f3d.sample_points(md, 10000, seed=1, counter=c1)
+        b = f3d.sample_points(m2, 10000, seed=2, counter=c2)
+        loss = f3d.chamfer_distance(a, b) + 0.1 * f3d.laplacian_loss(md) + f3d.edge_loss(md)
+        loss.backward()
+        return loss
+    us_eager = timed(train_step, args.steps, flush)
+    graphed = f3d.capture_step(train_step)
+    us_graph = timed(graphed, args.steps, flush)
+    report("fit_mesh step cfg4, forward + pullbacks, ONE CUDA-graph launch", 16 * 10000 * 10000, "pairs", us_graph,
+           2 * (nV * 12 + nF * 12 + 160000 * 12) + 2 * 160000 * 12, extra={"eager_us_per_call": us_eager})
+
     # ---- chamfer backward at cfg2 --------------------------------------------------------------------------
     A = torch.rand((32, 4096, 3), device="cuda")
     Bc = torch.rand((32, 4096, 3), device="cuda")

@@ -9,7 +9,7 @@ for spec in "$@"; do
   name="${spec%%:*}"; defs="${spec#*:}"
   d=$(mktemp -d)
   for f in capi chamfer chamfer_tc chamfer_pipe chamfer_bwd knn knn_tc knn_gram mesh sampling comm; do
-    if [ "$f" = chamfer ] || [ "$f" = chamfer_tc ] || [ "$f" = knn ] || [ "$f" = knn_tc ] || [ "$f" = knn_gram ]; then
+    if [ "$f" = chamfer ] || [ "$f" = chamfer_bwd ] || [ "$f" = chamfer_tc ] || [ "$f" = knn ] || [ "$f" = knn_tc ] || [ "$f" = knn_gram ]; then
       /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-fvisibility=hidden -I../../include $defs -c -o $d/$f.o $f.cu &
     else
       cp $f.o $d/$f.o
