@@ -1329,7 +1329,8 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
 
     // ---- default for problems that fill the machine: the filter sweep on the tensor cores (chamfer_tc.cu) --------------
     // (F3D_FLAG_TENSOR forces it for any shape: tests drive small and ragged shapes through it that way)
-    if (!fma && !(flags & (F3D_FLAG_EXACT_SWEEP | F3D_FLAG_CUDA_CORES)) && ((flags & F3D_FLAG_TENSOR) ? chamfer_tc_possible(B, N, M) : chamfer_tc_supported(B, N, M)))
+    if (!fma && !(flags & (F3D_FLAG_EXACT_SWEEP | F3D_FLAG_CUDA_CORES)) && (!upload || chamfer_tc_upload_possible(N, M)) &&
+        ((flags & F3D_FLAG_TENSOR) ? chamfer_tc_possible(B, N, M) : chamfer_tc_supported(B, N, M)))
         return chamfer_tc_launch(A, Bp, B, N, M, w1, w2, B_total, loss_dev, terms_dev, nnA_dev, nnB_dev, ws, ws_bytes, flags, stream, upload, peer);
 
     if (!fma && !(flags & F3D_FLAG_EXACT_SWEEP)) {

@@ -2,19 +2,19 @@
 //
 // The reference's array entry points (src/metrics/pcloud.jl:28-37) take host `Array`s and return a host Float32.  A
 // drop-in that uploads 12·B·(N+M) bytes, then launches, then reads the scalar back pays the copy and two host round
-// trips in full (cfg2: 3.1 MB ≈ 67 µs of PCIe + ≈ 30 µs for the read-back, against a ≈ 160 µs sweep).  Here
-//   * ONE grid is launched: its first CTAs pull the clouds out of page-locked host memory themselves (16-byte loads over
-//     PCIe, batch element by batch element, into a staging copy in HBM) and count every element as it lands; the other
-//     CTAs sweep, each waiting only for its own batch element.  The host issues a memset and a launch — no per-chunk
-//     copy calls (≈ 3.5 µs of host time each, which made a chunked cudaMemcpyAsync pipeline slower than plain copies).
-//     Same kernel, same arithmetic, same bits as f3d_chamfer_fwd on resident inputs.
+// trips in full (cfg2: 3.1 MB ≈ 60 µs of PCIe + ≈ 30 µs for the read-back, on top of the sweep).  Here
+//   * ONE grid is launched and it uploads for itself.  Tensor-core sweep (problems large enough for it): the two spare warps of
+//     every sweep CTA pull the clouds out of page-locked host memory (16-byte loads over PCIe, batch element by batch element,
+//     into a staging copy in HBM) and count every element as it lands; the producer waits per element and streams the raw
+//     points, the converters centre them and take the norms on the fly — no prepare grid, no copy call, no SM taken from the
+//     sweep.  CUDA-core sweep (small problems, F3D_FLAG_CUDA_CORES): the grid's first CTAs upload while the others sweep.
 //   * the loss is stored by the grid straight into page-locked, device-mapped host memory and the host spins on that
 //     word (falling back to the stream's status): no D2H copy, no driver synchronisation on the critical path.
-// Host arrays the device cannot address (pageable memory) or that are not 16-byte aligned take the plain route: two
-// cudaMemcpyAsync on the caller's stream, then the same grid on resident inputs.
+// Host arrays the device cannot address (pageable memory) take the plain route: two cudaMemcpyAsync on the caller's stream,
+// then the same kernels on resident inputs.  Same arithmetic, same bits as f3d_chamfer_fwd in every case.
 //
-// The handle owns 64 bytes of mapped host memory (created once, off the hot path); every device byte — the staging
-// copies of the clouds, the sweep workspace — lives in the caller's workspace.
+// The handle owns 64 bytes of mapped host memory (created once, off the hot path); every device
+// byte — the staging copies of the clouds, the sweep workspace — lives in the caller's workspace.
 #include <algorithm>
 #include <cstring>
 
@@ -94,6 +94,8 @@ extern "C" int32_t f3d_chamfer_pipe_run(void* pipe, const float* A_host, const f
     if (B <= 0 || N <= 0 || M <= 0) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: B, N, M must be positive (got %d, %d, %d)", B, N, M);
     if (B > 65535) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: B must be <= 65535 per call");
     if (flags & F3D_FLAG_SWEEP_ONLY) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: F3D_FLAG_SWEEP_ONLY is a single-call measurement aid");
+    if (B_total == 0) B_total = B;
+    if (B_total < B) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: B_total (%d) < B (%d)", B_total, B);
     Pipe* h = static_cast<Pipe*>(pipe);
     const PipePlan pl = make_pipe_plan(B, N, M);
     if (!ws || ws_bytes < pl.total) return fail(F3D_ERR_WORKSPACE, "f3d_chamfer_pipe_run: workspace %zu < required %zu bytes", ws_bytes, pl.total);
@@ -109,7 +111,15 @@ extern "C" int32_t f3d_chamfer_pipe_run(void* pipe, const float* A_host, const f
     float* target = loss_host ? reinterpret_cast<float*>(h->host_dev) : loss_dev;
     if (loss_host) reinterpret_cast<volatile uint32_t*>(h->host)[0] = kSentinel;
 
-    // the in-grid upload exists for the default (filtered) sweep on host memory the device can read in place
+    // sharded batch: the loss is summed over the ranks inside the step's last kernel (peer mailboxes over NVLink)
+    ChamferPeerSum peer;
+    const bool fused_sum = comm != nullptr;
+    if (fused_sum) {
+        if (flags & (F3D_FLAG_FMA | F3D_FLAG_EXACT_SWEEP)) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: the fused cross-rank sum exists only for the default sweep");
+        if (!comm_peek_peer_sum(comm, &peer)) return F3D_ERR_NCCL;  // the error string is set
+    }
+    // the in-grid upload exists for the filtered sweeps on host memory the device can read in place: the tensor-core sweep pulls the
+    // batch with its own spare warps; small problems (or F3D_FLAG_CUDA_CORES) take the CUDA-core sweep, whose first CTAs upload
     ChamferUpload up;
     up.A_host_dev = nullptr; up.B_host_dev = nullptr; up.uploaders = h->uploaders;
     if ((flags & (F3D_FLAG_FMA | F3D_FLAG_EXACT_SWEEP)) == 0) {
@@ -117,20 +127,9 @@ extern "C" int32_t f3d_chamfer_pipe_run(void* pipe, const float* A_host, const f
         up.B_host_dev = up.A_host_dev ? device_view(B_host) : nullptr;
     }
     const bool in_grid = up.A_host_dev && up.B_host_dev;
-    // In-grid upload: the CUDA-core sweep is the default carrier — its uploaders are CTAs of the sweep grid itself and the
-    // whole call is a memset + two launches (cfg2, host arrays -> host scalar: 204 us against 221 us for the tensor-core sweep
-    // with its separate upload + prepare grid, profiles/r02h_e2e_paths.txt).  F3D_FLAG_TENSOR selects the latter.
-    if (in_grid && !(flags & F3D_FLAG_TENSOR)) flags |= F3D_FLAG_CUDA_CORES;
     if (!in_grid) {
         F3D_CUDA(cudaMemcpyAsync(dA, A_host, sizeof(float) * 3 * (size_t)B * N, cudaMemcpyHostToDevice, stream));
         F3D_CUDA(cudaMemcpyAsync(dB, B_host, sizeof(float) * 3 * (size_t)B * M, cudaMemcpyHostToDevice, stream));
-    }
-    // sharded batch: the loss is summed over the ranks inside the finalize kernel (peer mailboxes over NVLink)
-    ChamferPeerSum peer;
-    const bool fused_sum = comm != nullptr;
-    if (fused_sum) {
-        if (flags & (F3D_FLAG_FMA | F3D_FLAG_EXACT_SWEEP)) return fail(F3D_ERR_INVALID, "f3d_chamfer_pipe_run: the fused cross-rank sum exists only for the default sweep");
-        if (!comm_peek_peer_sum(comm, &peer)) return F3D_ERR_NCCL;  // the error string is set
     }
     const int32_t rc = chamfer_fwd_launch(dA, dB, B, N, M, w1, w2, B_total, target, nullptr, nullptr, nullptr, w + pl.off_ws, pl.ws_chamfer,
                                           flags, stream, in_grid ? &up : nullptr, fused_sum ? &peer : nullptr);

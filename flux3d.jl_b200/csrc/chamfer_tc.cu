@@ -97,7 +97,7 @@ constexpr float kTcWinAbs = 4.2e-6f;        // >= 70.1 u = 4.178e-6
 constexpr float kTcWinRel = 6.2e-7f;        // >= 10.01 u
 constexpr float kTcErrAbs = 2.1e-6f, kTcErrRel = 3.1e-7f;
 // workspace header (ints); the first three words are diagnostics a caller may read after the call
-constexpr int kHdrDone = 0, kHdrAmb = 1, kHdrViol = 2, kHdrStarted = 32, kHdrInts = 64;
+constexpr int kHdrDone = 0, kHdrAmb = 1, kHdrViol = 2, kHdrInts = 64;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -311,124 +311,32 @@ __global__ void __launch_bounds__(kPrepT) chamfer_tc_prepare_kernel(TcPrepParams
     if (lane == 0) atomicMax(p.maxn + (size_t)(isA ? 0 : 1) * gridDim.y + b, __float_as_uint(mx));
 }
 
-// ---- host arrays: upload + prepare in ONE grid that runs beside the sweep (f3d_chamfer_pipe_run) --------------------------
-// The first U CTAs to start (roles go by start ticket, so whoever waits below waits for CTAs that are already running) pull
-// both clouds out of page-locked host memory over PCIe, batch element by batch element, into the staging copies the finalize
-// reads, and count every element as it lands; the other P CTAs wait for an element, centre it, write its compact operands
-// and count it as prepared.  The sweep's producer (launched programmatically right behind this grid) waits per ELEMENT:
-// it sweeps element b while elements b+1.. are still crossing PCIe.
-struct TcUploadParams {
-    TcPrepParams pp;          // A / Bp here are the device staging copies (written by the uploaders)
-    const float* hA;          // the host arrays as the device addresses them
-    const float* hB;
-    float* dA;
-    float* dB;
-    int B, U, P;
-    unsigned* arrived;        // [B]  uploader CTAs that have delivered their share of the element (target U)
-    int* prepared;            // [B]  preparer CTAs that have written their share of its operands (target P)
-    int* hdr;
-};
+// ---- host arrays: PCIe reads by the sweep CTAs' own spare warps (f3d_chamfer_pipe_run) --------------------------------------
 __device__ __forceinline__ float4 ld_host_f4(const float* p) {
     float4 v;  // volatile: never served from a stale cache line of a previous call's bytes at the same host address
     asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ float ld_host_f1(const float* p) {
-    float v;
-    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-// floats [s, e) of src -> dst (same index space, both bases 16-byte aligned) by ONE WARP of W cooperating warps (this one is
-// warp w): scalar head / tail, 16-byte body, four loads per lane in flight
-__device__ __forceinline__ void upload_span_warp(const float* __restrict__ src, float* __restrict__ dst, unsigned s, unsigned e, int w, int W, int lane) {
-    // (32-bit float offsets and two loads per lane in flight: the whole kernel has to live in 32 registers — see below)
-    unsigned s4 = (s + 3u) & ~3u, e4 = e & ~3u;
-    if (s4 > e4) s4 = e4 = e;  // fewer than one aligned quad: everything is "head"
-    if (w == 0) {
-        if (s + lane < s4) dst[s + lane] = ld_host_f1(src + s + lane);    // < 4 floats each
-        if (e4 + lane < e && e4 >= s4) dst[e4 + lane] = ld_host_f1(src + e4 + lane);
-    }
-    const unsigned n4 = (e4 - s4) >> 2, stride = (unsigned)W * 32u;
-    const float4* s16 = reinterpret_cast<const float4*>(src + s4);
-    float4* d16 = reinterpret_cast<float4*>(dst + s4);
-    for (unsigned i = (unsigned)w * 32u + lane; i < n4; i += 2 * stride) {
-        const bool two = i + stride < n4;
-        const float4 v0 = ld_host_f4(reinterpret_cast<const float*>(s16 + i));
-        float4 v1 = v0;
-        if (two) v1 = ld_host_f4(reinterpret_cast<const float*>(s16 + i + stride));
-        __stcg(d16 + i, v0);
-        if (two) __stcg(d16 + i + stride, v1);
+// One batch element of both clouds (whole 16-byte units: N, M are multiples of 4 on this path) by warp w of W cooperating warps:
+// the loads of both clouds are issued before the first store — four 16-byte PCIe reads per lane in flight
+__device__ __forceinline__ void upload_pair_warp(const float4* __restrict__ sa, float4* __restrict__ da, unsigned na4, const float4* __restrict__ sb,
+                                                 float4* __restrict__ db, unsigned nb4, int w, int W, int lane) {
+    const unsigned stride = (unsigned)W * 32u, n = max(na4, nb4);
+    for (unsigned i = (unsigned)w * 32u + lane; i < n; i += 2 * stride) {
+        const unsigned j = i + stride;
+        float4 a0, a1, b0, b1;
+        if (i < na4) a0 = ld_host_f4(reinterpret_cast<const float*>(sa + i));
+        if (i < nb4) b0 = ld_host_f4(reinterpret_cast<const float*>(sb + i));
+        if (j < na4) a1 = ld_host_f4(reinterpret_cast<const float*>(sa + j));
+        if (j < nb4) b1 = ld_host_f4(reinterpret_cast<const float*>(sb + j));
+        if (i < na4) __stcg(da + i, a0);
+        if (i < nb4) __stcg(db + i, b0);
+        if (j < na4) __stcg(da + j, a1);
+        if (j < nb4) __stcg(db + j, b1);
     }
 }
-constexpr int kUpT = 256;
-// <= 32 registers: an upload / prepare CTA must fit BESIDE a sweep CTA (55 296 of the SM's 65 536 registers), or the sweep
-// CTAs of a third of the SMs would only start once the whole batch has crossed PCIe
-__global__ void __launch_bounds__(kUpT, 8) chamfer_tc_upload_prepare_kernel(TcUploadParams p) {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the sweep becomes resident beside this grid; its producer waits per element
-    __shared__ int s_ticket;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_ticket = atomicAdd(p.hdr + kHdrStarted, 1);
-    __syncthreads();
-    const int ticket = s_ticket;
-    const TcPrepParams& q = p.pp;
-    if (ticket < p.U) {
-        // uploaders: every WARP moves its share of every element and counts it on its own — no block-wide barrier, so the warps
-        // of the grid spread over two or three elements and keep the PCIe read queue full
-        const unsigned ea = (unsigned)q.N * 3u, eb = (unsigned)q.M * 3u;   // (the host side checks B*N*3, B*M*3 < 2^31)
-        const int W = p.U * (kUpT / 32), w = ticket * (kUpT / 32) + warp;
-        for (int b = 0; b < p.B; ++b) {
-            upload_span_warp(p.hA, p.dA, b * ea, (b + 1) * ea, w, W, lane);
-            upload_span_warp(p.hB, p.dB, b * eb, (b + 1) * eb, w, W, lane);
-            __threadfence();   // this lane's stores are visible device-wide ...
-            __syncwarp();      // ... for every lane of the warp ...
-            if (lane == 0) atomicAdd(p.arrived + b, 1u);  // ... before the element counts as delivered by this warp
-        }
-        return;
-    }
-    const int v = ticket - p.U;
-    const int arrive_target = p.U * (kUpT / 32);
-    for (int b = 0; b < p.B; ++b) {
-        if (tid == 0) {
-            const int* f = reinterpret_cast<const int*>(p.arrived) + b;
-            while (ld_acquire_i32(f) < arrive_target) __nanosleep(100);
-        }
-        __syncthreads();
-        const float* gA = q.A + (size_t)b * q.N * 3;
-        const float* gB = q.Bp + (size_t)b * q.M * 3;
-        // the same centre, with the same operations, as chamfer_tc_prepare_kernel (the staging copies were written by other SMs: L2 loads)
-        const int ia = (int)(((long)lane * q.N) >> 5), ib = (int)(((long)lane * q.M) >> 5);
-        float cx = __ldcg(gA + 3 * ia) + __ldcg(gB + 3 * ib);
-        float cy = __ldcg(gA + 3 * ia + 1) + __ldcg(gB + 3 * ib + 1);
-        float cz = __ldcg(gA + 3 * ia + 2) + __ldcg(gB + 3 * ib + 2);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            cx += __shfl_xor_sync(0xffffffffu, cx, o);
-            cy += __shfl_xor_sync(0xffffffffu, cy, o);
-            cz += __shfl_xor_sync(0xffffffffu, cz, o);
-        }
-        cx *= (1.0f / 64.0f); cy *= (1.0f / 64.0f); cz *= (1.0f / 64.0f);
-        // points of both clouds, padded: [0, NpA) of A, then [0, NpB) of B; this CTA takes every P-th block of 256
-        const int total = q.NpA + q.NpB;
-        for (int i0 = v * kUpT; i0 < total; i0 += p.P * kUpT) {
-            const int i = i0 + tid;                    // NpA is a multiple of 256: a block never straddles the two clouds
-            const bool isA = i0 < q.NpA;
-            const int k = isA ? i : i - q.NpA, n = isA ? q.N : q.M, np = isA ? q.NpA : q.NpB;
-            float x = 0.f, y = 0.f, z = 0.f, nrm = kPadN, mx = 0.f;
-            if (k < n) {
-                const float* src = (isA ? gA : gB) + 3 * (size_t)k;
-                x = __ldcg(src) - cx; y = __ldcg(src + 1) - cy; z = __ldcg(src + 2) - cz;
-                nrm = fmaf(z, z, fmaf(y, y, x * x));
-                mx = nrm;
-            }
-            (isA ? q.PA : q.PB)[(size_t)b * np + k] = make_float4(x, y, z, nrm);
-            mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));
-            if (lane == 0) atomicMax(q.maxn + (size_t)(isA ? 0 : 1) * p.B + b, __float_as_uint(mx));
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) atomicAdd(p.prepared + b, 1);
-    }
-}
+// batch elements in flight: element b is moved by the uploader warps w with w % G == b % G
+__device__ __forceinline__ int upload_group_size(int W, int b, int G) { return (W - b % G + G - 1) / G; }
 
 // ---- sweep -------------------------------------------------------------------------------------------------------------
 #ifdef F3D_TC_PROF
@@ -478,8 +386,14 @@ struct TcSweepParams {
     float* tilemin;        // [B][ (nstB*NpA + nstA*NpB) * kParts ]  per supertile of the searched cloud, read-out group and row
     int nstA, nstB;        // supertiles of cloud A / B
     int wait_prepare;      // launched programmatically behind the prepare grid
-    const int* prepared;   // upload mode: [B] preparer CTAs that have written an element's operands (target prepared_target); else null
-    int prepared_target;
+    // Host arrays (f3d_chamfer_pipe_run): no prepare grid, no copy.  The two spare warps of EVERY sweep CTA pull the clouds out of
+    // page-locked host memory over PCIe, batch element by batch element, into staging copies in HBM (f.A / f.Bp) and count every
+    // element as it lands; the producer waits per element and streams the raw points (12 B each) as the tiles; the converters
+    // centre them and take the norms on the fly.
+    unsigned* arrived;     // [B] uploader warps that have delivered their share of an element (target: the element's group); null: resident inputs
+    int up_groups;         // batch elements the uploader warps move concurrently
+    const float* hA;       // the host arrays as the device addresses them (page-locked, mapped)
+    const float* hB;
     TcFinParams f;         // the certifier warps' inputs and outputs
 };
 
@@ -495,6 +409,8 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
         a_empty[2], pub_full, pub_empty;
     __shared__ unsigned s_tmem;
 
+    __shared__ float s_ctr[4][4];               // host arrays: the batch element's centre, per item
+    __shared__ unsigned s_maxw[4][kConvWarps];  // ... and the largest candidate norm each converter warp has seen in the item
     __shared__ double s_part[2][kCertWarps];
     __shared__ int s_cnt[2][kCertWarps];
 
@@ -536,9 +452,25 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
                 const float4* Pq = (dir ? p.PB : p.PA) + (size_t)b * npq + (size_t)rb * kItemRows;
                 const float4* Pc = (dir ? p.PA : p.PB) + (size_t)b * npc;
                 const int ntiles = npc / kTNc;
-                if (p.prepared) {   // upload mode: this batch element may still be crossing PCIe
-                    while (ld_acquire_i32(p.prepared + b) < p.prepared_target) __nanosleep(100);
-                    asm volatile("fence.proxy.async;" ::: "memory");   // the operands were written with generic stores; the TMA reads them through the async proxy
+                if (p.arrived) {   // host arrays: this batch element may still be crossing PCIe
+                    while (ld_acquire_i32(reinterpret_cast<const int*>(p.arrived) + b) < upload_group_size(2 * (int)gridDim.x, b, p.up_groups)) __nanosleep(100);
+                    asm volatile("fence.proxy.async;" ::: "memory");   // written with generic stores while this kernel runs; the TMA reads through the async proxy
+                    const int nq = dir ? p.f.M : p.f.N, nc = dir ? p.f.N : p.f.M;   // (multiples of 4: every tile is whole 16-byte units)
+                    const float* Rq = (dir ? p.f.Bp : p.f.A) + ((size_t)b * nq + (size_t)rb * kItemRows) * 3;
+                    const float* Rc = (dir ? p.f.A : p.f.Bp) + (size_t)b * nc * 3;
+                    for (int t = -1; t < ntiles; ++t, ++h) {
+                        const unsigned s = h % kCStages, n = h / kCStages;
+                        const int left = t < 0 ? nq - rb * kItemRows : nc - t * kTNc;
+                        const unsigned bytes = (unsigned)max(0, min(left, kTNc)) * 12u;
+                        mbar_wait(&cempty[s], (n & 1) ^ 1);
+                        if (bytes) {
+                            mbar_expect_tx(&cfull[s], bytes);
+                            tma_bulk_g2s(s_c + s * kTNc, t < 0 ? Rq : Rc + (size_t)t * kTNc * 3, bytes, &cfull[s]);
+                        } else {
+                            mbar_arrive(&cfull[s]);   // a tile of padding only
+                        }
+                    }
+                    continue;
                 }
                 for (int t = -1; t < ntiles; ++t, ++h) {   // t = -1: the item's 256 query rows
                     const unsigned s = h % kCStages, n = h / kCStages;
@@ -583,6 +515,22 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             }
             PROF_OUT(0, 5);
         }
+      } else if (warp > kWarpMma && warp < kWarpCert) {
+        // ---- uploaders (host arrays only): the two spare warps of every CTA; every warp moves its share of every element and counts
+        // it on its own, so the grid's warps spread over two or three elements and keep the PCIe read queue full ----------------
+        if (p.arrived) {
+            const unsigned na4 = (unsigned)p.f.N * 3u / 4u, nb4 = (unsigned)p.f.M * 3u / 4u;   // float4 units per element (N, M multiples of 4)
+            const int W = 2 * (int)gridDim.x, w = 2 * (int)blockIdx.x + (warp - kWarpMma - 1);
+            const int G = p.up_groups, g = w % G, wg = w / G, Wg = (W - g + G - 1) / G;
+            for (int b = g; b < p.B; b += G) {
+                upload_pair_warp(reinterpret_cast<const float4*>(p.hA) + (size_t)b * na4, reinterpret_cast<float4*>(const_cast<float*>(p.f.A)) + (size_t)b * na4, na4,
+                                 reinterpret_cast<const float4*>(p.hB) + (size_t)b * nb4, reinterpret_cast<float4*>(const_cast<float*>(p.f.Bp)) + (size_t)b * nb4, nb4,
+                                 wg, Wg, lane);
+                __threadfence();   // this lane's stores are visible device-wide ...
+                __syncwarp();      // ... for every lane of the warp ...
+                if (lane == 0) atomicAdd(p.arrived + b, 1u);  // ... before the element counts as delivered by this warp
+            }
+        }
       } else if (warp < kWarpProducer) {
         // ---- converters: thread <-> points pt and pt + 128 of the 256-point tile; compact {x, y, z, n} -> 16 TF32 pieces in the
         // operand row ----------------------------------------------------------------------------------------------------------
@@ -594,6 +542,31 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             const int b = item / ipe, k = item - b * ipe;
             const int ntiles = (k >= p.rbA ? p.NpA : p.NpB) / kTNc;
             const unsigned ab = it & 1;
+            const bool dirc = k >= p.rbA;
+            float cx = 0.f, cy = 0.f, cz = 0.f, mxn = 0.f;
+            if (p.arrived) {
+                // the centre of the batch element, with the operations of chamfer_tc_prepare_kernel (the same bits in every CTA and
+                // in the certifiers): converter warp 0 fetches the 32 + 32 sample points once the element has arrived
+                if (warp == kEpiWarps) {
+                    if (lane == 0) while (ld_acquire_i32(reinterpret_cast<const int*>(p.arrived) + b) < upload_group_size(2 * (int)gridDim.x, b, p.up_groups)) __nanosleep(100);
+                    __syncwarp();
+                    const float* gA = p.f.A + (size_t)b * p.f.N * 3;
+                    const float* gB = p.f.Bp + (size_t)b * p.f.M * 3;
+                    const int ia = (int)(((long)lane * p.f.N) >> 5), ib = (int)(((long)lane * p.f.M) >> 5);
+                    float sx = __ldcg(gA + 3 * ia) + __ldcg(gB + 3 * ib);
+                    float sy = __ldcg(gA + 3 * ia + 1) + __ldcg(gB + 3 * ib + 1);
+                    float sz = __ldcg(gA + 3 * ia + 2) + __ldcg(gB + 3 * ib + 2);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+                        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+                    }
+                    if (lane == 0) { s_ctr[it & 3][0] = sx * (1.0f / 64.0f); s_ctr[it & 3][1] = sy * (1.0f / 64.0f); s_ctr[it & 3][2] = sz * (1.0f / 64.0f); }
+                }
+                named_bar_sync(2, kConvWarps * 32);
+                cx = s_ctr[it & 3][0]; cy = s_ctr[it & 3][1]; cz = s_ctr[it & 3][2];
+            }
             mbar_wait(&a_empty[ab], ((it >> 1) & 1) ^ 1);
             for (int t = -1; t < ntiles; ++t, ++h) {
                 const unsigned cs = h % kCStages;
@@ -601,8 +574,29 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
                 mbar_wait(&cfull[cs], (h / kCStages) & 1);
                 PROF(0);
                 float4 v[2];
-                v[0] = s_c[cs * kTNc + pt];
-                v[1] = s_c[cs * kTNc + pt + 128];
+                if (p.arrived) {
+                    // raw points (12 B each): centre, norm — what chamfer_tc_prepare_kernel writes for resident inputs
+                    const float* raw = reinterpret_cast<const float*>(s_c + cs * kTNc);
+                    const int n = t < 0 ? (dirc ? p.f.M : p.f.N) - (k - (dirc ? p.rbA : 0)) * kItemRows : (dirc ? p.f.N : p.f.M) - t * kTNc;   // points left from this tile on
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int r = pt + 128 * u;
+                        float x = 0.f, y = 0.f, z = 0.f, nrm = kPadN;
+                        if (r < n) {
+                            x = raw[3 * r] - cx; y = raw[3 * r + 1] - cy; z = raw[3 * r + 2] - cz;
+                            nrm = fmaf(z, z, fmaf(y, y, x * x));
+                            if (t >= 0) mxn = fmaxf(mxn, nrm);
+                        }
+                        v[u] = make_float4(x, y, z, nrm);
+                    }
+                    if (t == ntiles - 1) {   // the item's largest candidate norm, published before the last tile is handed over
+                        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(mxn));   // norms are >= 0: bit order == value order
+                        if (lane == 0) s_maxw[it & 3][warp - kEpiWarps] = m;
+                    }
+                } else {
+                    v[0] = s_c[cs * kTNc + pt];
+                    v[1] = s_c[cs * kTNc + pt + 128];
+                }
                 // The compact slot is released only AFTER the stores below, which consume v: an mbarrier.arrive does not
                 // wait for an LDS in flight, and a 16-byte warp load executes in four quarter-warp passes — released right
                 // after the load, the slot was now and then refilled by the TMA before the last pass had read it (rows
@@ -678,7 +672,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             // what does not depend on the sweep is fetched before the wait (device-resident inputs; in upload mode the element
             // may still be crossing PCIe — its points are only known to have arrived once the item's records are here)
             float qx = 0.f, qy = 0.f, qz = 0.f, nq = 0.f, other = 0.f;
-            const bool early = p.prepared == nullptr;
+            const bool early = p.arrived == nullptr;
             if (valid && early) {
                 nq = __ldcg(&((dir ? p.PB : p.PA) + (size_t)b * (dir ? p.NpB : p.NpA) + q)->w);
                 other = __uint_as_float(__ldcg(f.maxn + (size_t)(dir ? 0 : 1) * p.B + b));
@@ -711,10 +705,11 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             int loc1 = -1, loc2 = -1;      // chunks to re-evaluate (-1: none)
             bool amb = false;
             if (valid) {
-                if (!early) {   // (the producer saw `prepared` before this item's first tile; L2 loads)
-                    nq = __ldcg(&((dir ? p.PB : p.PA) + (size_t)b * (dir ? p.NpB : p.NpA) + q)->w);
-                    other = __uint_as_float(__ldcg(f.maxn + (size_t)(dir ? 0 : 1) * p.B + b));
+                if (!early) {   // host arrays (the element had arrived before this item's first tile; L2 loads): the norms as the converters took them
                     qx = __ldcg(gQ + 3 * (size_t)q); qy = __ldcg(gQ + 3 * (size_t)q + 1); qz = __ldcg(gQ + 3 * (size_t)q + 2);
+                    const float x = qx - s_ctr[it & 3][0], y = qy - s_ctr[it & 3][1], z = qz - s_ctr[it & 3][2];
+                    nq = fmaf(z, z, fmaf(y, y, x * x));
+                    other = __uint_as_float(max(max(s_maxw[it & 3][0], s_maxw[it & 3][1]), max(s_maxw[it & 3][2], s_maxw[it & 3][3])));
                 }
                 best = fmaxf(e.b1, 0.0f);
                 // the chunk numbers embedded in the located values moved them by up to 2^(idbits-23) relative
@@ -736,7 +731,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             float d = INFINITY;
             int j = 0x7fffffff;
             unsigned char* myrow = s_chunk + rin * kChunkPitch;
-            if (p.prepared) asm volatile("fence.proxy.async;" ::: "memory");   // upload mode: the points were written with generic stores by the upload grid
+            if (p.arrived) asm volatile("fence.proxy.async;" ::: "memory");   // host arrays: the points were stored by uploader warps while this kernel runs
             for (int pass = 0; pass < 2; ++pass) {
                 const int c = pass == 0 ? loc1 : loc2;
                 if (pass == 1 && !__any_sync(full, c >= 0)) break;   // (about one warp in nine holds a two-chunk row)
@@ -1093,7 +1088,7 @@ TcPlan make_tc_plan(int B, int N, int M) {
     size_t o = 0;
     pl.off_hdr = o;     o = align_up(o + sizeof(int) * kHdrInts, 256);   // diagnostics first: a caller can find them
     pl.off_maxn = o;    o = align_up(o + sizeof(unsigned) * 2 * (size_t)B, 256);
-    pl.off_arrived = o; o = align_up(o + sizeof(int) * 2 * (size_t)B, 256);   // upload mode: arrived [B], prepared [B]
+    pl.off_arrived = o; o = align_up(o + sizeof(int) * (size_t)B, 256);   // host arrays: arrived [B]
     pl.zero_from = 0;
     pl.zero_bytes = o;  // header, norm maxima and arrival counters are zeroed by ONE memset per call
     pl.off_PA = o;      o = align_up(o + sizeof(float4) * (size_t)B * pl.NpA, 256);
@@ -1128,6 +1123,8 @@ bool chamfer_tc_possible(int B, int N, int M) {
     if ((long long)B * (pl.rbA + pl.rbB) * kItemRows > 0x3fffffffLL) return false;   // slots are ints
     return std::max(pl.NpA, pl.NpB) <= 131072;   // running chunk numbers travel in <= 10 mantissa bits, global chunk ids as 16 bits
 }
+// host arrays through the sweep's own uploader warps: every 256-point tile of the raw clouds must be whole 16-byte units (TMA)
+bool chamfer_tc_upload_possible(int N, int M) { return (N & 3) == 0 && (M & 3) == 0; }
 bool chamfer_tc_supported(int B, int N, int M) {
     if (!chamfer_tc_possible(B, N, M)) return false;
     const TcPlan pl = make_tc_plan(B, N, M);
@@ -1149,7 +1146,6 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
         // the grids that run BEFORE / BESIDE the sweep must leave the SMs in the sweep's shared-memory configuration: an SM that
         // an upload CTA has configured for a large L1 cannot take a sweep CTA (130 KB of shared memory) until it drains
         F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_upload_prepare_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_prepare_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         int sms = 0;
         F3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1163,23 +1159,11 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
     pp.PA = reinterpret_cast<float4*>(w + pl.off_PA);
     pp.PB = reinterpret_cast<float4*>(w + pl.off_PB);
     pp.maxn = reinterpret_cast<unsigned*>(w + pl.off_maxn);
-    int prepared_target = 0;
+    // Host arrays (upload): A / Bp are staging buffers; the sweep's own spare warps fill them over PCIe — no prepare grid, the
+    // converters centre the raw points and take the norms on the fly
     if (upload && ((long long)B * N * 3 >= 0x7fffffffLL || (long long)B * M * 3 >= 0x7fffffffLL))
         return fail(F3D_ERR_INVALID, "chamfer_tc_launch: batch too large for the in-grid upload");
-    if (upload) {
-        // host arrays: A / Bp are staging buffers; one grid uploads and prepares, element by element, beside the sweep
-        TcUploadParams up;
-        up.pp = pp;
-        up.hA = upload->A_host_dev; up.hB = upload->B_host_dev;
-        up.dA = const_cast<float*>(A); up.dB = const_cast<float*>(Bp);
-        up.B = B; up.U = std::max(1, std::min(upload->uploaders, 128)); up.P = 16;
-        up.arrived = reinterpret_cast<unsigned*>(w + pl.off_arrived);
-        up.prepared = reinterpret_cast<int*>(w + pl.off_arrived) + B;
-        up.hdr = reinterpret_cast<int*>(w + pl.off_hdr);
-        prepared_target = up.P;
-        chamfer_tc_upload_prepare_kernel<<<up.U + up.P, kUpT, 0, stream>>>(up);
-        F3D_CHECK_LAUNCH("chamfer_tc_upload_prepare_kernel");
-    } else {
+    if (!upload) {
         chamfer_tc_prepare_kernel<<<dim3((std::max(pl.NpA, pl.NpB) + kPrepT - 1) / kPrepT, B, 2), kPrepT, 0, stream>>>(pp);
         F3D_CHECK_LAUNCH("chamfer_tc_prepare_kernel");
     }
@@ -1209,8 +1193,13 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
     sp.tilemin = reinterpret_cast<float*>(w + pl.off_tilemin);
     sp.nstA = pl.nstA; sp.nstB = pl.nstB;
     sp.wait_prepare = upload ? 0 : 1;
-    sp.prepared = upload ? reinterpret_cast<const int*>(w + pl.off_arrived) + B : nullptr;
-    sp.prepared_target = prepared_target;
+    sp.arrived = upload ? reinterpret_cast<unsigned*>(w + pl.off_arrived) : nullptr;
+    sp.up_groups = 2;   // (1, 2: 171 us per cfg2 call; 4: 176-185; 8: 181 — same box)
+#ifdef F3D_TC_EXP_ENV
+    if (const char* e = getenv("F3D_UP_GROUPS")) sp.up_groups = std::max(1, std::min(atoi(e), 16));   // development
+#endif
+    sp.hA = upload ? upload->A_host_dev : nullptr;
+    sp.hB = upload ? upload->B_host_dev : nullptr;
     sp.f = fp;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1227,7 +1216,8 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
         // programmatic launch: the blocks are set up while the sweep runs and take the SMs as its CTAs leave (griddepcontrol.wait
         // holds them until the whole sweep grid has ended)
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(std::min(pl.nitems, sms)); cfg.blockDim = dim3(kCleanT);   // one wave: the reducer block waits for the others cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cfg.gridDim = dim3(std::min(pl.nitems, sms));   // one wave: the reducer block waits for the others
+        cfg.blockDim = dim3(kCleanT); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
 #ifdef F3D_TC_EXP_ENV
         if (getenv("F3D_TC_NOPDL")) attr[0].val.programmaticStreamSerializationAllowed = 0;  // development: cleanup launched strictly after the sweep
 #endif

@@ -58,6 +58,7 @@ void comm_commit_peer_sum(void* comm);
 size_t chamfer_tc_workspace_bytes(int B, int N, int M);
 bool chamfer_tc_possible(int B, int N, int M);   // hard limits of the path
 bool chamfer_tc_supported(int B, int N, int M);  // ... and large enough to be the default
+bool chamfer_tc_upload_possible(int N, int M);   // ... on host arrays pulled over PCIe by the sweep's own spare warps (ChamferUpload)
 int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M, float w1, float w2, int32_t B_total,
                           float* loss_dev, float* terms_dev, int32_t* nnA_dev, int32_t* nnB_dev, void* ws, size_t ws_bytes, int32_t flags,
                           cudaStream_t stream, const ChamferUpload* upload, const ChamferPeerSum* peer);

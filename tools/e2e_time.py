@@ -6,8 +6,8 @@ import flux3d_b200 as f3d
 B, N, M = (int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "32x4096x4096").split("x"))
 A = torch.from_numpy(np.random.default_rng(201).random((B, N, 3), dtype=np.float32)).pin_memory()
 Bc = torch.from_numpy(np.random.default_rng(202).random((B, M, 3), dtype=np.float32)).pin_memory()
-for name, fl in (("tensor-core sweep", 0), ("CUDA-core sweep", f3d.FLAG_CUDA_CORES)):
-    for ups in (0, 8, 16, 64):
+for name, fl in (("tensor-core sweep", f3d.FLAG_TENSOR), ("CUDA-core sweep", f3d.FLAG_CUDA_CORES)):
+    for ups in (0, 4, 8, 16, 32):
         for _ in range(5):
             l = f3d.chamfer_forward_host(A, Bc, to_host=True, flags=fl, uploaders=ups)
         torch.cuda.synchronize()
