@@ -397,6 +397,8 @@ struct TcSweepParams {
     TcFinParams f;         // the certifier warps' inputs and outputs
 };
 
+// kRaw: host arrays (uploader warps, raw tiles, centre / norms on the fly); the resident-input instantiation carries none of that code
+template <bool kRaw>
 __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p) {
     extern __shared__ unsigned char smem_raw_[];
     unsigned char* smem = smem_raw_ + ((1024u - (smem_u32(smem_raw_) & 1023u)) & 1023u);
@@ -452,7 +454,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
                 const float4* Pq = (dir ? p.PB : p.PA) + (size_t)b * npq + (size_t)rb * kItemRows;
                 const float4* Pc = (dir ? p.PA : p.PB) + (size_t)b * npc;
                 const int ntiles = npc / kTNc;
-                if (p.arrived) {   // host arrays: this batch element may still be crossing PCIe
+                if (kRaw) {   // host arrays: this batch element may still be crossing PCIe
                     while (ld_acquire_i32(reinterpret_cast<const int*>(p.arrived) + b) < upload_group_size(2 * (int)gridDim.x, b, p.up_groups)) __nanosleep(100);
                     asm volatile("fence.proxy.async;" ::: "memory");   // written with generic stores while this kernel runs; the TMA reads through the async proxy
                     const int nq = dir ? p.f.M : p.f.N, nc = dir ? p.f.N : p.f.M;   // (multiples of 4: every tile is whole 16-byte units)
@@ -518,7 +520,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
       } else if (warp > kWarpMma && warp < kWarpCert) {
         // ---- uploaders (host arrays only): the two spare warps of every CTA; every warp moves its share of every element and counts
         // it on its own, so the grid's warps spread over two or three elements and keep the PCIe read queue full ----------------
-        if (p.arrived) {
+        if (kRaw) {
             const unsigned na4 = (unsigned)p.f.N * 3u / 4u, nb4 = (unsigned)p.f.M * 3u / 4u;   // float4 units per element (N, M multiples of 4)
             const int W = 2 * (int)gridDim.x, w = 2 * (int)blockIdx.x + (warp - kWarpMma - 1);
             const int G = p.up_groups, g = w % G, wg = w / G, Wg = (W - g + G - 1) / G;
@@ -544,7 +546,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             const unsigned ab = it & 1;
             const bool dirc = k >= p.rbA;
             float cx = 0.f, cy = 0.f, cz = 0.f, mxn = 0.f;
-            if (p.arrived) {
+            if (kRaw) {
                 // the centre of the batch element, with the operations of chamfer_tc_prepare_kernel (the same bits in every CTA and
                 // in the certifiers): converter warp 0 fetches the 32 + 32 sample points once the element has arrived
                 if (warp == kEpiWarps) {
@@ -574,7 +576,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
                 mbar_wait(&cfull[cs], (h / kCStages) & 1);
                 PROF(0);
                 float4 v[2];
-                if (p.arrived) {
+                if (kRaw) {
                     // raw points (12 B each): centre, norm — what chamfer_tc_prepare_kernel writes for resident inputs
                     const float* raw = reinterpret_cast<const float*>(s_c + cs * kTNc);
                     const int n = t < 0 ? (dirc ? p.f.M : p.f.N) - (k - (dirc ? p.rbA : 0)) * kItemRows : (dirc ? p.f.N : p.f.M) - t * kTNc;   // points left from this tile on
@@ -672,7 +674,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             // what does not depend on the sweep is fetched before the wait (device-resident inputs; in upload mode the element
             // may still be crossing PCIe — its points are only known to have arrived once the item's records are here)
             float qx = 0.f, qy = 0.f, qz = 0.f, nq = 0.f, other = 0.f;
-            const bool early = p.arrived == nullptr;
+            const bool early = !kRaw;
             if (valid && early) {
                 nq = __ldcg(&((dir ? p.PB : p.PA) + (size_t)b * (dir ? p.NpB : p.NpA) + q)->w);
                 other = __uint_as_float(__ldcg(f.maxn + (size_t)(dir ? 0 : 1) * p.B + b));
@@ -731,7 +733,7 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             float d = INFINITY;
             int j = 0x7fffffff;
             unsigned char* myrow = s_chunk + rin * kChunkPitch;
-            if (p.arrived) asm volatile("fence.proxy.async;" ::: "memory");   // host arrays: the points were stored by uploader warps while this kernel runs
+            if (kRaw) asm volatile("fence.proxy.async;" ::: "memory");   // host arrays: the points were stored by uploader warps while this kernel runs
             for (int pass = 0; pass < 2; ++pass) {
                 const int c = pass == 0 ? loc1 : loc2;
                 if (pass == 1 && !__any_sync(full, c >= 0)) break;   // (about one warp in nine holds a two-chunk row)
@@ -1142,10 +1144,12 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
     static unsigned char attr_done[256];
     static int sm_count[256];
     if (dev < 0 || dev >= 256 || !attr_done[dev]) {
-        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
         // the grids that run BEFORE / BESIDE the sweep must leave the SMs in the sweep's shared-memory configuration: an SM that
         // an upload CTA has configured for a large L1 cannot take a sweep CTA (130 KB of shared memory) until it drains
-        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_sweep_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_sweep_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         F3D_CUDA(cudaFuncSetAttribute(chamfer_tc_prepare_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         int sms = 0;
         F3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1208,7 +1212,8 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(std::min(pl.nitems, sms)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kTcSmem; cfg.stream = stream;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_tc_sweep_kernel, sp));
+        if (upload) F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_tc_sweep_kernel<true>, sp));
+        else F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_tc_sweep_kernel<false>, sp));
     }
     F3D_CHECK_LAUNCH("chamfer_tc_sweep_kernel");
     if (flags & F3D_FLAG_SWEEP_ONLY) return F3D_OK;

@@ -339,3 +339,28 @@ def test_host_pipeline_tensor_path_full_size(f3d, oracle):
     # the default carrier of the in-grid upload (CUDA-core sweep): same rows, another summation order
     assert abs(f3d.chamfer_forward_host(pA, pB, to_host=True).item() - ld) <= 1e-6 * ld
     assert abs(ld - 0.0028460352) <= 1e-5 * 0.0028460352
+
+
+def test_every_launch_goes_to_the_callers_stream(f3d):
+    """The whole step runs on the stream it was given: with the default stream blocked for a second, a call on a side stream must
+    deliver its loss as soon as that side stream has drained (a launch that strayed to the default stream would sit behind the
+    sleep and the loss would still be the stale value)."""
+    import time
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for shape in ((32, 4096, 4096), (2, 700, 300)):          # tensor-core sweep + cleanup; CUDA-core sweep + finalize
+        A = torch.rand((shape[0], shape[1], 3), generator=g, device="cuda")
+        Bc = torch.rand((shape[0], shape[2], 3), generator=g, device="cuda")
+        ref = f3d.chamfer_forward_raw(A, Bc, 1.0, 1.0, want_indices=False)[0].item()
+        side = torch.cuda.Stream()
+        host = torch.zeros(1).pin_memory()
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(2.0e9))                         # ~1 s of the default stream
+        t0 = time.perf_counter()
+        with torch.cuda.stream(side):
+            out = f3d.chamfer_forward_raw(A, Bc, 1.0, 1.0, want_indices=False)
+            host.copy_(out[0].reshape(1), non_blocking=True)
+        side.synchronize()
+        dt = time.perf_counter() - t0
+        assert host.item() == ref, (shape, host.item(), ref)
+        assert dt < 0.5, dt
+        torch.cuda.synchronize()
