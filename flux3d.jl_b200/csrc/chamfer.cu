@@ -365,16 +365,6 @@ constexpr float kBallotRel = 1.0000007f;  // >= 1 + 10.01u
 constexpr float kPadF = 3.0e38f;     // padded rows / columns: filter value ~3e38 (or +inf), never a minimum
 constexpr float kNormLimit = 1.0e29f;  // above this the filter arithmetic could overflow: certify nothing
 
-#ifdef F3D_EXP_CLOCK
-__device__ long long g_dbg[8 * 8192];
-#define DBG_T(k) do { if (tid == 0) { long long c_ = clock64(); unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); int id_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; if (id_ < 8192) { g_dbg[id_ * 8 + (k)] = c_; if ((k) == 0) { g_dbg[id_ * 8 + 4] = (long long)g_; unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_dbg[id_ * 8 + 6] = sm_; } if ((k) == 3) g_dbg[id_ * 8 + 5] = (long long)g_; } } } while (0)
-__device__ long long g_dbgf[8 * 2048];  // finalize: per block, globaltimer at 6 phase boundaries + smid
-#define DBG_F(k) do { if (threadIdx.x == 0 && blockIdx.x < 2048) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); g_dbgf[blockIdx.x * 8 + (k)] = (long long)g_; if ((k) == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_dbgf[blockIdx.x * 8 + 7] = sm_; } } } while (0)
-#else
-#define DBG_T(k)
-#define DBG_F(k)
-#endif
-
 struct FiltParams {
     const float* A;
     const float* Bp;
@@ -566,8 +556,6 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
     __shared__ int s_ticket;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    DBG_T(0);
     // Programmatic dependent launch: let the finalize grid become resident as soon as every CTA of this grid has
     // started; its blocks wait on rowdone/coldone, so they soak up the SM slots the last partial wave leaves idle.
     // A CTA sweeps tiles c, c + G, c + 2G, ... (G = grid size).  By default G = number of tiles — one tile per CTA and
@@ -749,10 +737,6 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
     // (the LAST chunk's minima never leave the registers — they are still live when the loop ends — so nchunks - 1 chunks
     // are parked: 28 KB instead of 32 KB at 256 columns per warp, which is what lets a fifth CTA fit the SM's 228 KB)
     float* s_rm = reinterpret_cast<float*>(s_row) + (size_t)warp * (nchunks - 1) * kTileRows;
-    DBG_T(1);
-#ifdef F3D_EXP_REPEAT
-    for (int rep = 0; rep < F3D_EXP_REPEAT; ++rep)
-#endif
     float rm[kRowsPerLane];
     for (int ch = 0; ch < nchunks; ++ch) {
 #pragma unroll
@@ -779,15 +763,11 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
                 c0 = fminf(c0, f0);
                 c1v = fminf(c1v, f1);
             }
-#ifdef F3D_EXP_NOCOL
-            if (c0 + c1v == 123.0f) gcol4[pp] = make_uint4(1, 2, 3, 4);
-#else
             const int m0 = __reduce_min_sync(0xffffffffu, __float_as_int(c0));
             const int m1 = __reduce_min_sync(0xffffffffu, __float_as_int(c1v));
             const unsigned bal0 = __ballot_sync(0xffffffffu, c0 <= fmaf(__int_as_float(m0), kBallotRel, wt));
             const unsigned bal1 = __ballot_sync(0xffffffffu, c1v <= fmaf(__int_as_float(m1), kBallotRel, wt));
             if (lane == 0) gcol4[pp] = make_uint4((unsigned)m0, bal0, (unsigned)m1, bal1);
-#endif
         }
         if (ch + 1 < nchunks) {
 #pragma unroll
@@ -811,8 +791,6 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
         }
     }
     __syncthreads();  // s_row below aliases the s_rm regions of all warps
-
-    DBG_T(2);
     // ---- merge the 4 warps' row triples (ascending column order), store the partials ----------------------
 #pragma unroll
     for (int r = 0; r < kRowsPerLane; ++r)
@@ -838,7 +816,6 @@ __global__ void __launch_bounds__(kThreads, F3D_FILT_MINB) chamfer_filter_sweep_
         atomicAdd(p.rowdone + (size_t)b * p.RB + rb, 1);
         atomicAdd(p.coldone + (size_t)b * p.CS + cs, 1);
     }
-    DBG_T(3);
     // (the barrier above also separates this tile's last use of the shared tile / s_row from the next tile's staging)
   }
 }
@@ -921,26 +898,15 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
     // Blocks are numbered in the order the persistent sweep completes their inputs: batch element by batch element,
     // its row blocks (fbA = ceil(N/256) of them), then its column blocks (fbB = ceil(M/256)).
     const int fbA = (p.N + kFinThreads - 1) / kFinThreads, fbB = (p.M + kFinThreads - 1) / kFinThreads;
-#ifdef F3D_EXP_FIN_ROWS_FIRST
-    // (experiment) all row blocks of the batch first, then all column blocks
-    const int fe = (int)blockIdx.x < p.B * fbA ? (int)blockIdx.x / fbA : ((int)blockIdx.x - p.B * fbA) / fbB;
-    const int fj = (int)blockIdx.x < p.B * fbA ? (int)blockIdx.x - fe * fbA : fbA + ((int)blockIdx.x - p.B * fbA) - fe * fbB;
-#else
     const int fe = (int)blockIdx.x / (fbA + fbB), fj = (int)blockIdx.x - fe * (fbA + fbB);
-#endif
     const bool rows = fj < fbA;
     const int Q = rows ? p.N : p.M;        // items per batch element (queries)
     const long t = (long)fe * Q + (long)(rows ? fj : fj - fbA) * kFinThreads + tid;  // flat item index b*Q + q
     const int R = rows ? p.M : p.N;        // points searched per query
     const float* gQ = rows ? p.A : p.Bp;   // queries
     const float* gP = rows ? p.Bp : p.A;   // searched cloud
-#ifdef F3D_EXP_FIN_EMPTY
-    if (blockIdx.x + threadIdx.x == 0) p.loss[0] = 0.f;
-    return;
-#endif
     const bool valid = (rows ? fj : fj - fbA) * kFinThreads + tid < Q;
     double mine = 0.0;
-    DBG_F(0);
 
     // ---- phase 1: merge the sweep's partials ------------------------------------------------------------------------
     // Everything here and in phase 2 is a chain of L2 round trips (≈ 0.4 µs each on B200), so the loads of a step are
@@ -962,7 +928,6 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
             while (ld_acquire(flag) < target) __nanosleep(100);
         __syncwarp();
     }
-    DBG_F(1);
     if (valid) {
         const float* c = p.centre + 4 * b;
         const float* pt = gQ + ((size_t)b * Q + q) * 3;
@@ -1017,12 +982,9 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
         // written so that NaN / inf / out-of-range norms can only make the item ambiguous, never certified
         amb = !(nq <= kNormLimit && other <= kNormLimit && second > best + win);
     }
-
-    DBG_F(2);
     // ---- phase 2: certified items — each lane re-evaluates its own item's located candidates exactly -------------------
     // rows: the 32 columns of the located chunk (384 contiguous bytes); columns: the 8 rows of every balloted lane (96
     // contiguous bytes each, almost always one).  16-byte loads when the cloud is 16-byte aligned there (N, M % 4 == 0).
-#ifndef F3D_EXP_FIN_SKIP2
     if (valid && !amb) {
         const float* P = gP + (size_t)b * R * 3;
         float d = INFINITY;
@@ -1079,9 +1041,6 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
         if (nn) nn[t] = j;
         mine += (double)d;
     }
-#endif
-
-    DBG_F(3);
     // ---- phase 3: ambiguous items, one at a time, by the WHOLE BLOCK -------------------------------------------
     // An ambiguous item needs an exact scan of every tile within its window (up to BN = 1024 candidates each).  Done by
     // the owning warp alone that is a chain of dependent L2 round trips, and the few warps that own two or three such
@@ -1089,11 +1048,7 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
     // tile are in flight at once, and an item costs about one memory latency.  The order of the queue is fixed (warp,
     // lane), each owner adds its own item's distance: the block's partial sum stays run-to-run deterministic.
     {
-#ifdef F3D_EXP_FIN_SKIP3
-        const unsigned ambmask = 0u;
-#else
         const unsigned ambmask = __ballot_sync(0xffffffffu, valid && amb);
-#endif
         if (lane == 0) s_amb[warp] = ambmask;
         if (valid && amb) { s_ib[tid] = b; s_iq[tid] = q; s_ilim[tid] = best + win; }
         __syncthreads();
@@ -1188,8 +1143,6 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
             }
         }
     }
-
-    DBG_F(4);
     // ---- block partial sum → last block reduces in a fixed order (deterministic) ------------------------------
     mine = warp_sum(mine);
     if (lane == 0) s_red[warp] = mine;
@@ -1202,17 +1155,12 @@ __global__ void __launch_bounds__(kFinThreads, F3D_FIN_MINB) chamfer_filter_fina
         s_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
     }
     __syncthreads();
-    DBG_F(5);
     if (!s_last) return;
     __threadfence();
     double sa = 0.0, sb = 0.0;
     for (int k = tid; k < p.nbA + p.nbB; k += kFinThreads) {
         const double v = __ldcg(p.partial + k);
-#ifdef F3D_EXP_FIN_ROWS_FIRST
-        if (k < p.B * fbA) sa += v; else sb += v;
-#else
         if (k % (fbA + fbB) < fbA) sa += v; else sb += v;
-#endif
     }
     sa = warp_sum(sa);
     sb = warp_sum(sb);
@@ -1289,10 +1237,6 @@ size_t filt_smem_bytes(int BN) {
 }  // namespace
 }  // namespace f3d
 
-#ifdef F3D_EXP_CLOCK
-extern "C" __attribute__((visibility("default"))) int f3d_debug_read(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, f3d::g_dbg, nbytes); }
-extern "C" __attribute__((visibility("default"))) int f3d_debug_read_fin(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, f3d::g_dbgf, nbytes); }
-#endif
 
 extern "C" size_t f3d_chamfer_workspace_bytes(int32_t B, int32_t N, int32_t M) {
     if (B <= 0 || N <= 0 || M <= 0) return 0;
@@ -1384,9 +1328,6 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
         const long long ntiles = (long long)fl.CS * fl.RB * B;
         if (ntiles > 0x7fffffffLL - 2048) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: too many tiles (%lld)", ntiles);
         unsigned G = (unsigned)(kSweepCtasPerSm > 0 ? std::min<long long>(ntiles, (long long)kSweepCtasPerSm * sms) : ntiles);
-#ifdef F3D_EXP_GRID_ENV
-        if (const char* g = getenv("F3D_SWEEP_G")) G = (unsigned)std::min<long long>(ntiles, atoll(g));  // development aid
-#endif
         const bool loop = G != (unsigned)ntiles;  // a persistent grid (experiments); else one tile per CTA, 3-D grid
         if (fl.RB > 65535 && !loop && !sp.up.U) return fail(F3D_ERR_INVALID, "f3d_chamfer_fwd: N too large");
         if (sp.up.U) {
@@ -1398,7 +1339,6 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
             if (loop) chamfer_filter_sweep_kernel<true><<<dim3(G), kThreads, smem, stream>>>(sp);
             else chamfer_filter_sweep_kernel<false><<<dim3(fl.CS, fl.RB, B), kThreads, smem, stream>>>(sp);
         } else {
-#ifndef F3D_EXP_NOPREP
             // many row blocks: prepare the operands once, then the sweep — launched programmatically, it waits
             // (griddepcontrol.wait) only where it first reads them (B=16 N=M=10000: 430 → 419 µs)
             float4* Ap = reinterpret_cast<float4*>(w + fl.off_Ap);
@@ -1415,9 +1355,6 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
             cfg.attrs = attr; cfg.numAttrs = 1;
             if (loop) F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_filter_sweep_kernel<true>, sp));
             else F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_filter_sweep_kernel<false>, sp));
-#else
-            chamfer_filter_sweep_kernel<true><<<dim3(G), kThreads, smem, stream>>>(sp);
-#endif
         }
         F3D_CHECK_LAUNCH("chamfer_filter_sweep_kernel");
         if (flags & F3D_FLAG_SWEEP_ONLY) return F3D_OK;
@@ -1442,11 +1379,7 @@ int32_t f3d::chamfer_fwd_launch(const float* A, const float* Bp, int32_t B, int3
             cfg.gridDim = dim3(fl.nbA + fl.nbB); cfg.blockDim = dim3(kFinThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-#ifdef F3D_EXP_NOPDL
-            attr[0].val.programmaticStreamSerializationAllowed = 0;
-#else
             attr[0].val.programmaticStreamSerializationAllowed = 1;
-#endif
             cfg.attrs = attr; cfg.numAttrs = 1;
             F3D_CUDA(cudaLaunchKernelEx(&cfg, chamfer_filter_finalize_kernel, fp));
         }

@@ -364,3 +364,15 @@ def test_every_launch_goes_to_the_callers_stream(f3d):
         assert host.item() == ref, (shape, host.item(), ref)
         assert dt < 0.5, dt
         torch.cuda.synchronize()
+
+
+def test_cfg5_shard_against_the_kdtree_loss(f3d, oracle):
+    """BASELINE configs[4] per-GPU shard (B=32, N=M=8192) against the reference's CPU algorithm itself: the float64 KD-tree
+    1-NN loss (src/metrics/pcloud.jl:54-70), tolerance 1e-5 — on the tensor-core sweep and on the CUDA-core sweep."""
+    A = np.random.default_rng(501).random((32, 8192, 3), dtype=np.float32)
+    Bc = np.random.default_rng(502).random((32, 8192, 3), dtype=np.float32)
+    ref = float(oracle.kdtree_chamfer(A, Bc, workers=-1))
+    tA, tB = torch.from_numpy(A).cuda(), torch.from_numpy(Bc).cuda()
+    for fl in (0, f3d.FLAG_CUDA_CORES):
+        got = f3d.chamfer_forward_raw(tA, tB, 1.0, 1.0, want_indices=False, flags=fl)[0].item()
+        assert abs(got - ref) <= 1e-5 * ref, (fl, got, ref)
