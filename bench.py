@@ -81,8 +81,7 @@ def global_reference_loss(wl, world):
 
 def tc_path(B, N, M):
     """Mirror of chamfer_tc_supported (csrc/chamfer_tc.cu): does f3d_chamfer_fwd take the tensor-core sweep for this shape?"""
-    items = B * ((N + 255) // 256 + (M + 255) // 256)
-    return items >= 2 * 148 and min(N, M) >= 512
+    return min(N, M) >= 512 and max(N, M) <= 131072
 
 
 SAMPLER_SRC = r"""

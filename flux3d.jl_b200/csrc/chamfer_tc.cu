@@ -1117,8 +1117,9 @@ extern "C" __attribute__((visibility("default"))) int f3d_debug_read_cert(void* 
 extern "C" __attribute__((visibility("default"))) int f3d_debug_read_clean(void* host, size_t nbytes) { return (int)cudaMemcpyFromSymbol(host, g_cleanprof, nbytes); }
 #endif
 
-// The tensor-core sweep wants enough 256-row work items to keep every SM's pipeline full for a few items; smaller problems
-// stay on the CUDA-core sweep of chamfer.cu (one tile per CTA fills the machine from 592 tiles of 256 x 1024 pairs on).
+// The tensor-core sweep is the default whenever both clouds have at least 512 points (measured against the CUDA-core sweep of
+// chamfer.cu, step time cold: 1 x 512² 20.5 vs 24.5 us, 1 x 1024² 21 vs 31, 8 x 1000² 23 vs 31, 4 x 2048² 25 vs 31, 64 x 1024² 47 vs 48;
+// below that the per-item set-up no longer pays: 4 x 300 x 517 33 vs 27, 1 x 2048 x 64 22.5 vs 16.5).
 bool chamfer_tc_possible(int B, int N, int M) {
     if (B <= 0 || N < 1 || M < 1) return false;
     const TcPlan pl = make_tc_plan(B, N, M);
@@ -1128,9 +1129,7 @@ bool chamfer_tc_possible(int B, int N, int M) {
 // host arrays through the sweep's own uploader warps: every 256-point tile of the raw clouds must be whole 16-byte units (TMA)
 bool chamfer_tc_upload_possible(int N, int M) { return (N & 3) == 0 && (M & 3) == 0; }
 bool chamfer_tc_supported(int B, int N, int M) {
-    if (!chamfer_tc_possible(B, N, M)) return false;
-    const TcPlan pl = make_tc_plan(B, N, M);
-    return (long long)B * (pl.rbA + pl.rbB) >= 2 * 148 && std::min(N, M) >= 512;
+    return chamfer_tc_possible(B, N, M) && std::min(N, M) >= 512;
 }
 
 int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N, int32_t M, float w1, float w2, int32_t B_total,

@@ -67,7 +67,7 @@ enum {
     F3D_FLAG_TENSOR = 8,
     /* f3d_chamfer_fwd: keep the filter sweep on the CUDA cores (packed-FP32 FFMA2 expanded form, chamfer.cu) also for
        problems large enough for the tensor-core sweep (tcgen05 split-TF32 filter, chamfer_tc.cu), which is the default
-       from 296 work items of 256 query rows on.  Results are bit-identical either way. */
+       when both clouds have at least 512 points.  Results are bit-identical either way. */
     F3D_FLAG_CUDA_CORES = 16,
     /* f3d_knn_graph: write edge_feat in the layout EdgeConv's 1x1-convolution MLP consumes — C [B][2F][N][K], i.e. the Julia
        (K*N, 2F, B) array of src/models/dgcnn.jl:46-52 — instead of [B][N][K][2F] == Julia (2F, K, N, B) (:45): the reference's
