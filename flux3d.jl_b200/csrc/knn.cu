@@ -468,9 +468,9 @@ extern "C" int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F
     // default for wide features (F >= 16, where evaluating the distances dominates): Gram matrix on the tensor cores
     // as a filter + exact re-evaluation (bit-identical results); narrow features are selection-bound and stay on the CUDA cores;
     // F3D_FLAG_EXACT_SWEEP or shapes outside that path: every pair in the reference arithmetic on the CUDA cores
-    // (first choice: the TMA-fed Gram filter of knn_gram.cu — point clouds (F <= 4, split-TF32 rows) and wide features — when
-    // the caller has brought its workspace)
-    if (!(flags & F3D_FLAG_EXACT_SWEEP) && (F <= 4 || F >= 16 || (flags & F3D_FLAG_TENSOR)) && knn_gram_supported(N, F, K) && ws &&
+    // (first choice: the TMA-fed Gram filter of knn_gram.cu — every F <= 64 (split-TF32 rows for F <= 4), N <= 2048 — when the
+    // caller has brought its workspace; cfg3-sized clouds with F = 5 ... 12: 48-62 us against 100-170 us on the CUDA cores)
+    if (!(flags & F3D_FLAG_EXACT_SWEEP) && knn_gram_supported(N, F, K) && ws &&
         ws_bytes >= knn_gram_workspace_bytes(B, N, F)) {
         const int32_t rc = knn_gram_launch(X, B, N, F, K, idx, dist, ws, ws_bytes, stream);
         if (rc != F3D_OK) return rc;

@@ -61,9 +61,10 @@ enum {
        of the default filter + certified exact re-evaluation.  Both produce bit-identical results; this
        one does not depend on the filter's error bound and is kept as the cross-check. */
     F3D_FLAG_EXACT_SWEEP = 4,
-    /* f3d_knn_graph: take the tensor-core (tcgen05) filter path whenever the shape allows it (N <= 1024, F <= 64,
-       K <= 31), also for narrow features (F < 16) where the CUDA-core kernel is the default because the work is
-       selection-bound.  Results are identical either way. */
+    /* f3d_knn_graph: take a tensor-core (tcgen05) filter path whenever the shape allows it.  With the workspace of
+       f3d_knn_graph_workspace_bytes that is the default anyway (knn_gram.cu: F <= 64, K <= 31, N <= 2048 and at least
+       1.5 (K+1) chunks of 16 / 32 candidates); the flag also selects the older cp.async-staged filter (knn_tc.cu, N <= 1024)
+       for narrow features (F < 16) when no workspace is given.  Results are identical either way. */
     F3D_FLAG_TENSOR = 8,
     /* f3d_chamfer_fwd: keep the filter sweep on the CUDA cores (packed-FP32 FFMA2 expanded form, chamfer.cu) also for
        problems large enough for the tensor-core sweep (tcgen05 split-TF32 filter, chamfer_tc.cu), which is the default
