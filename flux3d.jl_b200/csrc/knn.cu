@@ -401,9 +401,10 @@ namespace {
 // neighbour's row (one sector), the (slice x pairs) tile is transposed through shared memory, and every output channel row
 // of the tile — kEmitPts*K consecutive floats — leaves with coalesced stores.
 constexpr int kEmitPts = 32, kEmitFS = 8, kEmitThreads = 256;
+template <bool kVec>
 __global__ void __launch_bounds__(kEmitThreads) knn_edge_mlp_kernel(const float* __restrict__ X, const int32_t* __restrict__ idx, int N, int F, int K,
                                                                     float* __restrict__ E) {
-    extern __shared__ float s_t[];                       // [2][kEmitFS][NK]: centre halves, difference halves
+    extern __shared__ __align__(16) float s_t[];         // [2][kEmitFS][NK]: centre halves, difference halves
     const int b = blockIdx.y, n0 = blockIdx.x * kEmitPts;
     const int np = min(kEmitPts, N - n0), NK = np * K, NKp = kEmitPts * K;
     const float* Xb = X + (size_t)b * N * F;
@@ -414,22 +415,44 @@ __global__ void __launch_bounds__(kEmitThreads) knn_edge_mlp_kernel(const float*
             const int n = pr / K;
             const float* xi = Xb + (size_t)(n0 + n) * F + c0;
             const float* xj = Xb + (size_t)__ldg(ib + pr) * F + c0;
+            if (kVec && fs == kEmitFS) {   // (kVec: F % 4 == 0 and X 16-byte aligned — the 32-byte slice of a row is two aligned quads)
+                const float4 a0 = __ldg(reinterpret_cast<const float4*>(xi)), a1 = __ldg(reinterpret_cast<const float4*>(xi) + 1);
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(xj)), w1 = __ldg(reinterpret_cast<const float4*>(xj) + 1);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-            for (int c = 0; c < kEmitFS; ++c) {
-                if (c < fs) {
-                    const float a = __ldg(xi + c);
-                    s_t[c * NKp + pr] = a;
-                    s_t[(kEmitFS + c) * NKp + pr] = __fsub_rn(__ldg(xj + c), a);   // KNNGraph - X  (dgcnn.jl:45)
+                for (int c = 0; c < kEmitFS; ++c) {
+                    s_t[c * NKp + pr] = a[c];
+                    s_t[(kEmitFS + c) * NKp + pr] = __fsub_rn(w[c], a[c]);   // KNNGraph - X  (dgcnn.jl:45)
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < kEmitFS; ++c) {
+                    if (c < fs) {
+                        const float a = __ldg(xi + c);
+                        s_t[c * NKp + pr] = a;
+                        s_t[(kEmitFS + c) * NKp + pr] = __fsub_rn(__ldg(xj + c), a);   // KNNGraph - X  (dgcnn.jl:45)
+                    }
                 }
             }
         }
         __syncthreads();
-        for (int h = 0; h < 2; ++h)
-            for (int c = 0; c < fs; ++c) {
-                float* dst = E + (((size_t)b * 2 * F + (size_t)h * F + c0 + c) * N + n0) * K;
-                const float* src = s_t + (h * kEmitFS + c) * NKp;
-                for (int pr = threadIdx.x; pr < NK; pr += kEmitThreads) dst[pr] = src[pr];
+        if (kVec && (NK & 3) == 0) {
+            // every output channel row of the tile is NK consecutive floats, 16-byte aligned (kVec: (N * K) % 4 == 0, E aligned; n0 * K is a
+            // multiple of 32): 16-byte stores, all 2 * fs rows dealt round over the threads
+            const int q = NK >> 2, total = 2 * fs * q;
+            for (int e = threadIdx.x; e < total; e += kEmitThreads) {
+                const int row = e / q, i = e - row * q, h = row / fs, c = row - h * fs;
+                const float4 v = *reinterpret_cast<const float4*>(s_t + (h * kEmitFS + c) * NKp + 4 * i);
+                __stcs(reinterpret_cast<float4*>(E + (((size_t)b * 2 * F + (size_t)h * F + c0 + c) * N + n0) * K) + i, v);   // streaming: written once, read by the MLP later
             }
+        } else {
+            for (int h = 0; h < 2; ++h)
+                for (int c = 0; c < fs; ++c) {
+                    float* dst = E + (((size_t)b * 2 * F + (size_t)h * F + c0 + c) * N + n0) * K;
+                    const float* src = s_t + (h * kEmitFS + c) * NKp;
+                    for (int pr = threadIdx.x; pr < NK; pr += kEmitThreads) dst[pr] = src[pr];
+                }
+        }
         __syncthreads();
     }
 }
@@ -460,8 +483,14 @@ extern "C" int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F
         const int32_t rc = f3d_knn_graph(X, B, N, F, K, idx, dist, gathered, nullptr, ws, ws_bytes, flags & ~F3D_FLAG_EDGE_MLP_LAYOUT, stream_);
         if (rc != F3D_OK) return rc;
         const size_t smem = sizeof(float) * 2 * kEmitFS * kEmitPts * (size_t)K;
-        F3D_CUDA(cudaFuncSetAttribute(knn_edge_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_edge_mlp_kernel<<<dim3((N + kEmitPts - 1) / kEmitPts, B), kEmitThreads, smem, stream>>>(X, idx, N, F, K, edge_feat);
+        const bool vec = (F & 3) == 0 && (((size_t)N * K) & 3) == 0 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(edge_feat)) & 15) == 0;
+        if (vec) {
+            F3D_CUDA(cudaFuncSetAttribute(knn_edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            knn_edge_mlp_kernel<true><<<dim3((N + kEmitPts - 1) / kEmitPts, B), kEmitThreads, smem, stream>>>(X, idx, N, F, K, edge_feat);
+        } else {
+            F3D_CUDA(cudaFuncSetAttribute(knn_edge_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            knn_edge_mlp_kernel<false><<<dim3((N + kEmitPts - 1) / kEmitPts, B), kEmitThreads, smem, stream>>>(X, idx, N, F, K, edge_feat);
+        }
         F3D_CHECK_LAUNCH("knn_edge_mlp_kernel");
         return F3D_OK;
     }
