@@ -404,27 +404,57 @@ constexpr int kEmitPts = 32, kEmitFS = 8, kEmitThreads = 256;
 template <bool kVec>
 __global__ void __launch_bounds__(kEmitThreads) knn_edge_mlp_kernel(const float* __restrict__ X, const int32_t* __restrict__ idx, int N, int F, int K,
                                                                     float* __restrict__ E) {
-    extern __shared__ __align__(16) float s_t[];         // [2][kEmitFS][NK]: centre halves, difference halves
+    extern __shared__ __align__(16) float s_t[];         // [2][kEmitFS][NKp]: centre halves, difference halves; then the pairs' neighbour ids [NKp]
     const int b = blockIdx.y, n0 = blockIdx.x * kEmitPts;
     const int np = min(kEmitPts, N - n0), NK = np * K, NKp = kEmitPts * K;
+    int* s_idx = reinterpret_cast<int*>(s_t + 2 * kEmitFS * NKp);
     const float* Xb = X + (size_t)b * N * F;
     const int32_t* ib = idx + ((size_t)b * N + n0) * K;
+    for (int pr = threadIdx.x; pr < NK; pr += kEmitThreads) s_idx[pr] = __ldg(ib + pr);   // once per CTA, not once per feature slice
+    __syncthreads();
+    constexpr int kPP = 3;   // pairs per thread and slice (kEmitPts * K <= 768 on the vector path)
+    float4 w0[kPP], w1[kPP];
+    // (vector path) the gathers of a slice are issued before the previous slice's tile is written out: their L2 round trip overlaps the stores
+    auto gather = [&](int c0) {
+#pragma unroll
+        for (int u = 0; u < kPP; ++u) {
+            const int pr = threadIdx.x + u * kEmitThreads;
+            if (pr < NK) {
+                const float4* xj = reinterpret_cast<const float4*>(Xb + (size_t)s_idx[pr] * F + c0);
+                w0[u] = __ldg(xj); w1[u] = __ldg(xj + 1);
+            }
+        }
+    };
+    const bool fast = kVec && (F % kEmitFS) == 0 && NKp <= kPP * kEmitThreads && (NK & 3) == 0;
+    int pn[kPP];   // the pairs' own points (no division per slice)
+#pragma unroll
+    for (int u = 0; u < kPP; ++u) pn[u] = n0 + min(threadIdx.x + u * kEmitThreads, (unsigned)max(NK - 1, 0)) / K;
+    // the thread's first output unit (row, 16-byte column) and its step of kEmitThreads units, without divisions in the loop
+    const int q = max(NK >> 2, 1), row0 = threadIdx.x / q, col0 = threadIdx.x - row0 * q, drow = kEmitThreads / q, dcol = kEmitThreads - drow * q;
+    if (fast) gather(0);
     for (int c0 = 0; c0 < F; c0 += kEmitFS) {
         const int fs = min(kEmitFS, F - c0);
-        for (int pr = threadIdx.x; pr < NK; pr += kEmitThreads) {
-            const int n = pr / K;
-            const float* xi = Xb + (size_t)(n0 + n) * F + c0;
-            const float* xj = Xb + (size_t)__ldg(ib + pr) * F + c0;
-            if (kVec && fs == kEmitFS) {   // (kVec: F % 4 == 0 and X 16-byte aligned — the 32-byte slice of a row is two aligned quads)
-                const float4 a0 = __ldg(reinterpret_cast<const float4*>(xi)), a1 = __ldg(reinterpret_cast<const float4*>(xi) + 1);
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(xj)), w1 = __ldg(reinterpret_cast<const float4*>(xj) + 1);
-                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        if (fast) {
 #pragma unroll
-                for (int c = 0; c < kEmitFS; ++c) {
-                    s_t[c * NKp + pr] = a[c];
-                    s_t[(kEmitFS + c) * NKp + pr] = __fsub_rn(w[c], a[c]);   // KNNGraph - X  (dgcnn.jl:45)
+            for (int u = 0; u < kPP; ++u) {
+                const int pr = threadIdx.x + u * kEmitThreads;
+                if (pr < NK) {
+                    const float4* xi = reinterpret_cast<const float4*>(Xb + (size_t)pn[u] * F + c0);   // (the K pairs of a point: L1 hits)
+                    const float4 a0 = __ldg(xi), a1 = __ldg(xi + 1);
+                    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const float w[8] = {w0[u].x, w0[u].y, w0[u].z, w0[u].w, w1[u].x, w1[u].y, w1[u].z, w1[u].w};
+#pragma unroll
+                    for (int c = 0; c < kEmitFS; ++c) {
+                        s_t[c * NKp + pr] = a[c];
+                        s_t[(kEmitFS + c) * NKp + pr] = __fsub_rn(w[c], a[c]);   // KNNGraph - X  (dgcnn.jl:45)
+                    }
                 }
-            } else {
+            }
+            if (c0 + kEmitFS < F) gather(c0 + kEmitFS);
+        } else {
+            for (int pr = threadIdx.x; pr < NK; pr += kEmitThreads) {
+                const float* xi = Xb + (size_t)(n0 + pr / K) * F + c0;
+                const float* xj = Xb + (size_t)s_idx[pr] * F + c0;
 #pragma unroll
                 for (int c = 0; c < kEmitFS; ++c) {
                     if (c < fs) {
@@ -439,11 +469,12 @@ __global__ void __launch_bounds__(kEmitThreads) knn_edge_mlp_kernel(const float*
         if (kVec && (NK & 3) == 0) {
             // every output channel row of the tile is NK consecutive floats, 16-byte aligned (kVec: (N * K) % 4 == 0, E aligned; n0 * K is a
             // multiple of 32): 16-byte stores, all 2 * fs rows dealt round over the threads
-            const int q = NK >> 2, total = 2 * fs * q;
-            for (int e = threadIdx.x; e < total; e += kEmitThreads) {
-                const int row = e / q, i = e - row * q, h = row / fs, c = row - h * fs;
+            for (int row = row0, i = col0; row < 2 * fs; ) {
+                const int h = row >= fs ? 1 : 0, c = row - h * fs;
                 const float4 v = *reinterpret_cast<const float4*>(s_t + (h * kEmitFS + c) * NKp + 4 * i);
                 __stcs(reinterpret_cast<float4*>(E + (((size_t)b * 2 * F + (size_t)h * F + c0 + c) * N + n0) * K) + i, v);   // streaming: written once, read by the MLP later
+                row += drow; i += dcol;
+                if (i >= q) { i -= q; ++row; }
             }
         } else {
             for (int h = 0; h < 2; ++h)
@@ -482,7 +513,7 @@ extern "C" int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F
         // neighbour search without the (2F,K,N,B) edge tensor, then the edge features once, in the MLP's layout
         const int32_t rc = f3d_knn_graph(X, B, N, F, K, idx, dist, gathered, nullptr, ws, ws_bytes, flags & ~F3D_FLAG_EDGE_MLP_LAYOUT, stream_);
         if (rc != F3D_OK) return rc;
-        const size_t smem = sizeof(float) * 2 * kEmitFS * kEmitPts * (size_t)K;
+        const size_t smem = sizeof(float) * (2 * kEmitFS + 1) * kEmitPts * (size_t)K;
         const bool vec = (F & 3) == 0 && (((size_t)N * K) & 3) == 0 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(edge_feat)) & 15) == 0;
         if (vec) {
             F3D_CUDA(cudaFuncSetAttribute(knn_edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
