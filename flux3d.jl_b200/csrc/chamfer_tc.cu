@@ -168,20 +168,6 @@ __device__ __forceinline__ void tmem_ld_wait(unsigned (&r)[32]) {
                  :
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld16_issue(unsigned taddr, unsigned (&r)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-                   "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait16(unsigned (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
-                   "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :
-                 : "memory");
-}
 __device__ __forceinline__ int ld_acquire_i32(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -195,12 +181,6 @@ __device__ __forceinline__ float min32(const unsigned (&r)[32]) {
     t[10] = fminf(__uint_as_float(r[30]), __uint_as_float(r[31]));
     const float u0 = min3(t[0], t[1], t[2]), u1 = min3(t[3], t[4], t[5]), u2 = min3(t[6], t[7], t[8]), u3 = fminf(t[9], t[10]);
     return fminf(min3(u0, u1, u2), u3);
-}
-__device__ __forceinline__ float min16(const unsigned (&r)[16]) {
-    float t[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) t[i] = min3(__uint_as_float(r[3 * i]), __uint_as_float(r[3 * i + 1]), __uint_as_float(r[3 * i + 2]));
-    return min3(min3(t[0], t[1], t[2]), fminf(t[3], t[4]), __uint_as_float(r[15]));
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // K-major SWIZZLE_64B operand descriptor (cute::UMMA::make_umma_desc<Major::K>, LayoutType::B64): rows of 64 B, the
@@ -256,15 +236,6 @@ __device__ __forceinline__ void loc3_insert(Loc3& l, float m, int chunk) {   // 
     l.c1 = lt1 ? chunk : l.c1;
     l.b1 = fminf(l.b1, m);
 }
-__device__ __forceinline__ float4 loc3_pack(const Loc3& l) { return make_float4(l.b1, l.b2, l.b3, __int_as_float(l.c1 | (l.c2 << 16))); }
-__device__ __forceinline__ Loc3 loc3_unpack(const float4 v) {
-    Loc3 l;
-    l.b1 = v.x; l.b2 = v.y; l.b3 = v.z;
-    const int pk = __float_as_int(v.w);
-    l.c1 = pk & 0xffff; l.c2 = (pk >> 16) & 0xffff;
-    return l;
-}
-
 // ---- prepare: compact operands {x', y', z', |p'|²} of both clouds, once per call ---------------------------------------
 struct TcPrepParams {
     const float* A;    // [B][N][3]
@@ -472,13 +443,13 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
                             mbar_arrive(&cfull[s]);   // a tile of padding only
                         }
                     }
-                    continue;
-                }
-                for (int t = -1; t < ntiles; ++t, ++h) {   // t = -1: the item's 256 query rows
-                    const unsigned s = h % kCStages, n = h / kCStages;
-                    mbar_wait(&cempty[s], (n & 1) ^ 1);
-                    mbar_expect_tx(&cfull[s], kTNc * 16);
-                    tma_bulk_g2s(s_c + s * kTNc, t < 0 ? Pq : Pc + (size_t)t * kTNc, kTNc * 16, &cfull[s]);
+                } else {
+                    for (int t = -1; t < ntiles; ++t, ++h) {   // t = -1: the item's 256 query rows
+                        const unsigned s = h % kCStages, n = h / kCStages;
+                        mbar_wait(&cempty[s], (n & 1) ^ 1);
+                        mbar_expect_tx(&cfull[s], kTNc * 16);
+                        tma_bulk_g2s(s_c + s * kTNc, t < 0 ? Pq : Pc + (size_t)t * kTNc, kTNc * 16, &cfull[s]);
+                    }
                 }
             }
         }
