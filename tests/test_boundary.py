@@ -149,3 +149,22 @@ def test_workspace_size_queries_are_host_only(f3d):
     assert L.f3d_chamfer_pipe_workspace_bytes(32, 0, 4096) == 0
     # ragged shapes: pads inside the last row block / column tile are accounted for
     assert L.f3d_chamfer_workspace_bytes(3, 257, 1025) >= L.f3d_chamfer_workspace_bytes(3, 256, 1024)
+
+
+def test_workspace_sizes_are_host_only_and_sane(f3d):
+    """The *_workspace_bytes entry points are pure host arithmetic (no CUDA call): callable on a machine without a GPU, monotone in
+    the batch size, and the kNN workspace exists exactly where the TMA-fed Gram-filter path (knn_gram.cu) can serve the shape."""
+    L = f3d._lib.lib()
+    c2 = L.f3d_chamfer_workspace_bytes(32, 4096, 4096)
+    assert 0 < c2 < (1 << 28)
+    assert L.f3d_chamfer_workspace_bytes(64, 4096, 4096) > c2 > L.f3d_chamfer_workspace_bytes(8, 4096, 4096)
+    assert L.f3d_chamfer_pipe_workspace_bytes(32, 4096, 4096) >= c2 + 2 * 32 * 4096 * 12    # + the two staging copies
+    # kNN: (B, N, F, K)
+    k3 = L.f3d_knn_graph_workspace_bytes(32, 1024, 3, 20)
+    k64 = L.f3d_knn_graph_workspace_bytes(32, 1024, 64, 20)
+    assert k3 >= 32 * 1024 * 128 and k64 >= 32 * 1024 * 256            # the operand image: 128 bytes per point and 32 features
+    assert k64 > k3
+    for shape in ((32, 4096, 3, 20), (32, 1024, 100, 20), (32, 1024, 3, 40), (2, 100, 3, 20)):   # N > 2048, F > 64, K > 31, too few chunks
+        assert L.f3d_knn_graph_workspace_bytes(*shape) == 256
+    assert L.f3d_sample_points_workspace_bytes(16, 2256) == 0           # the CDF fits in shared memory: fused path
+    assert L.f3d_sample_points_workspace_bytes(4, 100000) >= 4 * 100000 * 8
