@@ -25,8 +25,8 @@
 //              is still in shared memory (the image holds the exact FP32 values): no gather from L2, balanced over the
 //              lanes of the warp that found the hits
 //   ranking  every candidate finds its output slot by counting the (distance, index) keys below it
-// Rows whose candidate set overflows (> 64: heavy ties, degenerate clouds) are listed and redone by knn_gram_fixup_kernel
-// (exact scan of the whole cloud).
+// Rows whose candidate set overflows (> 64: heavy ties, degenerate clouds) are redone at the end of the same CTA by an exact scan
+// of the whole cloud.  Two launches per call (prepare, search), no memset.
 #include <algorithm>
 
 #include "f3d_common.cuh"
@@ -52,11 +52,10 @@ struct KnnGramParams {
     int Np, ntiles, halves, ksteps, split, fold;
     unsigned char* img;        // [B][ntiles][halves][256][128 B]
     float* nrm;                // [B][Np]   squared norms (+inf past N)
-    unsigned* maxn;            // [B]       largest squared norm of the cloud (float bits)
+    float* tmax;               // [B][ntiles] largest squared norm of every tile (the search takes the maximum over a cloud's tiles)
     int32_t* idx;              // [B][N][K]
     float* dist;               // [B][N][K] or null
-    unsigned* stats;           // [0] rows redone by the exact scan, [1] candidates re-evaluated exactly, [2] fixup list length
-    int* fixlist;              // [B*N]     rows for knn_gram_fixup_kernel
+    unsigned* stats;           // [0] rows redone by the exact scan, [1] candidates re-evaluated exactly, [3..5] why, [7] = 2: this path served the call
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
@@ -202,12 +201,19 @@ __global__ void __launch_bounds__(kGN) knn_gram_prepare_kernel(KnnGramParams p) 
                 *reinterpret_cast<float4*>(tile + (size_t)h * kGHalf + swz(r, c)) = v;
             }
     }
-    if (t == 0 && b == 0 && r == 0) p.stats[7] = 2u;   // diagnostics: this path served the call
+    if (t == 0 && b == 0 && r < 8) p.stats[r] = r == 7 ? 2u : 0u;   // diagnostics (the search grid only counts after this grid has ended); [7]: this path served the call
     p.nrm[(size_t)b * p.Np + j] = live ? n : INFINITY;
+    __shared__ float s_m[kGN / 32];
     float m = live ? n : 0.0f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(p.maxn + b, __float_as_uint(m));   // norms are >= 0: bit order == value order
+    if ((r & 31) == 0) s_m[r >> 5] = m;
+    __syncthreads();
+    if (r == 0) {
+#pragma unroll
+        for (int w = 1; w < kGN / 32; ++w) m = fmaxf(m, s_m[w]);
+        p.tmax[(size_t)b * p.ntiles + t] = m;   // no atomics, nothing to zero: the call needs no memset
+    }
 }
 
 // exact (reference-arithmetic) squared distance between row r of the query tile and row c of a candidate tile, both in
@@ -315,12 +321,12 @@ __global__ void __launch_bounds__(kGThreads, 1) knn_gram_kernel(KnnGramParams p)
     int* s_cnt = reinterpret_cast<int*>(s_thr + kGQ);                 // [128] candidates per query
     int* s_ovf = s_cnt + kGQ;                                         // [128] the query's candidate set is incomplete
     int* s_segcnt = s_ovf + kGQ;                                      // [16]
-    __shared__ unsigned long long a_full, full_b[2], empty_b[2], tfull[2], tempty[2];
+    __shared__ unsigned long long a_full, full_b[2], empty_b[2], tfull[2], tempty[2], s_key[2][8];
     __shared__ unsigned s_tmem;
+    __shared__ int s_nfix;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, q0 = blockIdx.x * kGQ;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the fixup grid may be set up (it waits for this grid's end)
     const int ntiles = p.ntiles, L = 2 * ntiles;
     const unsigned char* cloud = p.img + (size_t)b * ntiles * b_tile;
     if (tid == 0) {
@@ -331,6 +337,7 @@ __global__ void __launch_bounds__(kGThreads, 1) knn_gram_kernel(KnnGramParams p)
     if (warp == 0) tmem_alloc(&s_tmem, 2 * kGN);
     for (int i = tid; i < kGQ; i += kGThreads) { s_cnt[i] = 0; s_ovf[i] = 0; }
     if (tid < kGReadWarps) s_segcnt[tid] = 0;
+    if (tid == 0) s_nfix = 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");   // launched programmatically behind the prepare grid: the image is complete
     for (int i = tid; i < p.Np; i += kGThreads) s_nc[i] = __ldcg(p.nrm + (size_t)b * p.Np + i);
     tc_fence_before();
@@ -402,7 +409,9 @@ __global__ void __launch_bounds__(kGThreads, 1) knn_gram_kernel(KnnGramParams p)
                         const float a = ia < 32 ? s_dex[ia * kGQ + row] : INFINITY, bb = ib < ibend ? s_dex[ib * kGQ + row] : INFINITY;
                         if (a <= bb) { Tsel = a; ++ia; } else { Tsel = bb; ++ib; }
                     }
-                    const float nq = s_nc[min(q0 + row, p.Np - 1)], maxnc = __uint_as_float(__ldcg(p.maxn + b));
+                    const float nq = s_nc[min(q0 + row, p.Np - 1)];
+                    float maxnc = 0.0f;
+                    for (int tt = 0; tt < ntiles; ++tt) maxnc = fmaxf(maxnc, __ldcg(p.tmax + (size_t)b * ntiles + tt));
                     // E bounds |d' - (d - nq)|: the Gram entry's relative error on |q||c| plus the FP32 roundings of the norms and of the
                     // fma, which do not shrink with |q| (<= (F + 3) u (nq + max nc), doubled for slack)
                     const float E = (p.split ? kGErrSplit : kGErrPlain) * sqrtf(nq) * sqrtf(maxnc) + 2.0f * (float)(p.F + 4) * 5.9604645e-8f * (nq + maxnc);
@@ -528,7 +537,7 @@ __global__ void __launch_bounds__(kGThreads, 1) knn_gram_kernel(KnnGramParams p)
                 if (part == 0) {
                     atomicAdd(p.stats, 1u);
                     atomicAdd(p.stats + (cnt > kGCap ? 3 : (s_ovf[row] ? 4 : 5)), 1u);
-                    p.fixlist[atomicAdd(p.stats + 2, 1u)] = b * p.N + qi;
+                    reinterpret_cast<int*>(s_seg)[atomicAdd(&s_nfix, 1)] = row;   // (the hit segments are no longer needed)
                 }
             } else {
                 // the thread's own candidates (every fourth) live in registers as 64-bit keys (distance bits : index — distances
@@ -539,6 +548,50 @@ __global__ void __launch_bounds__(kGThreads, 1) knn_gram_kernel(KnnGramParams p)
                 else rank_row<16>(s_dex, s_cand, row, part, cnt, p.K, p.idx + obase, p.dist ? p.dist + obase : nullptr);
             }
         }
+        // ---- rows whose candidate set is incomplete (> 64 candidates: heavy ties, degenerate clouds; a threshold that is not finite):
+        // the exact scan of the whole cloud, here — two groups of eight warps take a row each: all its distances into shared memory
+        // (the candidate-tile ring is free now), then K + 1 selection rounds over 64-bit (distance bits : index) keys -------------------
+        named_bar_sync(1, kGReadWarps * 32);
+        const int nfix = s_nfix;
+        if (nfix) {
+            const int grp = warp >> 3, gt = tid & 255, gw = warp & 7;
+            float* sd = reinterpret_cast<float*>(s_b + (size_t)grp * b_tile);   // [N] (N <= 2048: 8 KB of a >= 32 KB stage)
+            const float* Xb = p.X + (size_t)b * p.N * p.F;
+            for (int e = grp; e < nfix; e += 2) {
+                const int qf = q0 + reinterpret_cast<const int*>(s_seg)[e];
+                const float* xq = Xb + (size_t)qf * p.F;
+                for (int j = gt; j < p.N; j += 256) {
+                    const float* xj = Xb + (size_t)j * p.F;
+                    float sum = 0.0f;
+                    for (int d = 0; d < p.F; ++d) { const float t = __fsub_rn(__ldg(xq + d), __ldg(xj + d)); sum = __fadd_rn(sum, __fmul_rn(t, t)); }
+                    sd[j] = sum;
+                }
+                named_bar_sync(2 + grp, 256);
+                unsigned long long last = 0ull;   // keys are (distance bits << 32 | index) + 1: strictly increasing from round to round
+                for (int r = 0; r <= p.K; ++r) {
+                    unsigned long long best = ~0ull;
+                    for (int j = gt; j < p.N; j += 256) {
+                        const unsigned long long key = (((unsigned long long)__float_as_uint(sd[j]) << 32) | (unsigned)j) + 1ull;   // d >= 0 (or NaN: sorts last)
+                        if (key > last && key < best) best = key;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { const unsigned long long ot = __shfl_xor_sync(0xffffffffu, best, o); best = ot < best ? ot : best; }
+                    if (lane == 0) s_key[grp][gw] = best;
+                    named_bar_sync(2 + grp, 256);
+                    best = s_key[grp][0];
+#pragma unroll
+                    for (int w = 1; w < 8; ++w) best = s_key[grp][w] < best ? s_key[grp][w] : best;
+                    named_bar_sync(2 + grp, 256);
+                    last = best;
+                    if (gt == 0 && r >= 1 && best != ~0ull) {
+                        const unsigned long long key = best - 1ull;
+                        const size_t o = ((size_t)b * p.N + qf) * p.K + r - 1;
+                        p.idx[o] = (int32_t)(key & 0xffffffffu);
+                        if (p.dist) p.dist[o] = __uint_as_float((unsigned)(key >> 32));
+                    }
+                }
+            }
+        }
     }
     GPROF(5);
     tc_fence_before();
@@ -546,55 +599,9 @@ __global__ void __launch_bounds__(kGThreads, 1) knn_gram_kernel(KnnGramParams p)
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 2 * kGN); }
 }
 
-// ---- fixup: the listed rows, exactly; CTA <-> row (strided): all distances into shared memory, then K + 1 selection rounds ---
-constexpr int kFixT = 256;
-__global__ void __launch_bounds__(kFixT) knn_gram_fixup_kernel(KnnGramParams p) {
-    extern __shared__ float s_d[];   // [N]
-    __shared__ unsigned long long s_key[kFixT / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // launched programmatically behind the search grid
-    const int nfix = (int)__ldcg(p.stats + 2);
-    for (int e = blockIdx.x; e < nfix; e += gridDim.x) {
-        const int bq = __ldcg(p.fixlist + e), b = bq / p.N, qi = bq - b * p.N;
-        const float* Xb = p.X + (size_t)b * p.N * p.F;
-        const float* xq = Xb + (size_t)qi * p.F;
-        for (int j = tid; j < p.N; j += kFixT) {
-            const float* xj = Xb + (size_t)j * p.F;
-            float s = 0.0f;
-            for (int d = 0; d < p.F; ++d) { const float t = __fsub_rn(__ldg(xq + d), __ldg(xj + d)); s = __fadd_rn(s, __fmul_rn(t, t)); }
-            s_d[j] = s;
-        }
-        __syncthreads();
-        unsigned long long last = 0ull;   // keys are (distance bits << 32 | index) + 1: strictly increasing from round to round
-        for (int r = 0; r <= p.K; ++r) {
-            unsigned long long best = ~0ull;
-            for (int j = tid; j < p.N; j += kFixT) {
-                const unsigned long long key = (((unsigned long long)__float_as_uint(s_d[j]) << 32) | (unsigned)j) + 1ull;   // d >= 0 (or NaN: sorts last)
-                if (key > last && key < best) best = key;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { const unsigned long long ot = __shfl_xor_sync(0xffffffffu, best, o); best = ot < best ? ot : best; }
-            if (lane == 0) s_key[warp] = best;
-            __syncthreads();
-            best = s_key[0];
-#pragma unroll
-            for (int w = 1; w < kFixT / 32; ++w) best = s_key[w] < best ? s_key[w] : best;
-            __syncthreads();
-            last = best;
-            if (tid == 0 && r >= 1 && best != ~0ull) {
-                const unsigned long long key = best - 1ull;
-                const size_t o = ((size_t)b * p.N + qi) * p.K + r - 1;
-                p.idx[o] = (int32_t)(key & 0xffffffffu);
-                if (p.dist) p.dist[o] = __uint_as_float((unsigned)(key >> 32));
-            }
-        }
-        __syncthreads();
-    }
-}
-
 struct GramPlan {
     int Np, ntiles, halves, ksteps, split, fold;
-    size_t off_stats, off_maxn, off_nrm, off_fix, off_img, total;
+    size_t off_stats, off_tmax, off_nrm, off_img, total;
 };
 GramPlan make_gram_plan(int B, int N, int F) {
     GramPlan pl;
@@ -606,9 +613,8 @@ GramPlan make_gram_plan(int B, int N, int F) {
     pl.ksteps = pl.split ? 2 : (F + 7) / 8;
     size_t o = 0;
     pl.off_stats = o; o = align_up(o + 64, 256);
-    pl.off_maxn = o;  o = align_up(o + sizeof(unsigned) * (size_t)B, 256);
-    pl.off_nrm = o;   o = align_up(o + sizeof(float) * (size_t)B * pl.Np, 256);
-    pl.off_fix = o;   o = align_up(o + sizeof(int) * (size_t)B * N, 1024);
+    pl.off_tmax = o;  o = align_up(o + sizeof(float) * (size_t)B * pl.ntiles, 256);
+    pl.off_nrm = o;   o = align_up(o + sizeof(float) * (size_t)B * pl.Np, 1024);
     pl.off_img = o;   o = align_up(o + (size_t)B * pl.ntiles * pl.halves * kGHalf, 256);
     pl.total = o;
     return pl;
@@ -637,17 +643,15 @@ int32_t knn_gram_launch(const float* X, int B, int N, int F, int K, int32_t* idx
     p.Np = pl.Np; p.ntiles = pl.ntiles; p.halves = pl.halves; p.ksteps = pl.ksteps; p.split = pl.split; p.fold = pl.fold;
     p.img = w + pl.off_img;
     p.nrm = reinterpret_cast<float*>(w + pl.off_nrm);
-    p.maxn = reinterpret_cast<unsigned*>(w + pl.off_maxn);
+    p.tmax = reinterpret_cast<float*>(w + pl.off_tmax);
     p.idx = idx; p.dist = dist;
     p.stats = reinterpret_cast<unsigned*>(w + pl.off_stats);
-    p.fixlist = reinterpret_cast<int*>(w + pl.off_fix);
     const size_t smem = gram_smem_bytes(pl.halves);
     static bool attr_done[2];
     if (!attr_done[pl.halves - 1]) {
         F3D_CUDA(cudaFuncSetAttribute(knn_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_smem_bytes(2)));
         attr_done[0] = attr_done[1] = true;
     }
-    F3D_CUDA(cudaMemsetAsync(w, 0, pl.off_nrm, stream));   // diagnostics, fixup counter, norm maxima
     knn_gram_prepare_kernel<<<dim3(pl.ntiles, B), kGN, 0, stream>>>(p);
     F3D_CHECK_LAUNCH("knn_gram_prepare_kernel");
     {
@@ -660,16 +664,6 @@ int32_t knn_gram_launch(const float* X, int B, int N, int F, int K, int32_t* idx
         F3D_CUDA(cudaLaunchKernelEx(&cfg, knn_gram_kernel, p));
     }
     F3D_CHECK_LAUNCH("knn_gram_kernel");
-    {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(148); cfg.blockDim = dim3(kFixT); cfg.dynamicSmemBytes = sizeof(float) * (size_t)N; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        F3D_CUDA(cudaLaunchKernelEx(&cfg, knn_gram_fixup_kernel, p));
-    }
-    F3D_CHECK_LAUNCH("knn_gram_fixup_kernel");
     return F3D_OK;
 }
 

@@ -178,7 +178,7 @@ def test_knn_gram_path(f3d, oracle, B, N, F, K):
 
 
 def test_knn_gram_degenerate_inputs(f3d, oracle):
-    """Heavy ties and clustered clouds overflow the candidate slots: those rows are redone by the exact scan (fixup kernel);
+    """Heavy ties and clustered clouds overflow the candidate slots: those rows are redone by the exact scan at the end of their CTA;
     zero rows and huge offsets must not be certified wrongly."""
     rng = np.random.default_rng(77)
     lattice = rng.integers(0, 4, size=(2, 1100, 3)).astype(np.float32)                    # ~17 copies of every point

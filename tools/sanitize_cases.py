@@ -51,7 +51,7 @@ for (B, N, M) in ((2, 500, 70), (1, 2100, 40), (1, 24600, 64)):
     tA, tB = cloud(B, N, 3).requires_grad_(True), cloud(B, M, 3).requires_grad_(True)
     f3d.chamfer_distance(tA, tB).backward()
 # kNN graph: CUDA-core kernel (narrow / wide), tensor-core kernel, gathered / edge outputs, MLP layout, gradient
-# knn_gram (TMA-fed Gram filter: split rows F <= 4, plain rows; its prepare / fixup kernels: the lattice cloud overflows the slots)
+# knn_gram (TMA-fed Gram filter: split rows F <= 4, plain rows; its prepare kernel and in-CTA exact scan: the lattice cloud overflows the slots)
 for (B, N, F, K, fl) in ((2, 200, 3, 10, 0), (1, 300, 20, 33, 0), (2, 256, 64, 20, 0), (1, 130, 3, 5, f3d.FLAG_TENSOR), (2, 600, 3, 10, 0), (1, 520, 40, 9, 0)):
     X = torch.from_numpy(rng.standard_normal((B, N, F)).astype(np.float32)).cuda()
     f3d.knn_graph(X, K, want_dist=True, want_gathered=True, want_edge=True, flags=fl)
