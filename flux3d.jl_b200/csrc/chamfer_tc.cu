@@ -245,14 +245,15 @@ struct TcPrepParams {
     float4* PB;        // [B][NpB]
     unsigned* maxn;    // [2][B]  max |p'|² per cloud and batch element (float bits; zeroed before the launch)
 };
-constexpr int kPrepT = 256;
+constexpr int kPrepT = 256, kPrepPts = 4;   // thread <-> four consecutive points: 48 bytes in, 64 bytes out
 __global__ void __launch_bounds__(kPrepT) chamfer_tc_prepare_kernel(TcPrepParams p) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the sweep's set-up overlaps this grid; it waits before it reads
     const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.y;
     const bool isA = blockIdx.z == 0;
     const int n = isA ? p.N : p.M, np = isA ? p.NpA : p.NpB;
-    if ((int)blockIdx.x * kPrepT >= np) return;
+    const int i0 = ((int)blockIdx.x * kPrepT + tid) * kPrepPts;
+    if ((int)blockIdx.x * kPrepT * kPrepPts >= np) return;
     const float* gA = p.A + (size_t)b * p.N * 3;
     const float* gB = p.Bp + (size_t)b * p.M * 3;
     // the centre of the batch element: the mean of 32 + 32 strided sample points (any point works — the certificate uses the
@@ -261,9 +262,18 @@ __global__ void __launch_bounds__(kPrepT) chamfer_tc_prepare_kernel(TcPrepParams
     float cx = __ldg(gA + 3 * ia) + __ldg(gB + 3 * ib);
     float cy = __ldg(gA + 3 * ia + 1) + __ldg(gB + 3 * ib + 1);
     float cz = __ldg(gA + 3 * ia + 2) + __ldg(gB + 3 * ib + 2);
-    const int i = blockIdx.x * kPrepT + tid;
-    const float* src = (isA ? gA : gB) + 3 * (size_t)min(i, n - 1);
-    const float rx = __ldg(src), ry = __ldg(src + 1), rz = __ldg(src + 2);
+    const float* src = (isA ? gA : gB) + 3 * (size_t)i0;
+    float r[3 * kPrepPts];
+    if (i0 + kPrepPts <= n && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src) + 1), v2 = __ldg(reinterpret_cast<const float4*>(src) + 2);
+        r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w; r[4] = v1.x; r[5] = v1.y; r[6] = v1.z; r[7] = v1.w; r[8] = v2.x; r[9] = v2.y; r[10] = v2.z; r[11] = v2.w;
+    } else {
+#pragma unroll
+        for (int u = 0; u < kPrepPts; ++u) {
+            const float* s1 = (isA ? gA : gB) + 3 * (size_t)min(i0 + u, n - 1);
+            r[3 * u] = __ldg(s1); r[3 * u + 1] = __ldg(s1 + 1); r[3 * u + 2] = __ldg(s1 + 2);
+        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         cx += __shfl_xor_sync(0xffffffffu, cx, o);
@@ -271,13 +281,19 @@ __global__ void __launch_bounds__(kPrepT) chamfer_tc_prepare_kernel(TcPrepParams
         cz += __shfl_xor_sync(0xffffffffu, cz, o);
     }
     cx *= (1.0f / 64.0f); cy *= (1.0f / 64.0f); cz *= (1.0f / 64.0f);
-    float x = 0.f, y = 0.f, z = 0.f, nrm = kPadN, mx = 0.f;
-    if (i < n) {
-        x = rx - cx; y = ry - cy; z = rz - cz;
-        nrm = fmaf(z, z, fmaf(y, y, x * x));
-        mx = nrm;
+    float mx = 0.f;
+    float4* dst = (isA ? p.PA : p.PB) + (size_t)b * np;
+#pragma unroll
+    for (int u = 0; u < kPrepPts; ++u) {
+        const int i = i0 + u;
+        float x = 0.f, y = 0.f, z = 0.f, nrm = kPadN;
+        if (i < n) {
+            x = r[3 * u] - cx; y = r[3 * u + 1] - cy; z = r[3 * u + 2] - cz;
+            nrm = fmaf(z, z, fmaf(y, y, x * x));
+            mx = fmaxf(mx, nrm);
+        }
+        if (i < np) dst[i] = make_float4(x, y, z, nrm);
     }
-    if (i < np) (isA ? p.PA : p.PB)[(size_t)b * np + i] = make_float4(x, y, z, nrm);
     mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));  // norms are >= 0 (NaN bits order above everything: caught by the limit test)
     if (lane == 0) atomicMax(p.maxn + (size_t)(isA ? 0 : 1) * gridDim.y + b, __float_as_uint(mx));
 }
@@ -1138,7 +1154,7 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
     if (upload && ((long long)B * N * 3 >= 0x7fffffffLL || (long long)B * M * 3 >= 0x7fffffffLL))
         return fail(F3D_ERR_INVALID, "chamfer_tc_launch: batch too large for the in-grid upload");
     if (!upload) {
-        chamfer_tc_prepare_kernel<<<dim3((std::max(pl.NpA, pl.NpB) + kPrepT - 1) / kPrepT, B, 2), kPrepT, 0, stream>>>(pp);
+        chamfer_tc_prepare_kernel<<<dim3((std::max(pl.NpA, pl.NpB) + kPrepT * kPrepPts - 1) / (kPrepT * kPrepPts), B, 2), kPrepT, 0, stream>>>(pp);
         F3D_CHECK_LAUNCH("chamfer_tc_prepare_kernel");
     }
 
