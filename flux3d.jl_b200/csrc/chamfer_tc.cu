@@ -243,7 +243,9 @@ struct TcPrepParams {
     int N, M, NpA, NpB;
     float4* PA;        // [B][NpA]
     float4* PB;        // [B][NpB]
-    unsigned* maxn;    // [2][B]  max |p'|² per cloud and batch element (float bits; zeroed before the launch)
+    unsigned* maxn;    // [2][B][nblk]  max |p'|² per cloud, batch element and block of this grid (float bits): no atomics, nothing to zero
+    int nblk;          // blocks per cloud and element (gridDim.x)
+    int* hdr;          // the workspace header: zeroed by this grid's first block (the sweep counts only after this grid has ended)
 };
 constexpr int kPrepT = 256, kPrepPts = 4;   // thread <-> four consecutive points: 48 bytes in, 64 bytes out
 __global__ void __launch_bounds__(kPrepT) chamfer_tc_prepare_kernel(TcPrepParams p) {
@@ -253,7 +255,10 @@ __global__ void __launch_bounds__(kPrepT) chamfer_tc_prepare_kernel(TcPrepParams
     const bool isA = blockIdx.z == 0;
     const int n = isA ? p.N : p.M, np = isA ? p.NpA : p.NpB;
     const int i0 = ((int)blockIdx.x * kPrepT + tid) * kPrepPts;
-    if ((int)blockIdx.x * kPrepT * kPrepPts >= np) return;
+    if ((int)blockIdx.x * kPrepT * kPrepPts >= np) {   // (the grid is sized for the larger cloud)
+        if (tid == 0) p.maxn[((size_t)(isA ? 0 : 1) * gridDim.y + b) * p.nblk + blockIdx.x] = 0u;
+        return;
+    }
     const float* gA = p.A + (size_t)b * p.N * 3;
     const float* gB = p.Bp + (size_t)b * p.M * 3;
     // the centre of the batch element: the mean of 32 + 32 strided sample points (any point works — the certificate uses the
@@ -294,8 +299,17 @@ __global__ void __launch_bounds__(kPrepT) chamfer_tc_prepare_kernel(TcPrepParams
         }
         if (i < np) dst[i] = make_float4(x, y, z, nrm);
     }
-    mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));  // norms are >= 0 (NaN bits order above everything: caught by the limit test)
-    if (lane == 0) atomicMax(p.maxn + (size_t)(isA ? 0 : 1) * gridDim.y + b, __float_as_uint(mx));
+    __shared__ unsigned s_mx[kPrepT / 32];
+    const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));  // norms are >= 0 (NaN bits order above everything: caught by the limit test)
+    if (lane == 0) s_mx[tid >> 5] = wm;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid < kHdrInts) p.hdr[tid] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned m = s_mx[0];
+#pragma unroll
+        for (int w = 1; w < kPrepT / 32; ++w) m = max(m, s_mx[w]);
+        p.maxn[((size_t)(isA ? 0 : 1) * gridDim.y + b) * p.nblk + blockIdx.x] = m;
+    }
 }
 
 // ---- host arrays: PCIe reads by the sweep CTAs' own spare warps (f3d_chamfer_pipe_run) --------------------------------------
@@ -347,7 +361,8 @@ struct TcFinParams {
     const float4* PB;
     int B, N, M, NpA, NpB, rbA, rbB, nstA, nstB;
     const float* tilemin;
-    const unsigned* maxn;   // [2][B]
+    const unsigned* maxn;   // [2][B][nblk] (resident inputs: chamfer_tc_prepare_kernel's block maxima)
+    int nblk;
     int32_t* nnA;
     int32_t* nnB;
     double* partial;        // [nitems]       sum of the certified rows' distances of every item
@@ -664,7 +679,9 @@ __global__ void __maxnreg__(kLaunchRegs) chamfer_tc_sweep_kernel(TcSweepParams p
             const bool early = !kRaw;
             if (valid && early) {
                 nq = __ldcg(&((dir ? p.PB : p.PA) + (size_t)b * (dir ? p.NpB : p.NpA) + q)->w);
-                other = __uint_as_float(__ldcg(f.maxn + (size_t)(dir ? 0 : 1) * p.B + b));
+                unsigned om = 0u;
+                for (int kb = 0; kb < f.nblk; ++kb) om = max(om, __ldcg(f.maxn + ((size_t)(dir ? 0 : 1) * p.B + b) * f.nblk + kb));   // (same address in every lane)
+                other = __uint_as_float(om);
                 qx = __ldcg(gQ + 3 * (size_t)q); qy = __ldcg(gQ + 3 * (size_t)q + 1); qz = __ldcg(gQ + 3 * (size_t)q + 2);
             }
             PROF(4);
@@ -1061,7 +1078,7 @@ __global__ void __launch_bounds__(kCleanT, 1) chamfer_tc_cleanup_kernel(TcFinPar
 }
 
 struct TcPlan {
-    int NpA, NpB, rbA, rbB, nstA, nstB, nitems;
+    int NpA, NpB, rbA, rbB, nstA, nstB, nitems, nblk;
     size_t off_PA, off_PB, off_tilemin, off_partial, off_ambcnt, off_ambq, off_amblim, off_amblist, off_ambd, zero_from, off_hdr, off_maxn, off_arrived, zero_bytes, total;
 };
 
@@ -1076,10 +1093,11 @@ TcPlan make_tc_plan(int B, int N, int M) {
     pl.nitems = B * (pl.rbA + pl.rbB);
     size_t o = 0;
     pl.off_hdr = o;     o = align_up(o + sizeof(int) * kHdrInts, 256);   // diagnostics first: a caller can find them
-    pl.off_maxn = o;    o = align_up(o + sizeof(unsigned) * 2 * (size_t)B, 256);
     pl.off_arrived = o; o = align_up(o + sizeof(int) * (size_t)B, 256);   // host arrays: arrived [B]
     pl.zero_from = 0;
-    pl.zero_bytes = o;  // header, norm maxima and arrival counters are zeroed by ONE memset per call
+    pl.zero_bytes = o;  // host arrays only: header and arrival counters are zeroed by ONE memset per call (resident inputs: by the prepare grid)
+    pl.nblk = (std::max(pl.NpA, pl.NpB) + kPrepT * kPrepPts - 1) / (kPrepT * kPrepPts);
+    pl.off_maxn = o;    o = align_up(o + sizeof(unsigned) * 2 * (size_t)B * pl.nblk, 256);
     pl.off_PA = o;      o = align_up(o + sizeof(float4) * (size_t)B * pl.NpA, 256);
     pl.off_PB = o;      o = align_up(o + sizeof(float4) * (size_t)B * pl.NpB, 256);
     pl.off_tilemin = o; o = align_up(o + sizeof(float) * kParts * (size_t)B * ((size_t)pl.nstB * pl.NpA + (size_t)pl.nstA * pl.NpB), 256);
@@ -1142,26 +1160,28 @@ int32_t chamfer_tc_launch(const float* A, const float* Bp, int32_t B, int32_t N,
         if (dev >= 0 && dev < 256) { sm_count[dev] = sms; attr_done[dev] = 1; }
     }
     const int sms = (dev >= 0 && dev < 256 && sm_count[dev] > 0) ? sm_count[dev] : 148;
-    F3D_CUDA(cudaMemsetAsync(w + pl.zero_from, 0, pl.zero_bytes, stream));
+    if (upload) F3D_CUDA(cudaMemsetAsync(w + pl.zero_from, 0, pl.zero_bytes, stream));   // (resident inputs: the prepare grid zeroes the header — no memset node in the step)
 
     TcPrepParams pp;
     pp.A = A; pp.Bp = Bp; pp.N = N; pp.M = M; pp.NpA = pl.NpA; pp.NpB = pl.NpB;
     pp.PA = reinterpret_cast<float4*>(w + pl.off_PA);
     pp.PB = reinterpret_cast<float4*>(w + pl.off_PB);
     pp.maxn = reinterpret_cast<unsigned*>(w + pl.off_maxn);
+    pp.nblk = pl.nblk;
+    pp.hdr = reinterpret_cast<int*>(w + pl.off_hdr);
     // Host arrays (upload): A / Bp are staging buffers; the sweep's own spare warps fill them over PCIe — no prepare grid, the
     // converters centre the raw points and take the norms on the fly
     if (upload && ((long long)B * N * 3 >= 0x7fffffffLL || (long long)B * M * 3 >= 0x7fffffffLL))
         return fail(F3D_ERR_INVALID, "chamfer_tc_launch: batch too large for the in-grid upload");
     if (!upload) {
-        chamfer_tc_prepare_kernel<<<dim3((std::max(pl.NpA, pl.NpB) + kPrepT * kPrepPts - 1) / (kPrepT * kPrepPts), B, 2), kPrepT, 0, stream>>>(pp);
+        chamfer_tc_prepare_kernel<<<dim3(pl.nblk, B, 2), kPrepT, 0, stream>>>(pp);
         F3D_CHECK_LAUNCH("chamfer_tc_prepare_kernel");
     }
 
     TcFinParams fp;
     fp.A = A; fp.Bp = Bp; fp.PA = pp.PA; fp.PB = pp.PB;
     fp.B = B; fp.N = N; fp.M = M; fp.NpA = pl.NpA; fp.NpB = pl.NpB; fp.rbA = pl.rbA; fp.rbB = pl.rbB; fp.nstA = pl.nstA; fp.nstB = pl.nstB;
-    fp.tilemin = reinterpret_cast<float*>(w + pl.off_tilemin); fp.maxn = pp.maxn;
+    fp.tilemin = reinterpret_cast<float*>(w + pl.off_tilemin); fp.maxn = pp.maxn; fp.nblk = pl.nblk;
     fp.nnA = nnA_dev; fp.nnB = nnB_dev;
     fp.partial = reinterpret_cast<double*>(w + pl.off_partial);
     fp.ambcnt = reinterpret_cast<int*>(w + pl.off_ambcnt);
