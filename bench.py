@@ -472,7 +472,7 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": pairs_step * steps / r["e2e_s"], "unit": "pairs/s", "h2d_bytes_per_step": r["h2d"],
                     "d2h_bytes_per_step": 4, "ms_per_step": r["e2e_s"] / steps * 1e3},
-            # kernels of this library per device-timed step: operand preparation, tensor-core sweep (certifies in-CTA), cleanup (+ 1 memset
+            # kernels of this library per device-timed step: operand preparation, tensor-core sweep (certifies in-CTA), cleanup (no memset
             # node); the CUDA-core path (small problems): sweep + finalize
             "gpu_launches": (3 if tensor_path else 2) * steps,
             "roofline": roofline,
