@@ -6,7 +6,7 @@
 // reported index and distance is evaluated in the reference arithmetic (sequential s = s + (a_d - b_d)²); the tensor cores
 // only decide WHICH ~35 of the N candidates of a query are worth evaluating.
 //
-// knn_gram_prepare_kernel writes the cloud once as an OPERAND IMAGE: 256-point tiles, rows of 128 bytes in the canonical
+// knn_gram_prepare_{split,plain}_kernel write the cloud once as an OPERAND IMAGE: 256-point tiles, rows of 128 bytes in the canonical
 // K-major SWIZZLE_128B layout — byte for byte what a tcgen05.mma wants to find in shared memory, so that a tile (32 KB per
 // 32 features) travels with ONE cp.async.bulk — plus the squared norms.  Two row formats:
 //   plain  (5 <= F <= 64)  the FP32 features; kind::tf32 reads their upper 19 bits: |g~ - g| <= 2^-8 |q||c|
@@ -52,7 +52,6 @@ struct KnnGramParams {
     int Np, ntiles, halves, ksteps, split, fold;
     unsigned char* img;        // [B][ntiles][halves][256][128 B]
     float* nrm;                // [B][Np]   squared norms (+inf past N)
-    float* tmax;               // [B][ntiles] largest squared norm of every tile (the search takes the maximum over a cloud's tiles)
     int32_t* idx;              // [B][N][K]
     float* dist;               // [B][N][K] or null
     unsigned* stats;           // [0] rows redone by the exact scan, [1] candidates re-evaluated exactly, [3..5] why, [7] = 2: this path served the call
@@ -162,58 +161,54 @@ __device__ __forceinline__ float split_row(const float* x, bool live, bool fold,
     return n;
 }
 
-// ---- prepare: the operand image + norms; grid (ntiles, B), thread <-> row of the tile --------------------------------------
-__global__ void __launch_bounds__(kGN) knn_gram_prepare_kernel(KnnGramParams p) {
+// ---- prepare: the operand image + norms -----------------------------------------------------------------------------------
+// split rows (F <= 4): grid (ntiles, B), thread <-> row of the tile (three loads, eight 16-byte stores)
+__global__ void __launch_bounds__(kGN) knn_gram_prepare_split_kernel(KnnGramParams p) {
     const int t = blockIdx.x, b = blockIdx.y, r = threadIdx.x, j = t * kGN + r;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the search grid may set itself up (it waits for this grid's end)
-    unsigned char* tile = p.img + ((size_t)(b * p.ntiles + t) * p.halves) * kGHalf;
+    unsigned char* tile = p.img + (size_t)(b * p.ntiles + t) * kGHalf;
     const float* x = p.X + ((size_t)b * p.N + min(j, p.N - 1)) * p.F;
     const bool live = j < p.N;
     float n = 0.0f;
-    if (p.split) {
-        float row[32];
-        switch (p.F) {
-            case 1: n = split_row<1>(x, live, p.fold != 0, row); break;
-            case 2: n = split_row<2>(x, live, p.fold != 0, row); break;
-            case 3: n = split_row<3>(x, live, p.fold != 0, row); break;
-            default: n = split_row<4>(x, live, p.fold != 0, row); break;
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4*>(tile + swz(r, c)) = make_float4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
-    } else {
-        const bool vec = (p.F & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0;
-        for (int h = 0; h < p.halves; ++h)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int d0 = h * 32 + c * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (live && d0 < p.F) {
-                    if (vec) v = __ldg(reinterpret_cast<const float4*>(x + d0));
-                    else {
-                        v.x = __ldg(x + d0);
-                        if (d0 + 1 < p.F) v.y = __ldg(x + d0 + 1);
-                        if (d0 + 2 < p.F) v.z = __ldg(x + d0 + 2);
-                        if (d0 + 3 < p.F) v.w = __ldg(x + d0 + 3);
-                    }
-                    n += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;   // any rounding will do: the norm only enters the filter
-                }
-                *reinterpret_cast<float4*>(tile + (size_t)h * kGHalf + swz(r, c)) = v;
-            }
+    float row[32];
+    switch (p.F) {
+        case 1: n = split_row<1>(x, live, p.fold != 0, row); break;
+        case 2: n = split_row<2>(x, live, p.fold != 0, row); break;
+        case 3: n = split_row<3>(x, live, p.fold != 0, row); break;
+        default: n = split_row<4>(x, live, p.fold != 0, row); break;
     }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(tile + swz(r, c)) = make_float4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
     if (t == 0 && b == 0 && r < 8) p.stats[r] = r == 7 ? 2u : 0u;   // diagnostics (the search grid only counts after this grid has ended); [7]: this path served the call
     p.nrm[(size_t)b * p.Np + j] = live ? n : INFINITY;
-    __shared__ float s_m[kGN / 32];
-    float m = live ? n : 0.0f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((r & 31) == 0) s_m[r >> 5] = m;
-    __syncthreads();
-    if (r == 0) {
-#pragma unroll
-        for (int w = 1; w < kGN / 32; ++w) m = fmaxf(m, s_m[w]);
-        p.tmax[(size_t)b * p.ntiles + t] = m;   // no atomics, nothing to zero: the call needs no memset
+}
+// plain rows (5 <= F <= 64): thread <-> (row, 16-byte chunk) — 8 or 16 threads per row, 32 or 16 rows per block: every load and
+// every store is one 16-byte access of a coalesced run, and a cfg3-sized call is 4096 blocks instead of 128
+__global__ void __launch_bounds__(256) knn_gram_prepare_plain_kernel(KnnGramParams p) {
+    const int cpr = 8 * p.halves, rpb = 256 / cpr, bpt = kGN / rpb;     // chunks per row, rows per block, blocks per tile
+    const int t = blockIdx.x / bpt, rb = blockIdx.x - t * bpt, b = blockIdx.y;
+    const int c = threadIdx.x % cpr, r = rb * rpb + threadIdx.x / cpr, j = t * kGN + r;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    unsigned char* tile = p.img + ((size_t)(b * p.ntiles + t) * p.halves) * kGHalf;
+    const float* x = p.X + ((size_t)b * p.N + min(j, p.N - 1)) * p.F;
+    const bool live = j < p.N, vec = (p.F & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0;
+    const int d0 = c * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live && d0 < p.F) {
+        if (vec) v = __ldg(reinterpret_cast<const float4*>(x + d0));
+        else {
+            v.x = __ldg(x + d0);
+            if (d0 + 1 < p.F) v.y = __ldg(x + d0 + 1);
+            if (d0 + 2 < p.F) v.z = __ldg(x + d0 + 2);
+            if (d0 + 3 < p.F) v.w = __ldg(x + d0 + 3);
+        }
     }
+    *reinterpret_cast<float4*>(tile + (size_t)(c >> 3) * kGHalf + swz(r, c & 7)) = v;
+    float n = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;   // any rounding will do: the norm only enters the filter
+    for (int o = cpr >> 1; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);   // (the threads of a row are cpr consecutive lanes)
+    if (blockIdx.x == 0 && b == 0 && threadIdx.x < 8) p.stats[threadIdx.x] = threadIdx.x == 7 ? 2u : 0u;
+    if (c == 0) p.nrm[(size_t)b * p.Np + j] = live ? n : INFINITY;
 }
 
 // exact (reference-arithmetic) squared distance between row r of the query tile and row c of a candidate tile, both in
@@ -324,6 +319,7 @@ __global__ void __launch_bounds__(kGThreads, 1) knn_gram_kernel(KnnGramParams p)
     __shared__ unsigned long long a_full, full_b[2], empty_b[2], tfull[2], tempty[2], s_key[2][8];
     __shared__ unsigned s_tmem;
     __shared__ int s_nfix;
+    __shared__ unsigned s_wmax[kGReadWarps + 1];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, q0 = blockIdx.x * kGQ;
@@ -339,7 +335,16 @@ __global__ void __launch_bounds__(kGThreads, 1) knn_gram_kernel(KnnGramParams p)
     if (tid < kGReadWarps) s_segcnt[tid] = 0;
     if (tid == 0) s_nfix = 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");   // launched programmatically behind the prepare grid: the image is complete
-    for (int i = tid; i < p.Np; i += kGThreads) s_nc[i] = __ldcg(p.nrm + (size_t)b * p.Np + i);
+    {   // the cloud's norms, and their maximum (padding is +inf) for the filter's error bound
+        float lm = 0.0f;
+        for (int i = tid; i < p.Np; i += kGThreads) {
+            const float v = __ldcg(p.nrm + (size_t)b * p.Np + i);
+            s_nc[i] = v;
+            if (v < INFINITY) lm = fmaxf(lm, v);
+        }
+        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(lm));   // norms are >= 0: bit order == value order
+        if (lane == 0) s_wmax[warp] = wm;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -410,8 +415,10 @@ __global__ void __launch_bounds__(kGThreads, 1) knn_gram_kernel(KnnGramParams p)
                         if (a <= bb) { Tsel = a; ++ia; } else { Tsel = bb; ++ib; }
                     }
                     const float nq = s_nc[min(q0 + row, p.Np - 1)];
-                    float maxnc = 0.0f;
-                    for (int tt = 0; tt < ntiles; ++tt) maxnc = fmaxf(maxnc, __ldcg(p.tmax + (size_t)b * ntiles + tt));
+                    unsigned mb = 0u;
+#pragma unroll
+                    for (int w = 0; w <= kGReadWarps; ++w) mb = max(mb, s_wmax[w]);
+                    const float maxnc = __uint_as_float(mb);
                     // E bounds |d' - (d - nq)|: the Gram entry's relative error on |q||c| plus the FP32 roundings of the norms and of the
                     // fma, which do not shrink with |q| (<= (F + 3) u (nq + max nc), doubled for slack)
                     const float E = (p.split ? kGErrSplit : kGErrPlain) * sqrtf(nq) * sqrtf(maxnc) + 2.0f * (float)(p.F + 4) * 5.9604645e-8f * (nq + maxnc);
@@ -601,7 +608,7 @@ __global__ void __launch_bounds__(kGThreads, 1) knn_gram_kernel(KnnGramParams p)
 
 struct GramPlan {
     int Np, ntiles, halves, ksteps, split, fold;
-    size_t off_stats, off_tmax, off_nrm, off_img, total;
+    size_t off_stats, off_nrm, off_img, total;
 };
 GramPlan make_gram_plan(int B, int N, int F) {
     GramPlan pl;
@@ -613,7 +620,6 @@ GramPlan make_gram_plan(int B, int N, int F) {
     pl.ksteps = pl.split ? 2 : (F + 7) / 8;
     size_t o = 0;
     pl.off_stats = o; o = align_up(o + 64, 256);
-    pl.off_tmax = o;  o = align_up(o + sizeof(float) * (size_t)B * pl.ntiles, 256);
     pl.off_nrm = o;   o = align_up(o + sizeof(float) * (size_t)B * pl.Np, 1024);
     pl.off_img = o;   o = align_up(o + (size_t)B * pl.ntiles * pl.halves * kGHalf, 256);
     pl.total = o;
@@ -643,7 +649,6 @@ int32_t knn_gram_launch(const float* X, int B, int N, int F, int K, int32_t* idx
     p.Np = pl.Np; p.ntiles = pl.ntiles; p.halves = pl.halves; p.ksteps = pl.ksteps; p.split = pl.split; p.fold = pl.fold;
     p.img = w + pl.off_img;
     p.nrm = reinterpret_cast<float*>(w + pl.off_nrm);
-    p.tmax = reinterpret_cast<float*>(w + pl.off_tmax);
     p.idx = idx; p.dist = dist;
     p.stats = reinterpret_cast<unsigned*>(w + pl.off_stats);
     const size_t smem = gram_smem_bytes(pl.halves);
@@ -652,7 +657,8 @@ int32_t knn_gram_launch(const float* X, int B, int N, int F, int K, int32_t* idx
         F3D_CUDA(cudaFuncSetAttribute(knn_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_smem_bytes(2)));
         attr_done[0] = attr_done[1] = true;
     }
-    knn_gram_prepare_kernel<<<dim3(pl.ntiles, B), kGN, 0, stream>>>(p);
+    if (pl.split) knn_gram_prepare_split_kernel<<<dim3(pl.ntiles, B), kGN, 0, stream>>>(p);
+    else knn_gram_prepare_plain_kernel<<<dim3(pl.ntiles * pl.halves * 8, B), 256, 0, stream>>>(p);   // blocks per tile = 256 rows / (256 / (8 halves)) rows per block
     F3D_CHECK_LAUNCH("knn_gram_prepare_kernel");
     {
         cudaLaunchConfig_t cfg = {};
