@@ -542,9 +542,6 @@ extern "C" int32_t f3d_knn_graph(const float* X, int32_t B, int32_t N, int32_t F
     p.idx = idx; p.dist = dist; p.gathered = gathered; p.edge = edge_feat;
     // narrow features (F <= 8: 16 + 1024 rows of <= 48 bytes = 49 KB): the whole selection block fits in shared memory
     p.stage_block = p.Fp <= 8 ? 1 : 0;
-#ifdef F3D_EXP_KNN_TILE_STAGING
-    p.stage_block = 0;
-#endif
     const size_t smem = knn_smem_bytes(p.Fp, p.stage_block != 0);
     dim3 grid((N + kQPC - 1) / kQPC, B);
     if (K + 1 <= 32) {

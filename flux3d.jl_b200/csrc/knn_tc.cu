@@ -239,9 +239,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(KnnTcParams p) {
     }
     // The tile sequence is pass 1 (tiles 0..ntiles-1) followed by pass 2 (the same tiles again): L steps, software-
     // pipelined — step s: [cp.async tile s+2] | norms + MMA of tile s | read-out (TMEM) of tile s-1.
-#ifdef F3D_EXP_CLOCK
-    long long tk0 = clock64();
-#endif
     const int L = 2 * ntiles;
     stage(s_a, kTQ, q0, true);                      // group 0: A (it is waited for together with step 0)
     for (int u = 0; u < 3; ++u) {                   // groups 1..3: sequence steps 0, 1, 2 (all three B buffers are free)
@@ -249,12 +246,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(KnnTcParams p) {
         else asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
-#ifdef F3D_EXP_CLOCK
-    long long pa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
-#define PK(i) do { long long n_ = clock64(); pa[i] += n_ - pt; pt = n_; } while (0)
-#else
-#define PK(i)
-#endif
     float thr = 0.0f, nq = 0.0f;
     unsigned tmem = 0;
     unsigned phbits = 0u;  // phase parity of the two mbarriers (bit u & 1)
@@ -263,17 +254,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(KnnTcParams p) {
         mbar_wait(&s_bar[u & 1], (phbits >> (u & 1)) & 1u);
         phbits ^= 1u << (u & 1);
         tc_fence_after();
-        PK(3);
         // the B buffer of step u is free again: start staging sequence step u + 3
         if (u + 3 < L) stage(s_b + (size_t)((u + 3) % 3) * b_tile, kTN, ((u + 3) % ntiles) * kTN, false);
         else asm volatile("cp.async.commit_group;" ::: "memory");   // keep the group count uniform
-        PK(4);
         if (is_mma) return;
         const int t = u % ntiles;
         const float* nc = s_nc + t * kTN;
         float v[32];
         tmem_ld32(tmem + ((unsigned)(quad * 32) << 16) + (unsigned)((u & 1) * kTN + qtr * 32), v);
-        PK(5);
         if (u < ntiles) {  // pass 1: the two smallest d~ of this thread's 32-column group
             float m1 = INFINITY, m2 = INFINITY;
 #pragma unroll
@@ -347,9 +335,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(KnnTcParams p) {
     tc_fence_before();
     __syncthreads();  // all TMEM reads and MMAs are done; the B region may be reused
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 2 * kTN); }
-#ifdef F3D_EXP_CLOCK
-    long long tk1 = clock64();
-#endif
 
     // ---- exact re-evaluation + ordered selection ----------------------------------------------------------------
     const int qi = q0 + row;
@@ -418,9 +403,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(KnnTcParams p) {
         ncand = 128;
     }
     __syncthreads();
-#ifdef F3D_EXP_CLOCK
-    long long tk2 = clock64();
-#endif
     if (!live) return;
     // every candidate finds its rank in the ascending (distance, index) order by counting; ranks 1..K are the
     // neighbours, rank 0 is dropped by position (dgcnn.jl:6)
@@ -440,9 +422,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(KnnTcParams p) {
             if (p.dist) p.dist[obase + rank - 1] = d;
         }
     }
-#ifdef F3D_EXP_CLOCK
-    if (p.stats && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { long long tk3 = clock64(); p.stats[4] = (unsigned)(tk1 - tk0); p.stats[5] = (unsigned)(tk2 - tk1); p.stats[6] = (unsigned)(tk3 - tk2); for (int i = 0; i < 7; ++i) p.stats[8 + i] = (unsigned)pa[i]; }
-#endif
 }
 
 // gathered (F,K,N,B) and edge features (2F,K,N,B) from the neighbour indices: pure data movement.  One CTA per point
