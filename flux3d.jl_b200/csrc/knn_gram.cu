@@ -551,6 +551,7 @@ __global__ void __launch_bounds__(kGThreads, 1) knn_gram_kernel(KnnGramParams p)
                 // are >= 0, bit order == value order); one pass over all the row's candidates counts the keys below each of them
                 const size_t obase = ((size_t)b * p.N + qi) * p.K;
                 if (cmax <= 32) rank_row<8>(s_dex, s_cand, row, part, cnt, p.K, p.idx + obase, p.dist ? p.dist + obase : nullptr);
+                else if (cmax <= 40) rank_row<10>(s_dex, s_cand, row, part, cnt, p.K, p.idx + obase, p.dist ? p.dist + obase : nullptr);
                 else if (cmax <= 48) rank_row<12>(s_dex, s_cand, row, part, cnt, p.K, p.idx + obase, p.dist ? p.dist + obase : nullptr);
                 else rank_row<16>(s_dex, s_cand, row, part, cnt, p.K, p.idx + obase, p.dist ? p.dist + obase : nullptr);
             }
