@@ -281,10 +281,17 @@ __device__ __forceinline__ void rank_row(const float* s_dex, const unsigned shor
     }
 #pragma unroll 2
     for (int o = 0; o < cnt; ++o) {
-        const unsigned long long ok = ((unsigned long long)__float_as_uint(s_dex[o * kGQ + row]) << 32) | s_cand[o * kGQ + row];
+        const unsigned okh = __float_as_uint(s_dex[o * kGQ + row]), okl = s_cand[o * kGQ + row];
+        // counts the keys NOT below the own key as the (absent) borrow of a 64-bit subtraction other - own — three instructions of one
+        // subtract-with-borrow chain per pair, no compare / select: n += 1 - borrow  (n - (-1 + borrow))
 #pragma unroll
-        for (int e = 0; e < S; ++e) rank[e] += ok < key[e] ? 1 : 0;
+        for (int e = 0; e < S; ++e)
+            asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %3;\n\tsubc.cc.u32 t, %2, %4;\n\tsubc.u32 %0, %0, 0xffffffff;\n\t}"
+                : "+r"(rank[e])
+                : "r"(okl), "r"(okh), "r"((unsigned)(key[e] & 0xffffffffu)), "r"((unsigned)(key[e] >> 32)));
     }
+#pragma unroll
+    for (int e = 0; e < S; ++e) rank[e] = cnt - rank[e];   // keys below the own key
 #pragma unroll
     for (int e = 0; e < S; ++e)
         if (part + 4 * e < cnt && rank[e] >= 1 && rank[e] <= K) {
