@@ -20,13 +20,15 @@ checked    BOTH losses (device-resident and end to end) are compared with the re
 roofline   the dominant kernel (chamfer_tc_sweep_kernel: the filter sweep as a split-TF32 GEMM on the tensor cores) timed alone,
            live, with CUDA events on its launch stream (F3D_FLAG_SWEEP_ONLY; includes the 3 us operand-preparation grid in front
            of it).  bound = tensor: achieved = EXECUTED tensor FLOPs (2 directions x K=16 x 2 = 64 FLOP per pair) / t against
-           the measured dense bf16 GEMM rate / 2 (TF32 runs at half the bf16 rate).  Beside it: the TMEM read-out roof that
-           actually binds the design (8 accumulator bytes per pair against the measured tcgen05.ld rate), the FP32-issue
+           the measured dense bf16 GEMM rate / 2 (TF32 runs at half the bf16 rate).  Beside it: the TMEM read-out roof
+           (8 accumulator bytes per pair against the measured tcgen05.ld rate; what binds the kernel is the ALU pipe that takes the
+           minima of those bytes: ncu 73-77 % active, profiles/r02o_chamfer_tc_ncu_full_*.csv), the FP32-issue
            convention of SURVEY §8d (8 lane-instructions per pair; what round 1 reported), and the HBM view BASELINE.json asks for.
 cpu_baseline  the reference's CPU algorithm restated with scipy's cKDTree, 1 thread, on this box's host cores.
 ops        (N=1 only, outside the headline timed region, same process and clocks) the other BASELINE configs: kNN graph cfg3
            (F=3 and F=64; indices only and with the edge features in the MLP layout), sample_points / laplacian_loss /
-           compute_verts_normals_packed at cfg4, each with the CPU port timed beside it.
+           compute_verts_normals_packed / edge_loss at cfg4, each with the CPU port timed beside it; the fit_mesh step (forward +
+           pullbacks) op by op and as one CUDA-graph launch; the chamfer pullback at cfg2.
 cfg5       (N>1) a sub-record for BASELINE configs[4] (B=32 per GPU, N=M=8192): step time with the cross-rank sum, the same
            shard without any exchange (= the single-GPU time), their ratio, and the loss checked against the CPU port.
 
