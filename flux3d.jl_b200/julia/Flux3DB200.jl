@@ -296,20 +296,33 @@ end
 # sample_points — src/transforms/mesh_func.jl:21-58: one launch for the whole batch, device RNG (Philox).  The padded verts
 # stay on the Zygote tape (get_verts_padded); the array-level function carries the adjoint (the face draws are constants,
 # :47 is @ignore): gverts[:, faces[k, face_s], mesh] += w_k * gsamples[:, s, mesh].
+# `counter` (a 1-element CuVector{UInt64}): the draw counter lives on the device — its value is added to `offset` when the kernel
+# runs and it is bumped after the draws, so a step recorded with CUDA.capture draws fresh samples at every replay (the reference's
+# fit_mesh samples anew in every iteration, examples/fit_mesh.jl:78-84).
 function _sample_points_dev(verts::CuArray{Float32,3}, faces::CuArray{Int32,3}, vlen::CuVector{Int32}, flen::CuVector{Int32},
-                            num_samples::Int, eps::Float64, seed::UInt64, offset::UInt64; want_aux::Bool = false)
+                            num_samples::Int, eps::Float64, seed::UInt64, offset::UInt64; want_aux::Bool = false,
+                            counter::Union{Nothing,CuVector{UInt64}} = nothing)
     (_, V, Nm) = size(verts); F = size(faces, 2)
     samples = similar(verts, 3, num_samples, Nm)
     fidx = want_aux ? CuArray{Int32}(undef, num_samples, Nm) : nothing
     bary = want_aux ? CuArray{Float32}(undef, 3, num_samples, Nm) : nothing
     nws = ccall((:f3d_sample_points_workspace_bytes, LIB), Csize_t, (Int32, Int32), Nm, F)
     ws = workspace((:sample, Nm, F), nws)
-    check(ccall((:f3d_sample_points, LIB), Int32,
-        (Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Int32, Int32, Int32, Float64, UInt64, UInt64,
-         Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
-        devptr(verts), devptr(faces), devptr(vlen), devptr(flen), Nm, V, F, num_samples, eps, seed, offset,
-        C_NULL, C_NULL, C_NULL, devptr(samples), want_aux ? devptr(fidx) : C_NULL, want_aux ? devptr(bary) : C_NULL,
-        devptr(ws), length(ws), cur_stream()))
+    if counter === nothing
+        check(ccall((:f3d_sample_points, LIB), Int32,
+            (Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Int32, Int32, Int32, Float64, UInt64, UInt64,
+             Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+            devptr(verts), devptr(faces), devptr(vlen), devptr(flen), Nm, V, F, num_samples, eps, seed, offset,
+            C_NULL, C_NULL, C_NULL, devptr(samples), want_aux ? devptr(fidx) : C_NULL, want_aux ? devptr(bary) : C_NULL,
+            devptr(ws), length(ws), cur_stream()))
+    else
+        check(ccall((:f3d_sample_points_replayable, LIB), Int32,
+            (Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Int32, Int32, Int32, Float64, UInt64, UInt64, Ptr{UInt64},
+             Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+            devptr(verts), devptr(faces), devptr(vlen), devptr(flen), Nm, V, F, num_samples, eps, seed, offset, devptr(counter),
+            C_NULL, C_NULL, C_NULL, devptr(samples), want_aux ? devptr(fidx) : C_NULL, want_aux ? devptr(bary) : C_NULL,
+            devptr(ws), length(ws), cur_stream()))
+    end
     return samples, fidx, bary
 end
 Zygote.@adjoint function _sample_points_dev(verts::CuArray{Float32,3}, faces::CuArray{Int32,3}, vlen::CuVector{Int32}, flen::CuVector{Int32},

@@ -132,8 +132,7 @@ def test_shim_binds_what_the_integration_table_lists():
     listed = set(re.findall(r"`(f3d_\w+)`", doc))
     protos = header_prototypes()
     assert listed <= set(protos), f"INTEGRATION.md names symbols the header does not declare: {sorted(listed - set(protos))}"
-    julia_side = listed - {"f3d_version", "f3d_comm_unique_id_host", "f3d_allreduce_sum_f32", "f3d_comm_destroy", "f3d_chamfer_pipe_destroy",
-                           "f3d_sample_points_replayable"}
+    julia_side = listed - {"f3d_version", "f3d_comm_unique_id_host", "f3d_allreduce_sum_f32", "f3d_comm_destroy", "f3d_chamfer_pipe_destroy"}
     assert julia_side <= bound, f"INTEGRATION.md lists bindings the shim does not make: {sorted(julia_side - bound)}"
     for needle in ("Flux3D._chamfer_distance(A::CuArray", "Zygote.@adjoint function Flux3D._chamfer_distance", "Flux3D._nearest_neighbors(x::CuArray",
                    "Flux3D.CreateSingleKNNGraph(X::CuArray", "(m::Flux3D.EdgeConv)(X::CuArray", "Flux3D.laplacian_loss(m::TriMesh{Float32,R,CuArray})",
