@@ -14,8 +14,8 @@ L.f3d_debug_read_tc.argtypes = [C.c_void_p, C.c_size_t]
 assert L.f3d_debug_read_tc(buf.ctypes.data, buf.nbytes) == 0
 p = buf.reshape(148, 16).astype(np.float64)
 names = ["mma: wait a_full", "mma: wait full_b (converter)", "mma: wait tempty[0] (read-out r0)", "mma: wait tempty[1] (read-out r1)", "mma: issue+commit",
-         "conv: wait cfull (TMA)", "conv: wait empty_b (MMA)", "conv: convert+store+fence", "epi r0: wait tfull (MMA)", "epi r0: read-out", "epi r0: between tiles",
-         "epi r1: wait tfull (MMA)", "epi r1: read-out", "epi r1: between tiles"]
+         "conv: wait cfull (TMA)", "conv: wait empty_b (MMA)", "conv: convert+store+fence", "read-out warp 0: wait tfull (MMA)", "read-out warp 0: read-out", "read-out warp 0: between tiles",
+         "read-out warp 8: wait tfull (MMA)", "read-out warp 8: read-out", "read-out warp 8: between tiles"]
 tiles = (B * (N + M) // 256) * (M // 256) / 148.0
 print(f"{B}x{N}x{M}: ~{tiles:.0f} candidate tiles per CTA; cycles per tile (mean over CTAs):")
 for i, n in enumerate(names):
